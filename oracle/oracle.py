@@ -1,0 +1,187 @@
+"""ctypes wrapper around the CPU oracle (oracle/saige_oracle.cpp).
+
+TEST INFRASTRUCTURE: import only from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package (saigegds_b200) never imports this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_build", "libsaige_oracle.so")
+
+
+class OrcParams(C.Structure):
+    _fields_ = [("tol", C.c_double), ("tolPCG", C.c_double), ("seed", C.c_int), ("maxiter", C.c_int),
+                ("maxiterPCG", C.c_int), ("no_iteration", C.c_int), ("nrun", C.c_int), ("num_marker", C.c_int),
+                ("traceCVcutoff", C.c_double), ("ratioCVcutoff", C.c_double), ("verbose", C.c_int)]
+
+
+def default_params(**kw) -> OrcParams:
+    """Defaults of seqFitNullGLMM_SPA (R/saige_main.r:223-229)."""
+    d = dict(tol=0.02, tolPCG=1e-5, seed=200, maxiter=20, maxiterPCG=500, no_iteration=0, nrun=30,
+             num_marker=30, traceCVcutoff=0.0025, ratioCVcutoff=0.001, verbose=0)
+    d.update(kw)
+    return OrcParams(**d)
+
+
+def build(force=False):
+    if force or not os.path.exists(LIB_PATH) or \
+            os.path.getmtime(LIB_PATH) < os.path.getmtime(os.path.join(HERE, "saige_oracle.cpp")):
+        subprocess.check_call(["make", "-C", HERE, "-s"])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.orc_create.restype = C.c_void_p
+        _lib.orc_last_error.restype = C.c_char_p
+        for f in ("orc_num_products", "orc_num_pcg", "orc_num_pcg_iter"):
+            getattr(_lib, f).restype = C.c_long
+    return _lib
+
+
+def _p(a, t=C.c_double):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+FAMILY = {"binomial": 0, "gaussian": 1}
+
+
+class Oracle:
+    def __init__(self):
+        self.h = C.c_void_p(lib().orc_create())
+        self.n = self.m = 0
+
+    def __del__(self):
+        try:
+            lib().orc_destroy(self.h)
+        except Exception:
+            pass
+
+    def store_2b_geno(self, packed: np.ndarray, n_samp: int, num_thread: int = 1):
+        """packed: [M][ceil(N/4)] uint8 (one row per variant == R RawMatrix column)."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        m, nb = packed.shape
+        self.n, self.m = int(n_samp), int(m)
+        lut = np.empty(4 * m)
+        diag = np.empty(self.n)
+        lib().orc_store_2b_geno(self.h, _p(packed, C.c_ubyte), C.c_long(self.n), C.c_long(nb), C.c_long(m),
+                                C.c_int(num_thread), _p(lut), _p(diag))
+        return lut.reshape(m, 4), diag
+
+    def allele_counts(self):
+        nv = np.empty(self.m, dtype=np.int32)
+        sm = np.empty(self.m, dtype=np.int32)
+        lib().orc_allele_counts(self.h, _p(nv, C.c_int), _p(sm, C.c_int))
+        return nv, sm
+
+    def get_geno_ds(self, snp_idx: int):
+        ds = np.empty(self.n)
+        lib().orc_get_geno_ds(self.h, C.c_long(snp_idx), _p(ds))
+        return ds
+
+    def grm_mv(self, b):
+        b = _f64(b)
+        out = np.empty(self.n)
+        lib().orc_grm_mv(self.h, _p(b), _p(out))
+        return out
+
+    def diag_sigma(self, w, tau):
+        w, tau = _f64(w), _f64(tau)
+        out = np.empty(self.n)
+        lib().orc_diag_sigma(self.h, _p(w), _p(tau), _p(out))
+        return out
+
+    def pcg(self, w, tau, b, maxiterPCG=500, tolPCG=1e-5):
+        w, tau, b = _f64(w), _f64(tau), _f64(b)
+        x = np.empty(self.n)
+        it = C.c_int(0)
+        lib().orc_pcg(self.h, _p(w), _p(tau), _p(b), C.c_int(maxiterPCG), C.c_double(tolPCG), _p(x), C.byref(it))
+        return x, it.value
+
+    # ---- R RNG ----
+    def set_seed(self, seed):
+        lib().orc_set_seed(self.h, C.c_uint(seed))
+
+    def unif_rand(self, n):
+        out = np.empty(n)
+        lib().orc_unif_rand(self.h, C.c_long(n), _p(out))
+        return out
+
+    def rademacher(self, n):
+        out = np.empty(n)
+        lib().orc_rademacher(self.h, C.c_long(n), _p(out))
+        return out
+
+    def sample_int(self, n):
+        out = np.empty(n, dtype=np.int32)
+        lib().orc_sample_int(self.h, C.c_int(n), _p(out, C.c_int))
+        return out
+
+    # ---- drivers ----
+    def fit_AI_PCG(self, trait, fit0, X, tau, params=None):
+        """saige_fit_AI_PCG_binary / _quant.  fit0: saigegds_b200.rsetup.Fit0-like."""
+        params = params or default_params()
+        X = np.asfortranarray(X, dtype=np.float64)
+        n, p = X.shape
+        y = _f64(fit0.y)
+        off = None if fit0.offset is None else _f64(fit0.offset)
+        eta, mu, coef, tau = _f64(fit0.linear_predictors), _f64(fit0.fitted_values), _f64(fit0.coefficients), _f64(tau)
+        o = dict(coefficients=np.empty(p), tau=np.empty(2), linear_predictors=np.empty(n), fitted_values=np.empty(n),
+                 residuals=np.empty(n), cov=np.empty((p, p), order="F"))
+        conv = C.c_int(0)
+        rc = lib().orc_fit_AI_PCG(self.h, C.c_int(1 if trait == "quantitative" else 0), C.c_int(FAMILY[fit0.family]),
+                                  C.c_long(n), C.c_int(p), _p(y), _p(off) if off is not None else None, _p(eta), _p(mu),
+                                  _p(coef), _p(X), _p(tau), C.byref(params), _p(o["coefficients"]), _p(o["tau"]),
+                                  _p(o["linear_predictors"]), _p(o["fitted_values"]), _p(o["residuals"]), _p(o["cov"]),
+                                  C.byref(conv))
+        if rc != 0:
+            raise RuntimeError(lib().orc_last_error(self.h).decode())
+        o["converged"] = bool(conv.value)
+        return o
+
+    def calc_var_ratio(self, trait, fit0, tau, noK, marker_list, params=None, cap=4096):
+        params = params or default_params()
+        n = len(fit0.y)
+        X1 = np.asfortranarray(noK.X1, dtype=np.float64)
+        XV = np.asfortranarray(noK.XV, dtype=np.float64)
+        XXVX_inv = np.asfortranarray(noK.XXVX_inv, dtype=np.float64)
+        p = X1.shape[1]
+        eta, mu, tau = _f64(fit0.linear_predictors), _f64(fit0.fitted_values), _f64(tau)
+        ml = np.ascontiguousarray(marker_list, dtype=np.int32)
+        oid = np.empty(cap, dtype=np.int32)
+        cols = [np.empty(cap) for _ in range(5)]
+        n_out = C.c_int(0)
+        rc = lib().orc_calc_var_ratio(self.h, C.c_int(1 if trait == "quantitative" else 0), C.c_int(FAMILY[fit0.family]),
+                                      C.c_long(n), C.c_int(p), _p(eta), _p(mu), _p(tau), _p(X1), _p(XV), _p(XXVX_inv),
+                                      C.byref(params), _p(ml, C.c_int), C.c_long(len(ml)), C.c_int(cap),
+                                      _p(oid, C.c_int), *[_p(c) for c in cols], C.byref(n_out))
+        if rc != 0:
+            raise RuntimeError(lib().orc_last_error(self.h).decode())
+        k = n_out.value
+        return dict(id=oid[:k].copy(), maf=cols[0][:k].copy(), mac=cols[1][:k].copy(), var1=cols[2][:k].copy(),
+                    var2=cols[3][:k].copy(), ratio=cols[4][:k].copy())
+
+    @property
+    def num_products(self):
+        return lib().orc_num_products(self.h)
+
+
+def max_threads():
+    return lib().orc_max_threads()

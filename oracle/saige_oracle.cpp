@@ -1,0 +1,733 @@
+// ===========================================================================
+// saige_oracle.cpp -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE)
+//
+// A from-scratch, R-free restatement of the null-model hot path of SAIGEgds
+// (reference: /root/reference/src/saige_fitnull.cpp, v1.12.5).  It exists only to
+// check the CUDA implementation and to serve as the reported CPU baseline:
+// only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+// reference legs may load it.  The product library never links or calls it.
+//
+// Parity status: PINNED.  tests/test_oracle_golden.py checks this file against the
+// reference's own golden fixtures (inst/unitTests/saige_model*.rds, converted by
+// tests/golden/make_golden.py): tau, coefficients, cov, fitted values and the whole
+// variance-ratio table reproduce to <= 1e-10.  The reference itself cannot be
+// compiled here (needs R, Rcpp, RcppArmadillo, TBB -- none installed), so there is
+// no oracle/_ref build; see DESIGN.md.
+//
+// Every function cites the reference lines it follows.  Armadillo calls are replaced
+// by small dense helpers; R closures (GLM family, RNG) by native restatements of
+// R's own C code (family.c logit_*, RNG.c MT19937, rbinom.c, do_sample).
+// ===========================================================================
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+typedef unsigned char BYTE;
+typedef std::vector<double> dvec;
+
+// column-major dense matrix
+struct dmat {
+    size_t nr = 0, nc = 0;
+    dvec a;
+    dmat() {}
+    dmat(size_t r, size_t c) : nr(r), nc(c), a(r * c, 0.0) {}
+    double &operator()(size_t i, size_t j) { return a[i + j * nr]; }
+    double operator()(size_t i, size_t j) const { return a[i + j * nr]; }
+    double *col(size_t j) { return &a[j * nr]; }
+    const double *col(size_t j) const { return &a[j * nr]; }
+};
+
+
+// per-variant body of get_crossprod_b_grm, saige_fitnull.cpp:481-515: dot = g'b, then buf += dot * g.
+// The reference compiles this with GCC target_clones + -Ofast (vectorization.h COREARRAY_TARGET_CLONES / MATH_OFAST).
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+__attribute__((target_clones("avx512f", "avx2", "default"), optimize("O3")))
+#endif
+void variant_dot_axpy(const BYTE *g0, const double *base, const double *pb, size_t N, double *pbb) {
+    const BYTE *g = g0;
+    double dot = 0; size_t n = N;
+    for (; n >= 4; n -= 4, pb += 4) {
+        BYTE gg = *g++;
+        dot += base[gg & 3] * pb[0] + base[(gg >> 2) & 3] * pb[1] +
+               base[(gg >> 4) & 3] * pb[2] + base[gg >> 6] * pb[3];
+    }
+    for (BYTE gg = (n > 0 ? *g : 0); n > 0; n--) { dot += base[gg & 3] * (*pb++); gg >>= 2; }
+    g = g0; n = N;
+    for (; n >= 4; n -= 4, pbb += 4) {
+        BYTE gg = *g++;
+        pbb[0] += dot * base[gg & 3]; pbb[1] += dot * base[(gg >> 2) & 3];
+        pbb[2] += dot * base[(gg >> 4) & 3]; pbb[3] += dot * base[gg >> 6];
+    }
+    for (BYTE gg = (n > 0 ? *g : 0); n > 0; n--) { (*pbb++) += dot * base[gg & 3]; gg >>= 2; }
+}
+
+// ---------------------------------------------------------------------------
+// R's random number generator (Mersenne-Twister, "Inversion", "Rounding")
+// restated from R's src/main/RNG.c; pinned by the golden tau / var-ratio ids.
+// ---------------------------------------------------------------------------
+struct RRng {
+    uint32_t mt[624];
+    int mti = 625;
+    // set.seed(): Randomize() -> 50 LCG scrambles, then RNG_Init fills 625 seeds,
+    // FixupSeeds sets dummy[0] (= mti) to 624.
+    void set_seed(uint32_t seed) {
+        for (int j = 0; j < 50; j++) seed = 69069u * seed + 1u;
+        uint32_t i_seed[625];
+        for (int j = 0; j < 625; j++) { seed = 69069u * seed + 1u; i_seed[j] = seed; }
+        for (int j = 0; j < 624; j++) mt[j] = i_seed[j + 1];
+        mti = 624;
+    }
+    uint32_t genrand() {
+        static const uint32_t mag01[2] = {0x0u, 0x9908b0dfu};
+        uint32_t y;
+        if (mti >= 624) {
+            int kk;
+            for (kk = 0; kk < 624 - 397; kk++) {
+                y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+                mt[kk] = mt[kk + 397] ^ (y >> 1) ^ mag01[y & 1u];
+            }
+            for (; kk < 623; kk++) {
+                y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+                mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ mag01[y & 1u];
+            }
+            y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+            mt[623] = mt[396] ^ (y >> 1) ^ mag01[y & 1u];
+            mti = 0;
+        }
+        y = mt[mti++];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        return y;
+    }
+    double unif_rand() {  // MT_genrand() + fixup()
+        const double i2_32m1 = 2.328306437080797e-10;
+        double v = genrand() * 2.3283064365386963e-10;
+        if (v <= 0.0) return 0.5 * i2_32m1;
+        if ((1.0 - v) <= 0.0) return 1.0 - 0.5 * i2_32m1;
+        return v;
+    }
+    // rbinom(n, 1, 0.5): inversion branch of rbinom.c consumes one uniform; result = (u >= 0.5)
+    int rbinom_half() { return unif_rand() < 0.5 ? 0 : 1; }
+};
+
+// ---------------------------------------------------------------------------
+// State == the file-scope statics of saige_fitnull.cpp:122-135
+// ---------------------------------------------------------------------------
+struct Oracle {
+    int NumThreads = 1;
+    const BYTE *Geno_PackedRaw = nullptr;
+    std::vector<BYTE> owned;
+    size_t Geno_NumSamp = 0, Geno_PackedNumSamp = 0, Geno_NumVariant = 0;
+    dvec buf_std_geno, buf_diag_grm, buf_crossprod;
+    std::vector<int> n_valid_v, sum_v;
+    RRng rng;
+    long n_products = 0;
+    long n_pcg = 0, n_pcg_iter = 0;
+    bool verbose = false;
+    std::string last_error;
+    BYTE num_valid[256], num_sum[256];
+
+    Oracle() { init_lookup_table(); }
+
+    // saige_fitnull.cpp:137-152
+    void init_lookup_table() {
+        for (int i = 0; i < 256; i++) {
+            int b0 = i & 0x03, b1 = (i >> 2) & 0x03, b2 = (i >> 4) & 0x03, b3 = (i >> 6) & 0x03;
+            num_valid[i] = (b0 < 3) + (b1 < 3) + (b2 < 3) + (b3 < 3);
+            num_sum[i] = (b0 < 3 ? b0 : 0) + (b1 < 3 ? b1 : 0) + (b2 < 3 ? b2 : 0) + (b3 < 3 ? b3 : 0);
+        }
+    }
+
+    // saige_store_2b_geno, saige_fitnull.cpp:159-230
+    void store_2b_geno(const BYTE *packed, size_t n_samp, size_t n_packed, size_t n_var, int nthread) {
+        owned.assign(packed, packed + n_packed * n_var);
+        Geno_PackedRaw = owned.data();
+        Geno_NumSamp = n_samp; Geno_PackedNumSamp = n_packed; Geno_NumVariant = n_var;
+        NumThreads = nthread;
+        if (NumThreads > (int)Geno_NumSamp) NumThreads = (int)Geno_NumSamp;
+        if (NumThreads > (int)Geno_NumVariant) NumThreads = (int)Geno_NumVariant;
+        if (NumThreads < 1) NumThreads = 1;
+        buf_crossprod.assign(n_samp * (size_t)NumThreads, 0.0);
+        buf_std_geno.assign(4 * n_var, 0.0);
+        n_valid_v.assign(n_var, 0); sum_v.assign(n_var, 0);
+        // :182-202 look-up table of standardized genotypes
+#pragma omp parallel for schedule(dynamic, 64) num_threads(NumThreads)
+        for (long i = 0; i < (long)n_var; i++) {
+            const BYTE *g = Geno_PackedRaw + Geno_PackedNumSamp * i;
+            int n_valid = 0, sum = 0;
+            for (size_t j = 0; j < Geno_PackedNumSamp; j++) { n_valid += num_valid[g[j]]; sum += num_sum[g[j]]; }
+            n_valid_v[i] = n_valid; sum_v[i] = sum;
+            double af = double(sum) / (2 * n_valid);
+            double inv = 1 / sqrt(2 * af * (1 - af));
+            if (!std::isfinite(af) || !std::isfinite(inv)) af = inv = 0;
+            double *p = &buf_std_geno[4 * i];
+            p[0] = (0 - 2 * af) * inv; p[1] = (1 - 2 * af) * inv; p[2] = (2 - 2 * af) * inv; p[3] = 0;
+        }
+        // :205-227 diag(GRM), serial in the reference
+        buf_diag_grm.assign(n_samp, 0.0);
+        for (size_t i = 0; i < n_var; i++) {
+            const BYTE *g = Geno_PackedRaw + Geno_PackedNumSamp * i;
+            const double *base = &buf_std_geno[4 * i];
+            size_t n = Geno_NumSamp; double *p = buf_diag_grm.data();
+            for (; n >= 4; n -= 4, p += 4) {
+                BYTE gg = *g++;
+                p[0] += base[gg & 3] * base[gg & 3];
+                p[1] += base[(gg >> 2) & 3] * base[(gg >> 2) & 3];
+                p[2] += base[(gg >> 4) & 3] * base[(gg >> 4) & 3];
+                p[3] += base[gg >> 6] * base[gg >> 6];
+            }
+            for (BYTE gg = (n > 0 ? *g : 0); n > 0; n--) { (*p++) += base[gg & 3] * base[gg & 3]; gg >>= 2; }
+        }
+        for (size_t i = 0; i < n_samp; i++) buf_diag_grm[i] *= 1.0 / Geno_NumVariant;
+    }
+
+    // get_geno_ds, saige_fitnull.cpp:394-427 (dense branch): missing -> NaN
+    void get_geno_ds(size_t snp_idx, dvec &ds) const {
+        ds.resize(Geno_NumSamp);
+        const BYTE *g = Geno_PackedRaw + Geno_PackedNumSamp * snp_idx;
+        for (size_t n = 0; n < Geno_NumSamp; n++) {
+            BYTE c = (g[n >> 2] >> (2 * (n & 3))) & 3;
+            ds[n] = (c < 3) ? double(c) : NAN;
+        }
+    }
+
+    // get_crossprod_b_grm, saige_fitnull.cpp:435-536 (dense branch :477-518)
+    void crossprod_b_grm(const double *b, double *out_b) {
+        n_products++;
+        const size_t N = Geno_NumSamp, M = Geno_NumVariant;
+        std::fill(buf_crossprod.begin(), buf_crossprod.end(), 0.0);
+#pragma omp parallel for schedule(dynamic, 16) num_threads(NumThreads)
+        for (long i = 0; i < (long)M; i++) {
+#ifdef _OPENMP
+            const int th_idx = omp_get_thread_num();
+#else
+            const int th_idx = 0;
+#endif
+            variant_dot_axpy(Geno_PackedRaw + Geno_PackedNumSamp * i, &buf_std_geno[4 * i], b, N,
+                             &buf_crossprod[N * (size_t)th_idx]);
+        }
+        // :520-535 reduce the per-thread buffers, scale by 1/M
+        for (size_t n = 0; n < N; n++) {
+            double s = 0;
+            for (int t = 0; t < NumThreads; t++) s += buf_crossprod[N * (size_t)t + n];
+            out_b[n] = s * (1.0 / M);
+        }
+    }
+
+    // get_diag_sigma, :542-558
+    void get_diag_sigma(const dvec &w, const double tau[2], dvec &out) const {
+        out.resize(Geno_NumSamp);
+        for (size_t i = 0; i < Geno_NumSamp; i++) {
+            double v = tau[0] / w[i] + tau[1] * buf_diag_grm[i];
+            if (v < 1e-4) v = 1e-4;
+            out[i] = v;
+        }
+    }
+
+    // get_crossprod, :564-576
+    dvec get_crossprod(const dvec &b, const dvec &w, const double tau[2]) {
+        const size_t N = Geno_NumSamp; dvec out(N);
+        if (tau[1] == 0) {
+            for (size_t i = 0; i < N; i++) out[i] = tau[0] * (b[i] * (1 / w[i]));
+        } else {
+            dvec ob(N); crossprod_b_grm(b.data(), ob.data());
+            for (size_t i = 0; i < N; i++) out[i] = tau[0] * (b[i] * (1 / w[i])) + tau[1] * ob[i];
+        }
+        return out;
+    }
+
+    static double dot(const dvec &a, const dvec &b) { double s = 0; for (size_t i = 0; i < a.size(); i++) s += a[i] * b[i]; return s; }
+
+    // PCG_diag_sigma, :581-614
+    dvec PCG_diag_sigma(const dvec &w, const double tau[2], const dvec &b, int maxiterPCG, double tolPCG, int *iters = nullptr) {
+        const size_t N = Geno_NumSamp;
+        dvec r = b, r1(N), minv; get_diag_sigma(w, tau, minv);
+        for (size_t i = 0; i < N; i++) minv[i] = 1 / minv[i];
+        dvec z(N), z1(N); for (size_t i = 0; i < N; i++) z[i] = minv[i] * r[i];
+        dvec p = z, x(N, 0.0);
+        int iter = 0;
+        while (iter < maxiterPCG && dot(r, r) > tolPCG) {
+            iter++;
+            dvec Ap = get_crossprod(p, w, tau);
+            double a = dot(r, z) / dot(p, Ap);
+            for (size_t i = 0; i < N; i++) x[i] += a * p[i];
+            for (size_t i = 0; i < N; i++) r1[i] = r[i] - a * Ap[i];
+            for (size_t i = 0; i < N; i++) z1[i] = minv[i] * r1[i];
+            double bet = dot(z1, r1) / dot(z, r);
+            for (size_t i = 0; i < N; i++) p[i] = z1[i] + bet * p[i];
+            z = z1; r = r1;
+        }
+        if (iter >= maxiterPCG) printf("PCG does not converge (may need to increase 'maxiter').\n");
+        n_pcg++; n_pcg_iter += iter;
+        if (iters) *iters = iter;
+        return x;
+    }
+};
+
+// calcCV, :618-623 (arma::stddev = n-1 normalisation)
+double calcCV(const dvec &x) {
+    size_t n = x.size(); double m = 0; for (double v : x) m += v; m /= n;
+    double ss = 0; for (double v : x) ss += (v - m) * (v - m);
+    double sd = sqrt(ss / (n - 1));
+    return sd / (m * int(n));
+}
+
+// ----- small dense helpers (replace Armadillo) -----
+dmat t_times(const dmat &A, const dmat &B) {  // A' * B
+    dmat C(A.nc, B.nc);
+    for (size_t i = 0; i < A.nc; i++) for (size_t j = 0; j < B.nc; j++) {
+        double s = 0; const double *a = A.col(i), *b = B.col(j);
+        for (size_t k = 0; k < A.nr; k++) s += a[k] * b[k];
+        C(i, j) = s;
+    }
+    return C;
+}
+dvec t_times(const dmat &A, const dvec &v) {  // A' * v
+    dvec o(A.nc);
+    for (size_t i = 0; i < A.nc; i++) { double s = 0; const double *a = A.col(i); for (size_t k = 0; k < A.nr; k++) s += a[k] * v[k]; o[i] = s; }
+    return o;
+}
+dvec times(const dmat &A, const dvec &v) {  // A * v
+    dvec o(A.nr, 0.0);
+    for (size_t j = 0; j < A.nc; j++) { const double *a = A.col(j); double vj = v[j]; for (size_t k = 0; k < A.nr; k++) o[k] += a[k] * vj; }
+    return o;
+}
+dmat general_inv(dmat a) {  // Gauss-Jordan with partial pivoting (arma::inv fallback)
+    size_t n = a.nr; dmat inv(n, n); for (size_t i = 0; i < n; i++) inv(i, i) = 1;
+    for (size_t c = 0; c < n; c++) {
+        size_t piv = c; for (size_t r = c + 1; r < n; r++) if (fabs(a(r, c)) > fabs(a(piv, c))) piv = r;
+        if (a(piv, c) == 0) throw std::runtime_error("inv(): matrix is singular");
+        if (piv != c) for (size_t j = 0; j < n; j++) { std::swap(a(c, j), a(piv, j)); std::swap(inv(c, j), inv(piv, j)); }
+        double d = 1 / a(c, c);
+        for (size_t j = 0; j < n; j++) { a(c, j) *= d; inv(c, j) *= d; }
+        for (size_t r = 0; r < n; r++) if (r != c) { double f = a(r, c); if (f != 0) for (size_t j = 0; j < n; j++) { a(r, j) -= f * a(c, j); inv(r, j) -= f * inv(c, j); } }
+    }
+    return inv;
+}
+// mat_inv, :722-733: inv_sympd(symmatu(m)), fallback inv()
+dmat mat_inv(const dmat &m) {
+    size_t n = m.nr; dmat xs = m;
+    for (size_t j = 0; j < n; j++) for (size_t i = j + 1; i < n; i++) xs(i, j) = m(j, i);  // symmatu: mirror upper
+    dmat L(n, n); bool ok = true;
+    for (size_t j = 0; j < n && ok; j++) {
+        double s = xs(j, j); for (size_t k = 0; k < j; k++) s -= L(j, k) * L(j, k);
+        if (!(s > 0)) { ok = false; break; }
+        L(j, j) = sqrt(s);
+        for (size_t i = j + 1; i < n; i++) { double t = xs(i, j); for (size_t k = 0; k < j; k++) t -= L(i, k) * L(j, k); L(i, j) = t / L(j, j); }
+    }
+    if (!ok) {
+        printf("Warning: arma::inv_sympd(), matrix is singular or not positive definite, use arma::inv() instead.\n");
+        return general_inv(xs);
+    }
+    dmat Li(n, n);  // inverse of lower-triangular L
+    for (size_t j = 0; j < n; j++) {
+        Li(j, j) = 1 / L(j, j);
+        for (size_t i = j + 1; i < n; i++) { double s = 0; for (size_t k = j; k < i; k++) s -= L(i, k) * Li(k, j); Li(i, j) = s / L(i, i); }
+    }
+    dmat rv(n, n);
+    for (size_t i = 0; i < n; i++) for (size_t j = 0; j <= i; j++) { double s = 0; for (size_t k = i; k < n; k++) s += Li(k, i) * Li(k, j); rv(i, j) = rv(j, i) = s; }
+    return rv;
+}
+
+// ----- GLM families: R's binomial(link="logit") (src/library/stats/src/family.c) and gaussian() -----
+enum { FAMILY_BINOMIAL = 0, FAMILY_GAUSSIAN = 1 };
+inline double linkinv1(int fam, double eta) {
+    if (fam == FAMILY_GAUSSIAN) return eta;
+    double tmp = (eta < -30) ? DBL_EPSILON : ((eta > 30) ? 1 / DBL_EPSILON : exp(eta));
+    return tmp / (1 + tmp);
+}
+inline double mu_eta1(int fam, double eta) {
+    if (fam == FAMILY_GAUSSIAN) return 1;
+    double opexp = 1 + exp(eta);
+    return (eta > 30 || eta < -30) ? DBL_EPSILON : exp(eta) / (opexp * opexp);
+}
+inline double variance1(int fam, double mu) { return fam == FAMILY_GAUSSIAN ? 1 : mu * (1 - mu); }
+
+struct Params {
+    double tol, tolPCG; int seed, maxiter, maxiterPCG, no_iteration, nrun, num_marker;
+    double traceCVcutoff, ratioCVcutoff; int verbose;
+};
+
+// get_coeff_w, :739-758
+void get_coeff_w(Oracle &o, const dvec &Y, const dmat &X, const dvec &w, const double tau[2], int maxiterPCG, double tolPCG,
+                 dvec &Sigma_iY, dmat &Sigma_iX, dmat &cov, dvec &alpha, dvec &eta) {
+    const size_t N = o.Geno_NumSamp; int p = (int)X.nc;
+    Sigma_iY = o.PCG_diag_sigma(w, tau, Y, maxiterPCG, tolPCG);
+    Sigma_iX = dmat(N, p);
+    for (int i = 0; i < p; i++) {
+        dvec xv(X.col(i), X.col(i) + N);
+        dvec s = o.PCG_diag_sigma(w, tau, xv, maxiterPCG, tolPCG);
+        std::copy(s.begin(), s.end(), Sigma_iX.col(i));
+    }
+    cov = mat_inv(t_times(X, Sigma_iX));
+    dvec t = t_times(Sigma_iX, Y);
+    alpha = times(cov, t);
+    dvec sxa = times(Sigma_iX, alpha);
+    eta.resize(N);
+    for (size_t i = 0; i < N; i++) eta[i] = Y[i] - tau[0] * (Sigma_iY[i] - sxa[i]) / w[i];
+}
+
+// get_sigma_X, :762-770
+dmat get_sigma_X(Oracle &o, const dvec &w, const double tau[2], const dmat &X, int maxiterPCG, double tolPCG) {
+    const size_t N = o.Geno_NumSamp; dmat S(N, X.nc);
+    for (size_t i = 0; i < X.nc; i++) {
+        dvec xv(X.col(i), X.col(i) + N);
+        dvec s = o.PCG_diag_sigma(w, tau, xv, maxiterPCG, tolPCG);
+        std::copy(s.begin(), s.end(), S.col(i));
+    }
+    return S;
+}
+
+// get_coeff, :778-813
+void get_coeff(Oracle &o, const dvec &y, const dmat &X, const double tau[2], int fam, const dvec &alpha0, const dvec &eta0,
+               const dvec &offset, int maxiterPCG, int maxiter, double tolPCG,
+               dvec &Y, dvec &mu, dvec &alpha, dvec &eta, dvec &W, dmat &cov, dvec &Sigma_iY, dmat &Sigma_iX) {
+    const double tol_coef = 0.1; const size_t N = y.size();
+    mu.resize(N); Y.resize(N); W.resize(N);
+    for (size_t i = 0; i < N; i++) {
+        mu[i] = linkinv1(fam, eta0[i]); double me = mu_eta1(fam, eta0[i]);
+        Y[i] = eta0[i] - offset[i] + (y[i] - mu[i]) / me;
+        W[i] = (me * me) / variance1(fam, mu[i]);
+    }
+    dvec a0 = alpha0;
+    for (int it = 0; it < maxiter; it++) {
+        get_coeff_w(o, Y, X, W, tau, maxiterPCG, tolPCG, Sigma_iY, Sigma_iX, cov, alpha, eta);
+        for (size_t i = 0; i < N; i++) {
+            eta[i] += offset[i];
+            mu[i] = linkinv1(fam, eta[i]); double me = mu_eta1(fam, eta[i]);
+            Y[i] = eta[i] - offset[i] + (y[i] - mu[i]) / me;
+            W[i] = (me * me) / variance1(fam, mu[i]);
+        }
+        double mx = 0;
+        for (size_t k = 0; k < alpha.size(); k++) mx = std::max(mx, fabs(alpha[k] - a0[k]) / (fabs(alpha[k]) + fabs(a0[k]) + tol_coef));
+        if (mx < tol_coef) break;
+        a0 = alpha;
+    }
+}
+
+// projection P v = Sigma_iv - Sigma_iX (cov (Sigma_iX' v_rhs))  -- pattern of :651, :823, :831
+dvec project(const dvec &Sigma_iv, const dmat &Sigma_iX, const dmat &cov, const dvec &rhs) {
+    dvec t = times(cov, t_times(Sigma_iX, rhs)); dvec s = times(Sigma_iX, t);
+    dvec o(Sigma_iv.size()); for (size_t i = 0; i < o.size(); i++) o[i] = Sigma_iv[i] - s[i];
+    return o;
+}
+
+// get_trace / get_trace_q, :627-718.  quant=true also fills trace0 = mean(u'Pu).
+void get_trace(Oracle &o, const dmat &Sigma_iX, const dvec &w, const double tau[2], const dmat &cov, int nrun, int maxiterPCG,
+               double tolPCG, double traceCVcutoff, int seed, bool quant, double &outTrace0, double &outTrace1) {
+    const size_t N = o.Geno_NumSamp;
+    o.rng.set_seed((uint32_t)seed);                       // :631 / :676 -- re-seeded on every call
+    int nrunStart = 0, nrunEnd = nrun;
+    double traceCV = traceCVcutoff + 0.1, traceCV0 = traceCVcutoff + 0.1;
+    dvec buf(nrun, 0.0), buf0(nrun, 0.0), u(N), Au(N);
+    while (traceCV > traceCVcutoff || (quant && traceCV0 > traceCVcutoff)) {
+        for (int i = nrunStart; i < nrunEnd; i++) {
+            for (size_t k = 0; k < N; k++) u[k] = 2.0 * o.rng.rbinom_half() - 1;   // :649
+            dvec Sigma_iu = o.PCG_diag_sigma(w, tau, u, maxiterPCG, tolPCG);
+            dvec Pu = project(Sigma_iu, Sigma_iX, cov, u);
+            o.crossprod_b_grm(u.data(), Au.data());
+            buf[i] = Oracle::dot(Au, Pu);
+            buf0[i] = Oracle::dot(u, Pu);
+        }
+        traceCV = calcCV(buf);
+        traceCV0 = quant ? calcCV(buf0) : 0;
+        if (traceCV > traceCVcutoff || (quant && traceCV0 > traceCVcutoff)) {
+            nrunStart = nrunEnd; nrunEnd += 10; buf.resize(nrunEnd, 0.0); buf0.resize(nrunEnd, 0.0);
+            printf("CV for trace random estimator using %d runs is %g > %g\ntry %d runs ...\n", nrun, traceCV, traceCVcutoff, nrunEnd);
+        }
+    }
+    double m1 = 0, m0 = 0; for (double v : buf) m1 += v; for (double v : buf0) m0 += v;
+    outTrace1 = m1 / buf.size(); outTrace0 = m0 / buf0.size();
+}
+
+// get_AI_score, :817-833
+void get_AI_score(Oracle &o, const dvec &Y, const dvec &w, const double tau[2], const dvec &Sigma_iY, const dmat &Sigma_iX,
+                  const dmat &cov, const Params &P, double &YPAPY, double &Trace, double &AI) {
+    const size_t N = o.Geno_NumSamp;
+    dvec PY = project(Sigma_iY, Sigma_iX, cov, Y);
+    dvec APY(N); o.crossprod_b_grm(PY.data(), APY.data());
+    YPAPY = Oracle::dot(PY, APY);
+    double t0;
+    get_trace(o, Sigma_iX, w, tau, cov, P.nrun, P.maxiterPCG, P.tolPCG, P.traceCVcutoff, P.seed, false, t0, Trace);
+    dvec PAPY_1 = o.PCG_diag_sigma(w, tau, APY, P.maxiterPCG, P.tolPCG);
+    dvec PAPY = project(PAPY_1, Sigma_iX, cov, PAPY_1);
+    AI = Oracle::dot(APY, PAPY);
+}
+
+// get_AI_score_q, :836-862
+void get_AI_score_q(Oracle &o, const dvec &Y, const dvec &w, const double tau[2], const dvec &Sigma_iY, const dmat &Sigma_iX,
+                    const dmat &cov, const Params &P, double YPAPY[2], double Trace[2], double AI[4]) {
+    const size_t N = o.Geno_NumSamp;
+    dvec PY = project(Sigma_iY, Sigma_iX, cov, Y);
+    dvec A0PY = PY, APY(N); o.crossprod_b_grm(PY.data(), APY.data());
+    YPAPY[0] = Oracle::dot(PY, APY); YPAPY[1] = Oracle::dot(PY, A0PY);
+    get_trace(o, Sigma_iX, w, tau, cov, P.nrun, P.maxiterPCG, P.tolPCG, P.traceCVcutoff, P.seed, true, Trace[0], Trace[1]);
+    dvec PA0PY_1 = o.PCG_diag_sigma(w, tau, A0PY, P.maxiterPCG, P.tolPCG);
+    dvec PA0PY = project(PA0PY_1, Sigma_iX, cov, PA0PY_1);
+    AI[0] = Oracle::dot(A0PY, PA0PY);
+    dvec PAPY_1 = o.PCG_diag_sigma(w, tau, APY, P.maxiterPCG, P.tolPCG);
+    dvec PAPY = project(PAPY_1, Sigma_iX, cov, PAPY_1);
+    AI[3] = Oracle::dot(APY, PAPY);
+    AI[1] = AI[2] = Oracle::dot(A0PY, PAPY);
+}
+
+// fitglmmaiRPCG, :866-895
+void fitglmmaiRPCG(Oracle &o, const dvec &Y, const dvec &w, const double in_tau[2], const dvec &Sigma_iY, const dmat &Sigma_iX,
+                   const dmat &cov, const Params &P, double tau[2]) {
+    double YPAPY, Trace, AI;
+    get_AI_score(o, Y, w, in_tau, Sigma_iY, Sigma_iX, cov, P, YPAPY, Trace, AI);
+    double score = YPAPY - Trace, Dtau = score / AI;
+    double tau0[2] = {in_tau[0], in_tau[1]}; tau[0] = in_tau[0]; tau[1] = tau0[1] + Dtau;
+    for (int i = 0; i < 2; i++) if (tau[i] < P.tol) tau[i] = 0;
+    double step = 1.0;
+    while (tau[1] < 0.0) { step *= 0.5; tau[1] = tau0[1] + step * Dtau; }
+    for (int i = 0; i < 2; i++) if (tau[i] < P.tol) tau[i] = 0;
+}
+
+// fitglmmaiRPCG_q, :898-928
+void fitglmmaiRPCG_q(Oracle &o, const dvec &Y, const dvec &w, const double in_tau[2], const dvec &Sigma_iY, const dmat &Sigma_iX,
+                     const dmat &cov, const Params &P, double tau[2]) {
+    bool zero_v[2] = {in_tau[0] < P.tol, in_tau[1] < P.tol};
+    double YPAPY[2], Trace[2], AI[4];
+    get_AI_score_q(o, Y, w, in_tau, Sigma_iY, Sigma_iX, cov, P, YPAPY, Trace, AI);
+    double score[2] = {YPAPY[1] - Trace[0], YPAPY[0] - Trace[1]};
+    // Dtau = solve(AI, score): 2x2 LU with partial pivoting (LAPACK dgesv)
+    double a = AI[0], b = AI[2], c = AI[1], d = AI[3], s0 = score[0], s1 = score[1], Dtau[2];
+    if (fabs(c) > fabs(a)) { std::swap(a, c); std::swap(b, d); std::swap(s0, s1); }
+    double l = c / a, d2 = d - l * b, t1 = s1 - l * s0;
+    Dtau[1] = t1 / d2; Dtau[0] = (s0 - b * Dtau[1]) / a;
+    double tau0[2] = {in_tau[0], in_tau[1]};
+    for (int i = 0; i < 2; i++) { tau[i] = tau0[i] + Dtau[i]; if (zero_v[i] && tau[i] < P.tol) tau[i] = 0; }
+    double step = 1.0;
+    while (tau[0] < 0.0 || tau[1] < 0.0) {
+        step *= 0.5;
+        for (int i = 0; i < 2; i++) { tau[i] = tau0[i] + step * Dtau[i]; if (zero_v[i] && tau[i] < P.tol) tau[i] = 0; }
+    }
+    for (int i = 0; i < 2; i++) if (tau[i] < P.tol) tau[i] = 0;
+}
+
+void print_vec(const char *s, const double *x, size_t n, bool nl = true) {
+    printf("%s(", s);
+    for (size_t i = 0; i < n; i++) { if (i) printf(", "); printf("%0.7g", x[i]); }
+    printf(nl ? ")\n" : ")");
+}
+
+}  // namespace
+
+// ===========================================================================
+// C interface for the ctypes harness (tests/oracle_lib.py)
+// ===========================================================================
+extern "C" {
+
+struct orc_params {  // the `param` list of R/saige_main.r:442-453
+    double tol, tolPCG;
+    int seed, maxiter, maxiterPCG, no_iteration, nrun, num_marker;
+    double traceCVcutoff, ratioCVcutoff;
+    int verbose;
+};
+
+void *orc_create() { return new Oracle(); }
+void orc_destroy(void *h) { delete (Oracle *)h; }
+const char *orc_last_error(void *h) { return ((Oracle *)h)->last_error.c_str(); }
+long orc_num_products(void *h) { return ((Oracle *)h)->n_products; }
+long orc_num_pcg(void *h) { return ((Oracle *)h)->n_pcg; }
+long orc_num_pcg_iter(void *h) { return ((Oracle *)h)->n_pcg_iter; }
+int orc_max_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+int orc_store_2b_geno(void *h, const unsigned char *packed, long n_samp, long n_packed, long n_var, int num_thread,
+                      double *buf_std_geno, double *buf_diag) {
+    Oracle &o = *(Oracle *)h;
+    o.store_2b_geno(packed, n_samp, n_packed, n_var, num_thread);
+    if (buf_std_geno) memcpy(buf_std_geno, o.buf_std_geno.data(), sizeof(double) * 4 * n_var);
+    if (buf_diag) memcpy(buf_diag, o.buf_diag_grm.data(), sizeof(double) * n_samp);
+    return 0;
+}
+int orc_allele_counts(void *h, int *n_valid, int *sum) {
+    Oracle &o = *(Oracle *)h;
+    memcpy(n_valid, o.n_valid_v.data(), sizeof(int) * o.Geno_NumVariant);
+    memcpy(sum, o.sum_v.data(), sizeof(int) * o.Geno_NumVariant);
+    return 0;
+}
+int orc_get_geno_ds(void *h, long snp_idx, double *ds) {
+    Oracle &o = *(Oracle *)h; dvec v; o.get_geno_ds(snp_idx, v); memcpy(ds, v.data(), sizeof(double) * v.size()); return 0;
+}
+int orc_grm_mv(void *h, const double *b, double *out) { ((Oracle *)h)->crossprod_b_grm(b, out); return 0; }
+int orc_diag_sigma(void *h, const double *w, const double *tau, double *out) {
+    Oracle &o = *(Oracle *)h; dvec wv(w, w + o.Geno_NumSamp), r; o.get_diag_sigma(wv, tau, r);
+    memcpy(out, r.data(), sizeof(double) * r.size()); return 0;
+}
+int orc_pcg(void *h, const double *w, const double *tau, const double *b, int maxiterPCG, double tolPCG, double *x, int *iters) {
+    Oracle &o = *(Oracle *)h; size_t N = o.Geno_NumSamp;
+    dvec wv(w, w + N), bv(b, b + N);
+    dvec r = o.PCG_diag_sigma(wv, tau, bv, maxiterPCG, tolPCG, iters);
+    memcpy(x, r.data(), sizeof(double) * N); return 0;
+}
+
+// f64_af_ac_impute, vectorization.cpp:186-205
+void orc_af_ac_impute(double *ds, long n, double *AF, double *AC, int *Num) {
+    double sum = 0; int num = 0;
+    for (long i = 0; i < n; i++) if (std::isfinite(ds[i])) { sum += ds[i]; num++; }
+    *AF = (num > 0) ? (sum / (2 * num)) : NAN; *AC = sum; *Num = num;
+    if (num < (int)n) { double d = *AF * 2; for (long i = 0; i < n; i++) if (!std::isfinite(ds[i])) ds[i] = d; }
+}
+
+// R RNG helpers
+void orc_set_seed(void *h, unsigned seed) { ((Oracle *)h)->rng.set_seed(seed); }
+void orc_unif_rand(void *h, long n, double *out) { Oracle &o = *(Oracle *)h; for (long i = 0; i < n; i++) out[i] = o.rng.unif_rand(); }
+void orc_rademacher(void *h, long n, double *out) { Oracle &o = *(Oracle *)h; for (long i = 0; i < n; i++) out[i] = 2.0 * o.rng.rbinom_half() - 1; }
+// sample.int(n, n) under sample.kind="Rounding" (do_sample: x[j] = x[--n]); 1-based output
+void orc_sample_int(void *h, int n, int *out) {
+    Oracle &o = *(Oracle *)h; std::vector<int> x(n); for (int i = 0; i < n; i++) x[i] = i;
+    int nn = n;
+    for (int i = 0; i < n; i++) { int j = (int)floor(nn * o.rng.unif_rand()); out[i] = x[j] + 1; x[j] = x[--nn]; }
+}
+
+// saige_fit_AI_PCG_binary (:949-1099) and saige_fit_AI_PCG_quant (:1103-1248); family: 0 binomial/logit, 1 gaussian/identity.
+// Outputs: coefficients[p], tau_out[2], linear_predictors[N], fitted_values[N], residuals[N], cov[p*p], converged.
+int orc_fit_AI_PCG(void *h, int quant, int family, long n, int p, const double *y_, const double *offset_,
+                   const double *lin_pred, const double *fitted, const double *coef, const double *X_, const double *tau_in,
+                   const orc_params *pp, double *coefficients, double *tau_out, double *linear_predictors,
+                   double *fitted_values, double *residuals, double *cov_out, int *converged) {
+    Oracle &o = *(Oracle *)h;
+    try {
+        Params P{pp->tol, pp->tolPCG, pp->seed, pp->maxiter, pp->maxiterPCG, pp->no_iteration, pp->nrun, pp->num_marker,
+                 pp->traceCVcutoff, pp->ratioCVcutoff, pp->verbose};
+        const double tol = P.tol, tol_inv_2 = 1 / (tol * tol);
+        const size_t N = n;
+        dvec y(y_, y_ + N), offset(N, 0.0); if (offset_) offset.assign(offset_, offset_ + N);
+        dmat X(N, p); memcpy(X.a.data(), X_, sizeof(double) * N * p);
+        dvec eta(lin_pred, lin_pred + N), eta0 = eta, mu(fitted, fitted + N), Y(N);
+        for (size_t i = 0; i < N; i++) Y[i] = eta[i] - offset[i] + (y[i] - mu[i]) / mu_eta1(family, eta0[i]);
+        dvec alpha0(coef, coef + p), alpha = alpha0; dmat cov;
+        double tau[2] = {tau_in[0], tau_in[1]}, tau0[2] = {tau_in[0], tau_in[1]};
+        if (P.verbose) printf("Initial variance component estimates, tau:\n    Sigma_E: %g, Sigma_G: %g\n", tau[0], tau[1]);
+
+        dvec re_Y, re_mu, re_alpha, re_eta, re_W, re_Sigma_iY; dmat re_cov, re_Sigma_iX;
+        get_coeff(o, y, X, tau, family, alpha0, eta0, offset, P.maxiterPCG, P.maxiter, P.tolPCG,
+                  re_Y, re_mu, re_alpha, re_eta, re_W, re_cov, re_Sigma_iY, re_Sigma_iX);
+        int iter = 1;
+        if (!quant && P.no_iteration) {   // :1004-1014
+            alpha = re_alpha; eta = re_eta; mu = re_mu; cov = re_cov;
+        } else {
+            if (!quant) {
+                double YPAPY, Trace, AI;
+                get_AI_score(o, re_Y, re_W, tau, re_Sigma_iY, re_Sigma_iX, re_cov, P, YPAPY, Trace, AI);
+                tau[1] = std::max(0.0, tau0[1] + tau0[1] * tau0[1] * (YPAPY - Trace) / N);     // :1024
+            } else {
+                double YPAPY[2], Trace[2], AI[4];
+                get_AI_score_q(o, re_Y, re_W, tau, re_Sigma_iY, re_Sigma_iX, re_cov, P, YPAPY, Trace, AI);
+                tau[0] = std::max(0.0, tau0[0] + tau0[0] * tau0[0] * (YPAPY[1] - Trace[0]) / N);  // :1166-1167
+                tau[1] = std::max(0.0, tau0[1] + tau0[1] * tau0[1] * (YPAPY[0] - Trace[1]) / N);
+            }
+            for (; iter <= P.maxiter; iter++) {
+                if (P.verbose) { printf("Iteration %d:\n", iter); print_vec("    tau: ", tau, 2); print_vec("    fixed coeff: ", alpha.data(), p); }
+                alpha0 = re_alpha; tau0[0] = tau[0]; tau0[1] = tau[1]; eta0 = eta;
+                for (int itry = 1; itry <= 11; itry++) {
+                    get_coeff(o, y, X, tau0, family, alpha0, eta0, offset, P.maxiterPCG, P.maxiter, P.tolPCG,
+                              re_Y, re_mu, re_alpha, re_eta, re_W, re_cov, re_Sigma_iY, re_Sigma_iX);
+                    if (!quant) fitglmmaiRPCG(o, re_Y, re_W, tau0, re_Sigma_iY, re_Sigma_iX, re_cov, P, tau);
+                    else fitglmmaiRPCG_q(o, re_Y, re_W, tau0, re_Sigma_iY, re_Sigma_iX, re_cov, P, tau);
+                    if (std::max(tau[0], tau[1]) > tol_inv_2) {
+                        if (itry <= 10) { tau0[1] *= 0.5; continue; }
+                        throw std::overflow_error("Large variance estimate observed in the iterations, model not converged!");
+                    }
+                    break;
+                }
+                cov = re_cov; alpha = re_alpha; eta = re_eta; Y = re_Y; mu = re_mu;
+                if (!quant) { if (tau[1] == 0) break; }
+                else if (tau[0] <= 0) throw std::overflow_error("Sigma_E = 0, model not converged!");
+                double mx = 0;
+                for (int k = 0; k < 2; k++) mx = std::max(mx, fabs(tau[k] - tau0[k]) / (fabs(tau[k]) + fabs(tau0[k]) + tol));
+                if (mx < tol) break;
+            }
+            get_coeff(o, y, X, tau, family, alpha0, eta0, offset, P.maxiterPCG, P.maxiter, P.tolPCG,
+                      re_Y, re_mu, re_alpha, re_eta, re_W, re_cov, re_Sigma_iY, re_Sigma_iX);
+            cov = re_cov; alpha = re_alpha; eta = re_eta; Y = re_Y; mu = re_mu;
+        }
+        if (P.verbose) { print_vec("Final tau: ", tau, 2); print_vec("    fixed coeff: ", alpha.data(), p); }
+        memcpy(coefficients, alpha.data(), sizeof(double) * p);
+        tau_out[0] = tau[0]; tau_out[1] = tau[1];
+        memcpy(linear_predictors, eta.data(), sizeof(double) * N);
+        memcpy(fitted_values, mu.data(), sizeof(double) * N);
+        for (size_t i = 0; i < N; i++) residuals[i] = y[i] - mu[i];
+        memcpy(cov_out, cov.a.data(), sizeof(double) * p * p);
+        *converged = (P.no_iteration && !quant) ? 1 : (iter <= P.maxiter);
+        return 0;
+    } catch (std::exception &e) { o.last_error = e.what(); return 1; }
+}
+
+// saige_calc_var_ratio_binary / _quant, :1255-1474.  fit0 eta/mu are the *glm* values (H6).
+// X1: N x p, XV: p x N, XXVX_inv: N x p (all column-major).  Outputs capacity `cap` rows; returns count in *n_out.
+int orc_calc_var_ratio(void *h, int quant, int family, long n, int p, const double *lin_pred, const double *fitted,
+                       const double *tau_, const double *X1_, const double *XV_, const double *XXVX_inv_,
+                       const orc_params *pp, const int *rand_index, long num_rand_snp, int cap,
+                       int *o_id, double *o_maf, double *o_mac, double *o_var1, double *o_var2, double *o_ratio, int *n_out) {
+    Oracle &o = *(Oracle *)h;
+    try {
+        const size_t N = n; const double tolPCG = pp->tolPCG; const int maxiterPCG = pp->maxiterPCG;
+        const double ratioCVcutoff = pp->ratioCVcutoff; int num_marker = pp->num_marker;
+        dvec eta(lin_pred, lin_pred + N), mu(fitted, fitted + N), W(N);
+        for (size_t i = 0; i < N; i++) { double me = mu_eta1(family, eta[i]); W[i] = me * me / variance1(family, mu[i]); }
+        double tau[2] = {tau_[0], tau_[1]};
+        dmat X1(N, p); memcpy(X1.a.data(), X1_, sizeof(double) * N * p);
+        dmat XV(p, N); memcpy(XV.a.data(), XV_, sizeof(double) * N * p);
+        dmat XXVX_inv(N, p); memcpy(XXVX_inv.a.data(), XXVX_inv_, sizeof(double) * N * p);
+        dmat Sigma_iX = get_sigma_X(o, W, tau, X1, maxiterPCG, tolPCG);
+        double ratioCV = ratioCVcutoff + 0.1; int num_tested = 0; long snp_idx = 0;
+        std::vector<double> lst_ratio; dvec G0(N);
+        while (ratioCV > ratioCVcutoff && snp_idx < num_rand_snp) {
+            while (num_tested < num_marker && snp_idx < num_rand_snp) {
+                const int i_snp = rand_index[snp_idx++];
+                o.get_geno_ds(i_snp - 1, G0);
+                double AF, AC; int Num;
+                orc_af_ac_impute(G0.data(), N, &AF, &AC, &Num);
+                if (AF > 0.5) { for (size_t i = 0; i < N; i++) G0[i] = 2 - G0[i]; AC = 2 * Num - AC; AF = 1 - AF; }
+                if (AC <= 20) continue;
+                dvec t = times(XV, G0); dvec G = times(XXVX_inv, t);
+                for (size_t i = 0; i < N; i++) G[i] = G0[i] - G[i];
+                dvec g(N); double sq = sqrt(AC); for (size_t i = 0; i < N; i++) g[i] = G[i] / sq;
+                dvec Sigma_iG = o.PCG_diag_sigma(W, tau, G, maxiterPCG, tolPCG);
+                // adj = Sigma_iX * mat_inv(X1' Sigma_iX) * X1' * Sigma_iG   (:1322)
+                dmat Minv = mat_inv(t_times(X1, Sigma_iX));
+                dmat SM(N, p);  // Sigma_iX * Minv
+                for (int c = 0; c < p; c++) { dvec e(Minv.col(c), Minv.col(c) + p); dvec col = times(Sigma_iX, e); std::copy(col.begin(), col.end(), SM.col(c)); }
+                dvec adj = times(SM, t_times(X1, Sigma_iG));
+                double s1 = 0, s2 = 0; for (size_t i = 0; i < N; i++) { s1 += G[i] * Sigma_iG[i]; s2 += G[i] * adj[i]; }
+                double var1 = (s1 - s2) / AC, var2 = 0;
+                if (!quant) for (size_t i = 0; i < N; i++) var2 += mu[i] * (1 - mu[i]) * g[i] * g[i];
+                else for (size_t i = 0; i < N; i++) var2 += g[i] * g[i];
+                double ratio = var1 / var2;
+                if (num_tested >= cap) throw std::runtime_error("var-ratio output capacity exceeded");
+                o_id[num_tested] = i_snp; o_maf[num_tested] = AF; o_mac[num_tested] = AC;
+                o_var1[num_tested] = var1; o_var2[num_tested] = var2; o_ratio[num_tested] = ratio;
+                num_tested++; lst_ratio.push_back(ratio);
+                if (pp->verbose) printf("%6d, maf: %0.4f, mac: %g,\tratio: %0.4f (var1: %.3g, var2: %.3g)\n", num_tested, AF, AC, ratio, var1, var2);
+            }
+            ratioCV = calcCV(lst_ratio);
+            if (ratioCV > ratioCVcutoff) num_marker += 10;
+        }
+        *n_out = num_tested;
+        return 0;
+    } catch (std::exception &e) { o.last_error = e.what(); return 1; }
+}
+
+}  // extern "C"
