@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py -- GRM-vector products per second at N=430K x M=100K (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo (CUDA, sm_100a)
+  python bench.py --impl reference [...]                         # the reference algorithm on the host cores
+
+One "step" = one product out = (1/M) G_std G_std' b over the whole packed genotype matrix
+(get_crossprod_b_grm, saige_fitnull.cpp:435-536) for one right-hand side.  For N > 1 GPUs the fixed
+N x M matrix is split by variant block across ranks (strong scaling) and every step ends with one
+sum all-reduce of the N-vector.
+
+value  : device-resident throughput (b and out already in HBM), CUDA events, max over ranks.
+e2e    : the same step through the C-ABI entry point sgb_grm_mv with HOST buffers (host->device copy of b,
+         device->host copy of the result inside the timed region) -- the call an R user's .Call makes.
+roofline: algorithmic bytes = ceil(N/4)*M_local packed bytes per product over the measured
+         product time, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+cpu_baseline: the CPU oracle's product (same algorithm and threading as the reference) on all host cores,
+         on a bounded variant sample, extrapolated linearly in M to the full shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_SAMP = int(os.environ.get("SGB_BENCH_N", 430000))
+N_VAR = int(os.environ.get("SGB_BENCH_M", 100000))
+MISSING = 0.005
+METRIC = "grm_vector_products_per_s"
+UNIT = "products/s"
+
+
+def workload_name():
+    return "synthetic N=%d M=%d (UKBB-scale) single-RHS GRM product, maf~U(0.005,0.5), %.1f%% missing" % (
+        N_SAMP, N_VAR, 100 * MISSING)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def numpy_packed_sample(n_samp, n_var, seed=200):
+    """Same distribution as the device generator (store.cu synth_kernel); bytes differ, timing does not."""
+    rng = np.random.default_rng(seed)
+    nb = (n_samp + 3) // 4
+    pool_n = min(n_var, 64)          # 64 distinct variants, tiled: the loop's cost does not depend on the codes
+    pool = np.empty((pool_n, nb), dtype=np.uint8)
+    for j in range(pool_n):
+        maf = rng.uniform(0.005, 0.5)
+        g = rng.binomial(2, maf, size=nb * 4).astype(np.uint8)
+        g[rng.random(nb * 4) < MISSING] = 3
+        g[n_samp:] = 3
+        q = g.reshape(nb, 4)
+        pool[j] = q[:, 0] | (q[:, 1] << 2) | (q[:, 2] << 4) | (q[:, 3] << 6)
+    return np.ascontiguousarray(pool[np.arange(n_var) % pool_n])
+
+
+def cpu_product_rate(steps, warmup, m_sample=None):
+    """Time the oracle's get_crossprod_b_grm on all host cores over a variant sample; extrapolate to N_VAR."""
+    from oracle.oracle import Oracle, build, max_threads
+    build()
+    cores = max_threads()
+    if m_sample is None:
+        # ~0.9 G genotypes/s/core: aim at ~1 s per sampled product
+        m_sample = int(max(64, min(N_VAR, 1.0 * 0.6e9 * cores / N_SAMP)))
+    packed = numpy_packed_sample(N_SAMP, m_sample)
+    o = Oracle()
+    o.store_2b_geno(packed, N_SAMP, num_thread=cores)
+    b = np.random.default_rng(1).standard_normal(N_SAMP)
+    for _ in range(warmup):
+        o.grm_mv(b)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.grm_mv(b)
+    dt = (time.perf_counter() - t0) / steps
+    full = dt * (N_VAR / m_sample)
+    return dict(value=1.0 / full, unit=UNIT, cores=cores, kind="port",
+                sample="%d of %d variants x %d samples, %d timed products of %.3f s each, scaled linearly in M"
+                       % (m_sample, N_VAR, N_SAMP, steps, dt)), full
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    cb, full = cpu_product_rate(steps, max(1, min(args.warmup, 1)))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": 1, "ms_per_step": full * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(), "n_samp": N_SAMP, "n_var": N_VAR},
+            "cpu_baseline": cb, "gpu_launches": 0,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import saigegds_b200 as sg
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = sg.Context(local_rank)
+    if world > 1:
+        sg.init_comm_from_torch(ctx)
+    a, b_end = sg.shard_range(N_VAR, rank, world)
+    m_local = b_end - a
+    ctx.store_synthetic(N_SAMP, m_local, N_VAR, a, seed=200, missing_rate=MISSING)
+    if args.kernel:
+        ctx.set_kernel(args.kernel)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    rng = np.random.default_rng(1)
+    b_host = rng.standard_normal(N_SAMP)
+    d_b = ctx.device_vector(b_host)
+    d_out = ctx.device_empty(8 * N_SAMP)
+
+    # ---- device-resident throughput (value) ----
+    for _ in range(max(3, args.warmup)):
+        ctx.grm_mv_device(d_b, d_out, 1)
+    ctx.reset_stats()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ms = ctx.time_products_device(d_b, d_out, 1, args.steps)       # CUDA events on the launching stream, synced both sides
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(ms)
+    st = ctx.stats()
+    launches = int(st["n_kernel_launches"])
+    ms_per_step = ms / args.steps
+    value = 1e3 / ms_per_step
+
+    # ---- end to end through the C-ABI with host buffers (e2e) ----
+    for _ in range(2):
+        ctx.get_crossprod_b_grm(b_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out_host = ctx.get_crossprod_b_grm(b_host)
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+
+    # ---- per-kernel event timing (separate, untimed pass) ----
+    ctx.set_profiling(True)
+    for _ in range(3):
+        ctx.grm_mv_device(d_b, d_out, 1)
+    ktimes = ctx.kernel_times()
+    ctx.set_profiling(False)
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peaks()
+    alg_bytes = ((N_SAMP + 3) // 4) * m_local
+    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    kern = {k: {"ms_per_launch": v[0] / v[1], "launches_per_product": v[1] / 3.0,
+                "gbs_on_packed_bytes": alg_bytes / (v[0] / v[1] * 1e-3) / 1e9} for k, v in ktimes.items()}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(), "n_samp": N_SAMP, "n_var": N_VAR, "n_var_per_gpu": m_local,
+                   "parallelism": "variant-sharded x%d + sum all-reduce of the N-vector" % world,
+                   "l2": "inputs (%.2f GB packed per GPU) exceed the 126 MB L2; no flush needed" % (alg_bytes / 1e9),
+                   "kernel": args.kernel or "auto"},
+        "clocks": clocks,
+        "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * N_SAMP, "d2h_bytes_per_step": 8 * N_SAMP,
+                "ms_per_step": e2e_s * 1e3, "note": "sgb_grm_mv with pageable host b/out; genotypes resident as in the reference"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "note": "whole product (all kernels of one step): algorithmic bytes = ceil(N/4)*M_local packed bytes",
+                     "kernels": kern},
+        "result_checksum": float(np.sum(out_host)),
+    }
+    if world == 1 and not args.no_cpu:
+        cb, _ = cpu_product_rate(3, 1)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kernel", default=None, choices=[None, "auto", "simt", "imma"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

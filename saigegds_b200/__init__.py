@@ -1,0 +1,11 @@
+"""saigegds_b200: B200-native GRM-vector product and null-model fit behind SAIGEgds' own native interface.
+
+Only the hot path of seqFitNullGLMM_SPA is here: packed-genotype store, GRM product,
+PCG, trace / AI-REML / variance-ratio drivers.  All numerics run in libsaigegds_b200.so (CUDA, sm_100a).
+"""
+from ._lib import InvalidArgument, OverflowErrorSGB, SgbError, build  # noqa: F401
+from .api import Context, DeviceArray, NullModel, default_context, make_param, seqFitNullGLMM_SPA  # noqa: F401
+from .dist import init_comm_from_torch, shard_range  # noqa: F401
+
+__all__ = ["Context", "DeviceArray", "NullModel", "default_context", "make_param", "seqFitNullGLMM_SPA",
+           "init_comm_from_torch", "shard_range", "build", "SgbError", "InvalidArgument", "OverflowErrorSGB"]

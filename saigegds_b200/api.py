@@ -1,0 +1,378 @@
+"""Host-side mirror of the reference interface for the null-model hot path.
+
+Names, argument meaning and error behaviour follow the reference:
+
+  native entry points (src/saige_fitnull.cpp)         here
+  -------------------------------------------         ---------------------------------
+  saige_store_2b_geno        (:159)                   Context.saige_store_2b_geno
+  get_crossprod_b_grm        (:436)                   Context.get_crossprod_b_grm
+  get_diag_sigma / PCG_diag_sigma (:543, :582)        Context.get_diag_sigma / PCG_diag_sigma
+  saige_fit_AI_PCG_binary / _quant (:949, :1103)      Context.saige_fit_AI_PCG_binary / _quant
+  saige_calc_var_ratio_binary / _quant (:1255, :1366) Context.saige_calc_var_ratio_binary / _quant
+  R driver seqFitNullGLMM_SPA (R/saige_main.r:223)    seqFitNullGLMM_SPA
+
+Everything numeric runs in libsaigegds_b200.so on the GPU; this module only marshals numpy arrays
+into the C-ABI.  torch is used for plumbing only (device selection, torch.distributed rendezvous).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib as L
+from . import rsetup
+
+
+def _p(a, t=C.c_double):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _f64(a, order="C"):
+    return np.require(a, dtype=np.float64, requirements=["F" if order == "F" else "C", "A"])
+
+
+def make_param(tol=0.02, tolPCG=1e-5, seed=200, maxiter=20, maxiterPCG=500, no_iteration=False, nrun=30,
+               num_marker=30, traceCVcutoff=0.0025, ratioCVcutoff=0.001, verbose=False, indent="", **_ignored) -> L.Param:
+    """The `param` list of R/saige_main.r:442-453 (num.thread has no meaning on the GPU and is ignored)."""
+    return L.Param(tol, tolPCG, int(seed), int(maxiter), int(maxiterPCG), int(bool(no_iteration)), int(nrun),
+                   int(num_marker), traceCVcutoff, ratioCVcutoff, int(bool(verbose)), indent.encode())
+
+
+class Context:
+    """One GPU, one shard of variants: the state kept in file-scope statics at saige_fitnull.cpp:122-131."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        L.check(L.lib().sgb_ctx_create(C.byref(self._h), C.c_int(device)))
+        self.device = device
+        self.n_samp = self.n_var = self.n_var_total = 0
+        self.var_offset = 0
+        self.rank, self.world = 0, 1
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.lib().sgb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- configuration ----
+    def set_kernel(self, name: str):
+        L.check(L.lib().sgb_set_kernel(self._h, C.c_int(L.KERNEL[name])))
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        L.check(L.lib().sgb_comm_init(self._h, buf, C.c_int(rank), C.c_int(world)))
+        self.rank, self.world = rank, world
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_ubyte * 128)()
+        L.check(L.lib().sgb_comm_unique_id(buf))
+        return bytes(buf)
+
+    # ---- saige_store_2b_geno ----
+    def saige_store_2b_geno(self, rawgeno: np.ndarray, num_samp: int, n_variant_total: int | None = None,
+                            variant_offset: int = 0):
+        """rawgeno: uint8 [n_variant_local][ceil(num_samp/4)] -- the transpose of R's RawMatrix, i.e. the same
+        bytes in memory.  Returns (buf_std_geno [M][4], buf_diag_grm [N]) as the reference fills them."""
+        g = np.require(rawgeno, dtype=np.uint8, requirements=["C", "A"])
+        if g.ndim != 2:
+            raise L.InvalidArgument(L.SGB_ERR_INVALID, "rawgeno must be a 2-d uint8 array")
+        m, nb = g.shape
+        total = m if n_variant_total is None else int(n_variant_total)
+        lut = np.empty((m, 4))
+        diag = np.empty(int(num_samp))
+        L.check(L.lib().sgb_store_2b_geno(self._h, _p(g, C.c_ubyte), C.c_int64(num_samp), C.c_int64(nb), C.c_int64(m),
+                                          C.c_int64(total), C.c_int64(variant_offset), _p(lut), _p(diag)))
+        self.n_samp, self.n_var, self.n_var_total, self.var_offset = int(num_samp), m, total, variant_offset
+        return lut, diag
+
+    def store_synthetic(self, n_samp: int, n_variant_local: int, n_variant_total: int | None = None,
+                        variant_offset: int = 0, seed: int = 200, missing_rate: float = 0.005, want_outputs=False):
+        """Generate the SURVEY section 8(d) synthetic genotypes directly in HBM and store them."""
+        total = n_variant_local if n_variant_total is None else int(n_variant_total)
+        ptr = C.c_void_p()
+        L.check(L.lib().sgb_synth_geno_device(self._h, C.c_int64(n_samp), C.c_int64(n_variant_local),
+                                              C.c_int64(variant_offset), C.c_uint64(seed), C.c_double(missing_rate),
+                                              C.byref(ptr)))
+        nb = (n_samp + 3) // 4
+        lut = np.empty((n_variant_local, 4)) if want_outputs else None
+        diag = np.empty(n_samp) if want_outputs else None
+        L.check(L.lib().sgb_store_2b_geno_device(self._h, ptr, C.c_int(1), C.c_int64(n_samp), C.c_int64(nb),
+                                                 C.c_int64(n_variant_local), C.c_int64(total), C.c_int64(variant_offset),
+                                                 _p(lut) if want_outputs else None, _p(diag) if want_outputs else None))
+        self.n_samp, self.n_var, self.n_var_total, self.var_offset = n_samp, n_variant_local, total, variant_offset
+        return lut, diag
+
+    def synth_to_host(self, n_samp: int, n_variant_local: int, variant_offset: int = 0, seed: int = 200,
+                      missing_rate: float = 0.005) -> np.ndarray:
+        """The same synthetic bytes as store_synthetic, copied to the host (so the oracle can consume them)."""
+        ptr = C.c_void_p()
+        L.check(L.lib().sgb_synth_geno_device(self._h, C.c_int64(n_samp), C.c_int64(n_variant_local),
+                                              C.c_int64(variant_offset), C.c_uint64(seed), C.c_double(missing_rate),
+                                              C.byref(ptr)))
+        nb = (n_samp + 3) // 4
+        out = np.empty((n_variant_local, nb), dtype=np.uint8)
+        L.check(L.lib().sgb_copy_from_device(self._h, _p(out, C.c_ubyte), ptr, C.c_int64(out.nbytes)))
+        L.check(L.lib().sgb_free_device(self._h, ptr))
+        return out
+
+    def allele_counts(self):
+        nv = np.empty(self.n_var, dtype=np.int32)
+        sm = np.empty(self.n_var, dtype=np.int32)
+        L.check(L.lib().sgb_allele_counts(self._h, _p(nv, C.c_int32), _p(sm, C.c_int32)))
+        return nv, sm
+
+    def get_geno_ds(self, snp_idx: int) -> np.ndarray:
+        ds = np.empty(self.n_samp)
+        L.check(L.lib().sgb_get_geno_ds(self._h, C.c_int64(snp_idx), _p(ds)))
+        return ds
+
+    # ---- products and solves ----
+    def get_crossprod_b_grm(self, b: np.ndarray) -> np.ndarray:
+        """(1/M) G G' b for one vector [N] or k vectors [N, k] (host in, host out)."""
+        b = np.asarray(b, dtype=np.float64)
+        one = b.ndim == 1
+        bb = _f64(b.reshape(self.n_samp, -1), "F")
+        out = np.empty_like(bb, order="F")
+        L.check(L.lib().sgb_grm_mv(self._h, _p(bb), _p(out), C.c_int(bb.shape[1])))
+        return out[:, 0].copy() if one else out
+
+    def get_diag_sigma(self, w, tau) -> np.ndarray:
+        w, tau = _f64(w), _f64(tau)
+        out = np.empty(self.n_samp)
+        L.check(L.lib().sgb_diag_sigma(self._h, _p(w), _p(tau), _p(out)))
+        return out
+
+    def PCG_diag_sigma(self, w, tau, b, maxiterPCG=500, tolPCG=1e-5):
+        """Returns (x, iterations); b may be [N] or [N, k] (k independent solves in lock-step)."""
+        w, tau = _f64(w), _f64(tau)
+        b = np.asarray(b, dtype=np.float64)
+        one = b.ndim == 1
+        bb = _f64(b.reshape(self.n_samp, -1), "F")
+        k = bb.shape[1]
+        x = np.empty_like(bb, order="F")
+        it = np.zeros(k, dtype=np.int32)
+        L.check(L.lib().sgb_pcg(self._h, _p(w), _p(tau), _p(bb), C.c_int(k), C.c_int(maxiterPCG), C.c_double(tolPCG),
+                                _p(x), _p(it, C.c_int)))
+        return (x[:, 0].copy(), int(it[0])) if one else (x, it)
+
+    # ---- fits ----
+    def _fit(self, fn, fit0: rsetup.Fit0, X, tau, param):
+        X = _f64(X, "F")
+        n, p = X.shape
+        y, eta, mu, coef = _f64(fit0.y), _f64(fit0.linear_predictors), _f64(fit0.fitted_values), _f64(fit0.coefficients)
+        off = None if fit0.offset is None else _f64(fit0.offset)
+        f = L.Fit0(n, p, _p(y), _p(off) if off is not None else None, _p(eta), _p(mu), _p(coef), L.FAMILY[fit0.family])
+        o = dict(coefficients=np.empty(p), linear_predictors=np.empty(n), fitted_values=np.empty(n), residuals=np.empty(n),
+                 cov=np.empty((p, p), order="F"))
+        g = L.Glmm(_p(o["coefficients"]), (C.c_double * 2)(), _p(o["linear_predictors"]), _p(o["fitted_values"]),
+                   _p(o["residuals"]), _p(o["cov"]), 0)
+        tau = _f64(tau)
+        L.check(fn(self._h, C.byref(f), _p(X), _p(tau), C.byref(param), C.byref(g)))
+        o["tau"] = np.array([g.tau[0], g.tau[1]])
+        o["converged"] = bool(g.converged)
+        return o
+
+    def saige_fit_AI_PCG_binary(self, fit0, X, tau, param=None):
+        return self._fit(L.lib().sgb_fit_AI_PCG_binary, fit0, X, tau, param or make_param())
+
+    def saige_fit_AI_PCG_quant(self, fit0, X, tau, param=None):
+        return self._fit(L.lib().sgb_fit_AI_PCG_quant, fit0, X, tau, param or make_param())
+
+    def _var_ratio(self, fn, fit0, glmm_tau, noK: rsetup.ObjNoK, param, marker_list, cap=4096):
+        n = len(fit0.y)
+        X1, XV, XXVX_inv = _f64(noK.X1, "F"), _f64(noK.XV, "F"), _f64(noK.XXVX_inv, "F")
+        p = X1.shape[1]
+        y, eta, mu, coef = _f64(fit0.y), _f64(fit0.linear_predictors), _f64(fit0.fitted_values), _f64(fit0.coefficients)
+        f = L.Fit0(n, p, _p(y), None, _p(eta), _p(mu), _p(coef), L.FAMILY[fit0.family])
+        nk = L.NoK(p, _p(X1), _p(XV), _p(XXVX_inv))
+        ml = np.require(marker_list, dtype=np.int32, requirements=["C"])
+        oid = np.empty(cap, dtype=np.int32)
+        cols = [np.empty(cap) for _ in range(5)]
+        vr = L.VarRatio(cap, 0, _p(oid, C.c_int), *[_p(c) for c in cols])
+        tau = _f64(glmm_tau)
+        L.check(fn(self._h, C.byref(f), _p(tau), C.byref(nk), C.byref(param), _p(ml, C.c_int32), C.c_int64(len(ml)),
+                   C.byref(vr)))
+        k = vr.n
+        return dict(id=oid[:k].copy(), maf=cols[0][:k].copy(), mac=cols[1][:k].copy(), var1=cols[2][:k].copy(),
+                    var2=cols[3][:k].copy(), ratio=cols[4][:k].copy())
+
+    def saige_calc_var_ratio_binary(self, fit0, glmm, noK, param, marker_list):
+        return self._var_ratio(L.lib().sgb_calc_var_ratio_binary, fit0, glmm["tau"], noK, param or make_param(), marker_list)
+
+    def saige_calc_var_ratio_quant(self, fit0, glmm, noK, param, marker_list):
+        return self._var_ratio(L.lib().sgb_calc_var_ratio_quant, fit0, glmm["tau"], noK, param or make_param(), marker_list)
+
+    # ---- R RNG ----
+    def set_seed(self, seed: int):
+        L.check(L.lib().sgb_r_set_seed(self._h, C.c_uint32(seed)))
+
+    def runif(self, n: int) -> np.ndarray:
+        out = np.empty(n)
+        L.check(L.lib().sgb_r_unif_rand(self._h, C.c_int64(n), _p(out)))
+        return out
+
+    def sample_int(self, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.int32)
+        L.check(L.lib().sgb_r_sample_int(self._h, C.c_int32(n), _p(out, C.c_int32)))
+        return out
+
+    # ---- instrumentation / device buffers (bench.py) ----
+    def stats(self) -> dict:
+        s = L.Stats()
+        L.check(L.lib().sgb_get_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
+    def reset_stats(self):
+        L.check(L.lib().sgb_reset_stats(self._h))
+
+    def set_profiling(self, on: bool):
+        L.check(L.lib().sgb_set_profiling(self._h, C.c_int(int(on))))
+
+    def kernel_times(self) -> dict:
+        """{kernel name: (total ms, launches)} accumulated since set_profiling(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        L.check(L.lib().sgb_kernel_times(self._h, buf, C.c_int64(len(buf))))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, cnt = line.split()
+            out[name] = (float(ms), int(cnt))
+        return out
+
+    def device_vector(self, host: np.ndarray) -> "DeviceArray":
+        host = _f64(host, "F")
+        d = DeviceArray(self, host.nbytes)
+        L.check(L.lib().sgb_copy_to_device(self._h, d.ptr, _p(host), C.c_int64(host.nbytes)))
+        return d
+
+    def device_empty(self, nbytes: int) -> "DeviceArray":
+        return DeviceArray(self, nbytes)
+
+    def time_products_device(self, b: "DeviceArray", out: "DeviceArray", k: int, reps: int) -> float:
+        ms = C.c_float(0)
+        L.check(L.lib().sgb_time_products_device(self._h, b.ptr, out.ptr, C.c_int(k), C.c_int(reps), C.byref(ms)))
+        return float(ms.value)
+
+    def grm_mv_device(self, b: "DeviceArray", out: "DeviceArray", k: int = 1):
+        L.check(L.lib().sgb_grm_mv_device(self._h, b.ptr, out.ptr, C.c_int(k)))
+
+
+class DeviceArray:
+    def __init__(self, ctx: Context, nbytes: int):
+        self.ctx, self.nbytes = ctx, nbytes
+        self.ptr = C.c_void_p()
+        L.check(L.lib().sgb_malloc_device(ctx._h, C.c_int64(nbytes), C.byref(self.ptr)))
+
+    def to_host(self, shape, dtype=np.float64, order="F") -> np.ndarray:
+        out = np.empty(shape, dtype=dtype, order=order)
+        L.check(L.lib().sgb_copy_from_device(self.ctx._h, out.ctypes.data_as(C.c_void_p), self.ptr, C.c_int64(out.nbytes)))
+        return out
+
+    def free(self):
+        if self.ptr:
+            L.lib().sgb_free_device(self.ctx._h, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.free()
+        except Exception:
+            pass
+
+
+_default_ctx: Context | None = None
+
+
+def default_context() -> Context:
+    """Process-global context: the analogue of the reference's file-scope state (not re-entrant either)."""
+    global _default_ctx
+    if _default_ctx is None:
+        import os
+        _default_ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default_ctx
+
+
+@dataclass
+class NullModel:
+    """The `ClassSAIGE_NullModel` list assembled at R/saige_main.r:516-628."""
+    coefficients: np.ndarray
+    tau: np.ndarray
+    linear_predictors: np.ndarray
+    fitted_values: np.ndarray
+    residuals: np.ndarray
+    cov: np.ndarray
+    converged: bool
+    obj_noK: rsetup.ObjNoK
+    var_ratio: dict
+    trait_type: str
+    sample_id: np.ndarray | None = None
+    variant_id: np.ndarray | None = None
+
+
+def seqFitNullGLMM_SPA(formula: str, data: dict, packed_geno: np.ndarray, trait_type="binary", sample_id=None,
+                       variant_id=None, inv_norm=True, X_transform=True, tol=0.02, maxiter=20, nrun=30, tolPCG=1e-5,
+                       maxiterPCG=500, num_marker=30, tau_init=(0, 0), traceCVcutoff=0.0025, ratioCVcutoff=0.001,
+                       seed=200, verbose=False, ctx: Context | None = None) -> NullModel:
+    """Mirror of seqFitNullGLMM_SPA (R/saige_main.r:223-654) for data already in memory.
+
+    `packed_geno` replaces the GDS file + SeqArray:::.seqGet2bGeno (R/saige_main.r:420): a uint8 array
+    [n_variant][ceil(n_samp/4)] in the 2-bit format.  Sample/variant filtering, which the reference does
+    through SeqArray (:305-333), is the caller's job.  `geno.sparse` does not exist here: the dense 2-bit
+    path is the only one (same GRM).
+    """
+    if trait_type not in ("binary", "quantitative"):
+        raise ValueError("Invalid 'trait.type'.")
+    ctx = ctx or default_context()
+    phenovar, terms, intercept = rsetup.parse_formula(formula)
+    y = np.asarray(data[phenovar], dtype=np.float64)
+    n = len(y)
+    X = rsetup.model_matrix(data, terms, intercept)
+    if X.shape[1] <= 1:
+        X_transform = False
+    X_qrr = None
+    if X_transform:
+        X, X_qrr = rsetup.qr_transform(X)                                   # :378-380
+    ctx.saige_store_2b_geno(packed_geno, n)                                 # :437
+    n_var = ctx.n_var_total
+    param = make_param(tol=tol, tolPCG=tolPCG, seed=seed, maxiter=maxiter, maxiterPCG=maxiterPCG, nrun=nrun,
+                       num_marker=num_marker, traceCVcutoff=traceCVcutoff, ratioCVcutoff=ratioCVcutoff, verbose=verbose)
+    if trait_type == "binary":
+        if len(np.unique(y)) != 2:
+            raise ValueError("The outcome variable has more than 2 categories!")
+        fit0 = rsetup.glm_binomial(X, y)                                    # :480
+        noK = rsetup.null_model_binary(X, fit0)                             # :488
+        tau = rsetup.initial_tau_binary(tau_init)                           # :491-497
+        glmm = ctx.saige_fit_AI_PCG_binary(fit0, X, tau, param)             # :501
+        ctx.set_seed(seed)                                                  # :509
+        vr = ctx.saige_calc_var_ratio_binary(fit0, glmm, noK, param, ctx.sample_int(n_var))
+    else:
+        if inv_norm:                                                        # :536-548
+            f = rsetup.glm_gaussian(X, y)
+            y = rsetup.rank_norm(f.residuals) * rsetup.sd(f.residuals)
+        fit0 = rsetup.glm_gaussian(X, y)                                    # :551
+        noK = rsetup.null_model_quant(X, fit0)                              # :560-570
+        tau = rsetup.initial_tau_quant(fit0, tau_init)                      # :573-583
+        glmm = ctx.saige_fit_AI_PCG_quant(fit0, noK.X1, tau, param)         # :586
+        ctx.set_seed(seed)                                                  # :594
+        vr = ctx.saige_calc_var_ratio_quant(fit0, glmm, noK, param, ctx.sample_int(n_var))
+    order = np.argsort(vr["id"], kind="stable")                             # :512-513
+    vr = {k: v[order] for k, v in vr.items()}
+    if variant_id is not None:
+        vr["id"] = np.asarray(variant_id)[vr["id"] - 1]
+    coef = glmm["coefficients"]
+    if X_transform:
+        coef = np.linalg.solve(X_qrr, coef * np.sqrt(n))                    # :620
+    return NullModel(coefficients=coef, tau=glmm["tau"], linear_predictors=glmm["linear_predictors"],
+                     fitted_values=glmm["fitted_values"], residuals=glmm["residuals"], cov=glmm["cov"],
+                     converged=glmm["converged"], obj_noK=noK, var_ratio=vr, trait_type=trait_type,
+                     sample_id=None if sample_id is None else np.asarray(sample_id),
+                     variant_id=None if variant_id is None else np.asarray(variant_id))

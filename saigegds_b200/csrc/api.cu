@@ -1,0 +1,323 @@
+// extern "C" entry points of include/saigegds_b200.h: argument checks, exception -> status code.
+#include <cstring>
+
+#include "vecops.cuh"
+
+namespace sgb {
+void fit_AI_PCG(Context &c, bool quant, const sgb_fit0 *f, const double *hX, const double tau_in[2], const sgb_param *Pin,
+                sgb_glmm *out);
+void calc_var_ratio(Context &c, bool quant, const sgb_fit0 *f, const double tau_in[2], const sgb_noK *noK,
+                    const sgb_param *Pin, const int32_t *marker_list, int64_t n_marker, sgb_var_ratio *out);
+}  // namespace sgb
+
+struct sgb_context : sgb::Context {};
+
+namespace {
+
+thread_local std::string g_last_error;
+
+template <typename F>
+int guarded(sgb_context *ctx, F &&fn, bool need_ctx = true) {
+    try {
+        if (need_ctx) {
+            if (!ctx) throw sgb::Error(SGB_ERR_INVALID, "context is NULL");
+            SGB_CUDA(cudaSetDevice(ctx->dev));
+        }
+        fn();
+        return SGB_OK;
+    } catch (const sgb::Error &e) {
+        g_last_error = e.what();
+        return e.code;
+    } catch (const std::exception &e) {
+        g_last_error = e.what();
+        return SGB_ERR_INVALID;
+    }
+}
+
+void store_common(sgb::Context &c, int64_t n_samp, int64_t nb, int64_t m_local, int64_t m_total, int64_t offset) {
+    if (n_samp < 1 || m_local < 1) throw sgb::Error(SGB_ERR_INVALID, "empty genotype matrix");
+    if (nb != (n_samp + 3) / 4) throw sgb::Error(SGB_ERR_INVALID, "n_bytes_per_variant must equal ceil(n_samp/4)");
+    if (m_total < m_local || offset < 0 || offset + m_local > m_total)
+        throw sgb::Error(SGB_ERR_INVALID, "inconsistent variant shard description");
+    if (c.world == 1 && m_total != m_local) throw sgb::Error(SGB_ERR_INVALID, "sharded store needs sgb_comm_init first");
+    sgb::imma_release(c);
+    c.stored = false;
+    c.N = n_samp; c.NB = nb; c.M = m_local; c.M_total = m_total; c.var_offset = offset;
+}
+
+void store_outputs(sgb::Context &c, double *buf_std_geno, double *buf_diag_grm) {
+    if (buf_std_geno) c.d2h(buf_std_geno, c.lut.get(), sizeof(double) * 4 * c.M);
+    if (buf_diag_grm) c.d2h(buf_diag_grm, c.diag.get(), sizeof(double) * c.N);
+    c.sync();
+    c.stored = true;
+    sgb::imma_prepare(c);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *sgb_last_error(void) { return g_last_error.c_str(); }
+
+int sgb_ctx_create(sgb_context **out, int device_ordinal) {
+    return guarded(nullptr, [&] {
+        if (!out) throw sgb::Error(SGB_ERR_INVALID, "out is NULL");
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0)
+            throw sgb::Error(SGB_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                                               "); this library has no CPU fallback");
+        if (device_ordinal < 0 || device_ordinal >= n) throw sgb::Error(SGB_ERR_INVALID, "device ordinal out of range");
+        SGB_CUDA(cudaSetDevice(device_ordinal));
+        sgb_context *c = new sgb_context();
+        c->dev = device_ordinal;
+        cudaDeviceProp prop;
+        SGB_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
+        c->sm_count = prop.multiProcessorCount;
+        SGB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        SGB_CUDA(cudaEventCreate(&c->ev0));
+        SGB_CUDA(cudaEventCreate(&c->ev1));
+        SGB_CUDA(cudaEventCreate(&c->pev0));
+        SGB_CUDA(cudaEventCreate(&c->pev1));
+        *out = c;
+    }, false);
+}
+
+int sgb_ctx_destroy(sgb_context *ctx) {
+    return guarded(ctx, [&] {
+        cudaStreamSynchronize(ctx->stream);
+        sgb::imma_release(*ctx);
+        sgb::comm_destroy(*ctx);
+        cudaEventDestroy(ctx->ev0);
+        cudaEventDestroy(ctx->ev1);
+        cudaEventDestroy(ctx->pev0);
+        cudaEventDestroy(ctx->pev1);
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+    });
+}
+
+int sgb_set_callbacks(sgb_context *ctx, void (*print_fn)(const char *),
+                      void (*rademacher_fn)(void *, int, int, int64_t, int8_t *), void *user) {
+    return guarded(ctx, [&] { ctx->print_fn = print_fn; ctx->rademacher_fn = rademacher_fn; ctx->cb_user = user; });
+}
+
+int sgb_set_kernel(sgb_context *ctx, int kernel) {
+    return guarded(ctx, [&] {
+        if (kernel < SGB_KERNEL_AUTO || kernel > SGB_KERNEL_IMMA) throw sgb::Error(SGB_ERR_INVALID, "unknown kernel id");
+        ctx->kernel = kernel;
+    });
+}
+
+int sgb_comm_unique_id(unsigned char id[128]) {
+    return guarded(nullptr, [&] { sgb::comm_unique_id(id); }, false);
+}
+
+int sgb_comm_init(sgb_context *ctx, const unsigned char id[128], int rank, int world_size) {
+    return guarded(ctx, [&] { sgb::comm_init(*ctx, id, rank, world_size); });
+}
+
+int sgb_store_2b_geno(sgb_context *ctx, const uint8_t *packed, int64_t n_samp, int64_t n_bytes_per_variant,
+                      int64_t n_variant_local, int64_t n_variant_total, int64_t variant_offset, double *buf_std_geno,
+                      double *buf_diag_grm) {
+    return guarded(ctx, [&] {
+        if (!packed) throw sgb::Error(SGB_ERR_INVALID, "packed is NULL");
+        store_common(*ctx, n_samp, n_bytes_per_variant, n_variant_local, n_variant_total, variant_offset);
+        sgb::DevBuf<uint8_t> raw;
+        const size_t bytes = (size_t)n_bytes_per_variant * n_variant_local;
+        raw.ensure(bytes);
+        ctx->h2d(raw.get(), packed, bytes);
+        sgb::store_device_layout(*ctx, raw.get(), (size_t)n_bytes_per_variant);
+        store_outputs(*ctx, buf_std_geno, buf_diag_grm);
+    });
+}
+
+int sgb_store_2b_geno_device(sgb_context *ctx, uint8_t *packed_device, int take_ownership, int64_t n_samp,
+                             int64_t n_bytes_per_variant, int64_t n_variant_local, int64_t n_variant_total,
+                             int64_t variant_offset, double *buf_std_geno, double *buf_diag_grm) {
+    return guarded(ctx, [&] {
+        if (!packed_device) throw sgb::Error(SGB_ERR_INVALID, "packed_device is NULL");
+        store_common(*ctx, n_samp, n_bytes_per_variant, n_variant_local, n_variant_total, variant_offset);
+        sgb::store_device_layout(*ctx, packed_device, (size_t)n_bytes_per_variant);
+        if (take_ownership) SGB_CUDA(cudaFree(packed_device));
+        store_outputs(*ctx, buf_std_geno, buf_diag_grm);
+    });
+}
+
+int sgb_allele_counts(sgb_context *ctx, int32_t *n_valid, int32_t *sum) {
+    return guarded(ctx, [&] {
+        ctx->require_stored();
+        if (n_valid) ctx->d2h(n_valid, ctx->n_valid.get(), sizeof(int32_t) * ctx->M);
+        if (sum) ctx->d2h(sum, ctx->sum.get(), sizeof(int32_t) * ctx->M);
+        ctx->sync();
+    });
+}
+
+int sgb_get_geno_ds(sgb_context *ctx, int64_t snp_idx, double *ds) {
+    return guarded(ctx, [&] {
+        ctx->require_stored();
+        if (snp_idx < 0 || snp_idx >= ctx->M || !ds) throw sgb::Error(SGB_ERR_INVALID, "variant index out of range");
+        ctx->ws_vec.ensure(ctx->N);
+        sgb::decode_variant(*ctx, snp_idx, ctx->ws_vec.get());
+        ctx->d2h(ds, ctx->ws_vec.get(), sizeof(double) * ctx->N);
+        ctx->sync();
+    });
+}
+
+int sgb_grm_mv_device(sgb_context *ctx, const double *b_device, double *out_device, int k) {
+    return guarded(ctx, [&] {
+        if (!b_device || !out_device || k < 1) throw sgb::Error(SGB_ERR_INVALID, "invalid arguments");
+        SGB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        sgb::grm_mv_device(*ctx, b_device, out_device, k);
+        SGB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        ctx->sync();
+        float ms = 0;
+        SGB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->stats.last_product_ms = ms;
+    });
+}
+
+int sgb_grm_mv(sgb_context *ctx, const double *b, double *out, int k) {
+    return guarded(ctx, [&] {
+        ctx->require_stored();
+        if (!b || !out || k < 1) throw sgb::Error(SGB_ERR_INVALID, "invalid arguments");
+        const size_t n = (size_t)ctx->N * k;
+        sgb::DevBuf<double> &db = ctx->io_in, &dout = ctx->io_out;
+        db.ensure(n); dout.ensure(n);
+        ctx->h2d(db.get(), b, sizeof(double) * n);
+        SGB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        sgb::grm_mv_device(*ctx, db.get(), dout.get(), k);
+        SGB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        ctx->d2h(out, dout.get(), sizeof(double) * n);
+        ctx->sync();
+        float ms = 0;
+        SGB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->stats.last_product_ms = ms;
+    });
+}
+
+int sgb_diag_sigma(sgb_context *ctx, const double *w, const double tau[2], double *out) {
+    return guarded(ctx, [&] {
+        ctx->require_stored();
+        sgb::DevBuf<double> dw, dout;
+        dw.ensure(ctx->N); dout.ensure(ctx->N);
+        ctx->h2d(dw.get(), w, sizeof(double) * ctx->N);
+        sgb::diag_sigma(*ctx, dw.get(), tau[0], tau[1], dout.get(), false);
+        ctx->d2h(out, dout.get(), sizeof(double) * ctx->N);
+        ctx->sync();
+    });
+}
+
+int sgb_pcg(sgb_context *ctx, const double *w, const double tau[2], const double *b, int k, int maxiterPCG, double tolPCG,
+            double *x, int *iters) {
+    return guarded(ctx, [&] {
+        ctx->require_stored();
+        if (!w || !tau || !b || !x || k < 1) throw sgb::Error(SGB_ERR_INVALID, "invalid arguments");
+        const size_t n = (size_t)ctx->N * k;
+        sgb::DevBuf<double> dw, db, dx;
+        dw.ensure(ctx->N); db.ensure(n); dx.ensure(n);
+        ctx->h2d(dw.get(), w, sizeof(double) * ctx->N);
+        ctx->h2d(db.get(), b, sizeof(double) * n);
+        sgb::PcgWork ws;
+        sgb::pcg_solve(*ctx, ws, dw.get(), tau[0], tau[1], db.get(), k, maxiterPCG, tolPCG, dx.get(), iters);
+        ctx->d2h(x, dx.get(), sizeof(double) * n);
+        ctx->sync();
+    });
+}
+
+int sgb_fit_AI_PCG_binary(sgb_context *ctx, const sgb_fit0 *fit0, const double *X, const double tau[2], const sgb_param *param,
+                          sgb_glmm *out) {
+    return guarded(ctx, [&] { sgb::fit_AI_PCG(*ctx, false, fit0, X, tau, param, out); });
+}
+
+int sgb_fit_AI_PCG_quant(sgb_context *ctx, const sgb_fit0 *fit0, const double *X, const double tau[2], const sgb_param *param,
+                         sgb_glmm *out) {
+    return guarded(ctx, [&] { sgb::fit_AI_PCG(*ctx, true, fit0, X, tau, param, out); });
+}
+
+int sgb_calc_var_ratio_binary(sgb_context *ctx, const sgb_fit0 *fit0, const double tau[2], const sgb_noK *noK,
+                              const sgb_param *param, const int32_t *marker_list, int64_t n_marker, sgb_var_ratio *out) {
+    return guarded(ctx, [&] { sgb::calc_var_ratio(*ctx, false, fit0, tau, noK, param, marker_list, n_marker, out); });
+}
+
+int sgb_calc_var_ratio_quant(sgb_context *ctx, const sgb_fit0 *fit0, const double tau[2], const sgb_noK *noK,
+                             const sgb_param *param, const int32_t *marker_list, int64_t n_marker, sgb_var_ratio *out) {
+    return guarded(ctx, [&] { sgb::calc_var_ratio(*ctx, true, fit0, tau, noK, param, marker_list, n_marker, out); });
+}
+
+int sgb_r_set_seed(sgb_context *ctx, uint32_t seed) {
+    return guarded(ctx, [&] { ctx->rng.set_seed(seed); });
+}
+int sgb_r_unif_rand(sgb_context *ctx, int64_t n, double *out) {
+    return guarded(ctx, [&] { for (int64_t i = 0; i < n; i++) out[i] = ctx->rng.unif_rand(); });
+}
+int sgb_r_sample_int(sgb_context *ctx, int32_t n, int32_t *out) {
+    return guarded(ctx, [&] { ctx->rng.sample_int(n, out); });
+}
+
+int sgb_get_stats(sgb_context *ctx, sgb_stats *out) {
+    return guarded(ctx, [&] { *out = ctx->stats; });
+}
+int sgb_reset_stats(sgb_context *ctx) {
+    return guarded(ctx, [&] { ctx->stats = sgb_stats{}; });
+}
+
+int sgb_synth_geno_device(sgb_context *ctx, int64_t n_samp, int64_t n_variant_local, int64_t variant_offset, uint64_t seed,
+                          double missing_rate, uint8_t **packed_device) {
+    return guarded(ctx, [&] {
+        if (!packed_device || n_samp < 1 || n_variant_local < 1) throw sgb::Error(SGB_ERR_INVALID, "invalid arguments");
+        const size_t bytes = (size_t)((n_samp + 3) / 4) * n_variant_local;
+        uint8_t *p = nullptr;
+        SGB_CUDA(cudaMalloc((void **)&p, bytes));
+        try {
+            sgb::synth_geno(*ctx, n_samp, n_variant_local, variant_offset, seed, missing_rate, p);
+        } catch (...) {
+            cudaFree(p);
+            throw;
+        }
+        *packed_device = p;
+    });
+}
+
+int sgb_set_profiling(sgb_context *ctx, int on) {
+    return guarded(ctx, [&] { ctx->profiling = on != 0; if (on) ctx->ktimes.clear(); });
+}
+int sgb_kernel_times(sgb_context *ctx, char *buf, int64_t buf_size) {
+    return guarded(ctx, [&] {
+        std::string s;
+        for (auto &kv : ctx->ktimes) {
+            char line[256];
+            snprintf(line, sizeof(line), "%s %.6f %lld\n", kv.first.c_str(), kv.second.first, (long long)kv.second.second);
+            s += line;
+        }
+        if ((int64_t)s.size() + 1 > buf_size) throw sgb::Error(SGB_ERR_INVALID, "buffer too small");
+        memcpy(buf, s.c_str(), s.size() + 1);
+    });
+}
+
+int sgb_malloc_device(sgb_context *ctx, int64_t bytes, void **ptr_device) {
+    return guarded(ctx, [&] { SGB_CUDA(cudaMalloc(ptr_device, (size_t)bytes)); });
+}
+int sgb_free_device(sgb_context *ctx, void *ptr_device) {
+    return guarded(ctx, [&] { SGB_CUDA(cudaFree(ptr_device)); });
+}
+int sgb_copy_to_device(sgb_context *ctx, void *dst_device, const void *src_host, int64_t bytes) {
+    return guarded(ctx, [&] { ctx->h2d(dst_device, src_host, (size_t)bytes); ctx->sync(); });
+}
+int sgb_copy_from_device(sgb_context *ctx, void *dst_host, const void *src_device, int64_t bytes) {
+    return guarded(ctx, [&] { ctx->d2h(dst_host, src_device, (size_t)bytes); ctx->sync(); });
+}
+
+int sgb_time_products_device(sgb_context *ctx, const double *b_device, double *out_device, int k, int reps, float *total_ms) {
+    return guarded(ctx, [&] {
+        if (!b_device || !out_device || k < 1 || reps < 1 || !total_ms) throw sgb::Error(SGB_ERR_INVALID, "invalid arguments");
+        ctx->sync();
+        SGB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        for (int r = 0; r < reps; r++) sgb::grm_mv_device(*ctx, b_device, out_device, k);
+        SGB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        ctx->sync();
+        SGB_CUDA(cudaEventElapsedTime(total_ms, ctx->ev0, ctx->ev1));
+    });
+}
+
+}  // extern "C"

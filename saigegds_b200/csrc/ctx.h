@@ -1,0 +1,182 @@
+// Internal context and helpers of libsaigegds_b200 (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <map>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/saigegds_b200.h"
+#include "rrng.h"
+
+namespace sgb {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define SGB_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            throw sgb::Error(SGB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +    \
+                                               __FILE__ + ":" + std::to_string(__LINE__) + ")");          \
+    } while (0)
+
+#define SGB_CHECK_LAUNCH() SGB_CUDA(cudaGetLastError())
+
+// Owning device buffer (cudaMalloc / cudaFree), resizable without preserving contents.
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void ensure(size_t count) {
+        if (count <= n) return;
+        release();
+        SGB_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+        n = count;
+    }
+    T *get() const { return p; }
+};
+
+// Pinned host staging buffer
+template <typename T>
+struct PinBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+    void ensure(size_t count) {
+        if (count <= n) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        SGB_CUDA(cudaMallocHost((void **)&p, count * sizeof(T)));
+        n = count;
+    }
+};
+
+struct Comm;  // comm.cu (NCCL through dlopen)
+
+// Tiled int8-tensor-core layout of the genotype shard (grm_imma.cu)
+struct ImmaPlan;
+
+struct Context {
+    int dev = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    // ---- genotype shard (state of saige_fitnull.cpp:122-131) ----
+    int64_t N = 0;        // Geno_NumSamp
+    int64_t NB = 0;       // Geno_PackedNumSamp = ceil(N/4)
+    int64_t M = 0;        // local variants
+    int64_t M_total = 0;  // Geno_NumVariant across all ranks
+    int64_t var_offset = 0;
+    size_t pitch = 0;     // bytes per variant row on the device (NB rounded up to 16)
+    DevBuf<uint8_t> packed;   // [M][pitch], pad samples and pitch padding = code 3
+    DevBuf<double> lut;       // buf_std_geno [M][4]
+    DevBuf<double> diag;      // buf_diag_grm [N]
+    DevBuf<int32_t> n_valid, sum;   // reference allele counts (all NB bytes, incl. pad codes)
+    DevBuf<int32_t> cnt_num, cnt_sum;  // counts over samples < N only (get_geno_ds / f64_af_ac_impute semantics)
+    std::vector<int32_t> h_cnt_num, h_cnt_sum;
+    bool stored = false;
+
+    // ---- product workspaces ----
+    int kernel = SGB_KERNEL_AUTO;
+    DevBuf<double> ws_partial;  // SIMT: [n_chunk][M] partial dots
+    DevBuf<double> ws_tab;      // [M][4] per-variant apply table
+    DevBuf<double> ws_vec;      // scratch N x k
+    ImmaPlan *imma = nullptr;
+
+    // ---- generic reduction workspace ----
+    DevBuf<double> red_partial;
+    DevBuf<double> red_out;
+    DevBuf<unsigned int> red_counter;
+    PinBuf<double> h_scalars;
+    PinBuf<double> h_stage;    // pinned staging for host<->device vector copies
+
+    // ---- multi-GPU ----
+    Comm *comm = nullptr;
+    int rank = 0, world = 1;
+
+    // ---- host callbacks ----
+    void (*print_fn)(const char *) = nullptr;
+    void (*rademacher_fn)(void *, int, int, int64_t, int8_t *) = nullptr;
+    void *cb_user = nullptr;
+    RRng rng;
+
+    sgb_stats stats{};
+    DevBuf<double> io_in, io_out;   // persistent device buffers of the host-pointer entry points
+
+    // per-kernel CUDA-event timing (sgb_set_profiling): serialises the stream, use outside timed regions
+    bool profiling = false;
+    std::map<std::string, std::pair<double, int64_t>> ktimes;
+    cudaEvent_t pev0 = nullptr, pev1 = nullptr;
+    void prof_begin() { if (profiling) cudaEventRecord(pev0, stream); }
+    void prof_end(const char *name) {
+        if (!profiling) return;
+        cudaEventRecord(pev1, stream);
+        cudaEventSynchronize(pev1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, pev0, pev1);
+        auto &e = ktimes[name];
+        e.first += ms;
+        e.second += 1;
+    }
+
+    void printf(const char *fmt, ...) {
+        char buf[1024];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        if (print_fn) print_fn(buf);
+        else { fputs(buf, stdout); fflush(stdout); }
+    }
+    void require_stored() const {
+        if (!stored) throw Error(SGB_ERR_STATE, "no genotypes stored: call sgb_store_2b_geno first");
+    }
+    void sync() { SGB_CUDA(cudaStreamSynchronize(stream)); }
+    void h2d(void *dst, const void *src, size_t bytes) {
+        SGB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+    }
+    void d2h(void *dst, const void *src, size_t bytes) {
+        SGB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
+    }
+};
+
+// ---- store.cu ----
+void store_device_layout(Context &c, const uint8_t *src_device, size_t src_pitch);  // fills packed/lut/diag/counts
+void decode_variant(Context &c, int64_t local_idx, double *out_device);             // get_geno_ds, missing -> NaN
+void synth_geno(Context &c, int64_t n_samp, int64_t m_local, int64_t var_offset, uint64_t seed, double miss,
+                uint8_t *out_device);
+// ---- grm_simt.cu ----
+void simt_table_apply(Context &c, const double *tab_device, double *out_device, double scale);
+void simt_grm_mv(Context &c, const double *b_device, double *out_device);  // local shard, scaled by 1/M_total
+// ---- grm_imma.cu ----
+void imma_prepare(Context &c);
+void imma_release(Context &c);
+bool imma_available(const Context &c);
+void imma_grm_mv(Context &c, const double *b_device, double *out_device, int k);
+// ---- product dispatch (solver.cu) ----
+void grm_mv_device(Context &c, const double *b_device, double *out_device, int k);
+// ---- comm.cu ----
+void comm_unique_id(unsigned char id[128]);
+void comm_init(Context &c, const unsigned char id[128], int rank, int world);
+void comm_destroy(Context &c);
+void comm_allreduce_sum(Context &c, double *buf_device, size_t count);
+
+}  // namespace sgb

@@ -1,0 +1,250 @@
+"""GPU parity tests (pytest -m gpu): the CUDA library, called through its C-ABI, against the CPU oracle,
+the committed goldens of the reference, and size-independent properties at larger shapes.
+
+Tolerances (north star): integer work bit-exact; per-product vectors <= 1e-10 relative to the output's
+infinity norm; tau, variance ratio and fitted values <= 1e-6 relative (observed far tighter).
+"""
+import numpy as np
+import pytest
+
+from conftest import random_packed
+
+pytestmark = pytest.mark.gpu
+PROD_TOL = 1e-10
+FIT_TOL = 1e-6
+
+
+def relinf(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def gstore(gpu, fx):
+    lut, diag = gpu.saige_store_2b_geno(fx.packed, fx.n_samp)
+    return dict(lut=lut, diag=diag)
+
+
+# ---------------------------------------------------------------- store: counts, LUT, diag, decode
+def test_allele_counts_bit_exact(gpu, gstore, oracle):
+    nv, sm = gpu.allele_counts()
+    onv, osm = oracle.allele_counts()
+    assert np.array_equal(nv, onv) and np.array_equal(sm, osm)
+
+
+def test_lut_bit_exact_and_diag(gpu, gstore, oracle):
+    assert np.array_equal(gstore["lut"], oracle.lut)          # same IEEE operations on identical integers
+    assert relinf(gstore["diag"], oracle.diag) < 1e-13
+
+
+def test_decode_bit_exact(gpu, gstore, oracle):
+    for j in (0, 17, 9975):
+        a, b = gpu.get_geno_ds(j), oracle.get_geno_ds(j)
+        assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(np.nan_to_num(a), np.nan_to_num(b))
+
+
+@pytest.mark.parametrize("n_samp,n_var,missing", [(1, 3, 0.0), (7, 5, 0.3), (1001, 257, 0.05), (4099, 130, 0.02),
+                                                  (2048, 128, 0.0), (6150, 33, 0.5)])
+def test_ragged_shapes_missing_and_pad_codes(gpu, n_samp, n_var, missing):
+    """N % 4 != 0 with arbitrary pad codes, missing genotypes, monomorphic and all-missing variants."""
+    from oracle.oracle import Oracle
+    rng = np.random.default_rng(n_samp * 1000 + n_var)
+    packed = random_packed(rng, n_samp, n_var, missing)
+    if n_var >= 5:
+        packed[1, :] = 0x00        # monomorphic: af = 0 -> all-zero LUT (saige_fitnull.cpp:195-196)
+        packed[2, :] = 0xFF        # no valid call at all
+        packed[3, :] = 0xAA        # af = 1
+    o = Oracle()
+    olut, odiag = o.store_2b_geno(packed, n_samp)
+    lut, diag = gpu.saige_store_2b_geno(packed, n_samp)
+    nv, sm = gpu.allele_counts()
+    onv, osm = o.allele_counts()
+    assert np.array_equal(nv, onv) and np.array_equal(sm, osm)
+    assert np.array_equal(lut, olut)
+    assert relinf(diag, odiag) < 1e-12 or np.max(np.abs(odiag)) == 0
+    for j in range(min(n_var, 4)):
+        a, b = gpu.get_geno_ds(j), o.get_geno_ds(j)
+        assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(np.nan_to_num(a), np.nan_to_num(b))
+    b = rng.standard_normal(n_samp)
+    want = o.grm_mv(b)
+    got = gpu.get_crossprod_b_grm(b)
+    assert np.max(np.abs(got - want)) <= PROD_TOL * max(np.max(np.abs(want)), 1e-300) + 1e-300
+
+
+# ---------------------------------------------------------------- product
+def test_product_matches_oracle_on_fixture(gpu, gstore, oracle, fx):
+    gpu.saige_store_2b_geno(fx.packed, fx.n_samp)
+    rng = np.random.default_rng(1)
+    for scale in (1.0, 1e-6, 1e8):
+        b = rng.standard_normal(fx.n_samp) * scale
+        assert relinf(gpu.get_crossprod_b_grm(b), oracle.grm_mv(b)) < PROD_TOL
+    b = np.zeros(fx.n_samp)
+    assert np.all(gpu.get_crossprod_b_grm(b) == 0)
+    u = rng.integers(0, 2, fx.n_samp) * 2.0 - 1            # Rademacher vectors of the trace estimator
+    assert relinf(gpu.get_crossprod_b_grm(u), oracle.grm_mv(u)) < PROD_TOL
+    spike = np.zeros(fx.n_samp); spike[3] = 1e12; spike[500] = 1e-12   # wide dynamic range
+    assert relinf(gpu.get_crossprod_b_grm(spike), oracle.grm_mv(spike)) < PROD_TOL
+
+
+def test_product_multi_rhs_equals_single(gpu, fx, oracle):
+    gpu.saige_store_2b_geno(fx.packed, fx.n_samp)
+    rng = np.random.default_rng(2)
+    B = rng.standard_normal((fx.n_samp, 5))
+    out = gpu.get_crossprod_b_grm(B)
+    for k in range(5):
+        assert relinf(out[:, k], oracle.grm_mv(B[:, k])) < PROD_TOL
+
+
+@pytest.mark.parametrize("kernel", ["simt", "auto"])
+def test_product_properties_at_scale(gpu, kernel):
+    """N=50K, M=4K synthetic (too big for the scalar oracle in seconds): linearity, symmetry, PSD, and a
+    column-sampled check against the definition."""
+    n, m = 50000, 4000
+    gpu.set_kernel(kernel)
+    try:
+        lut, diag = gpu.store_synthetic(n, m, seed=7, missing_rate=0.01, want_outputs=True)
+        rng = np.random.default_rng(3)
+        x, y = rng.standard_normal(n), rng.standard_normal(n)
+        Ax, Ay = gpu.get_crossprod_b_grm(x), gpu.get_crossprod_b_grm(y)
+        Axy = gpu.get_crossprod_b_grm(2.5 * x - 0.5 * y)
+        assert relinf(Axy, 2.5 * Ax - 0.5 * Ay) < 1e-11                      # linearity
+        assert abs(y @ Ax - x @ Ay) / abs(y @ Ax) < 1e-10                    # symmetry
+        assert x @ Ax > 0                                                    # positive semi-definite
+        # definition on decoded columns: x'Ax = (1/M) sum_j (g_j'x)^2; e_i'A e_i = diag_i
+        tot = 0.0
+        for j in range(0, m, 400):
+            ds = gpu.get_geno_ds(j)
+            code = np.where(np.isnan(ds), 3, ds).astype(np.int64)
+            tot += (lut[j][code] @ x) ** 2
+        e = np.zeros(n); e[12345] = 1.0
+        assert abs(gpu.get_crossprod_b_grm(e)[12345] - diag[12345]) / diag[12345] < 1e-11
+        assert np.isfinite(tot)
+    finally:
+        gpu.set_kernel("auto")
+
+
+def test_synthetic_generator_is_shard_invariant(gpu):
+    full = gpu.synth_to_host(1003, 64, 0, seed=11)
+    part = gpu.synth_to_host(1003, 20, 30, seed=11)
+    assert np.array_equal(full[30:50], part)
+    codes = np.stack([(full >> s) & 3 for s in (0, 2, 4, 6)], axis=2).reshape(64, -1)
+    assert np.all(codes[:, 1003:] == 3)                      # pad codes are 3
+    assert 0.0 < np.mean(codes[:, :1003] == 3) < 0.02        # ~0.5 % missing
+
+
+# ---------------------------------------------------------------- diag sigma, PCG
+def test_diag_sigma_and_pcg_match_oracle(gpu, fx, oracle, setup_binary):
+    gpu.saige_store_2b_geno(fx.packed, fx.n_samp)
+    mu = setup_binary["fit0"].fitted_values
+    w = mu * (1 - mu)
+    tau = np.array([1.0, 0.5])
+    assert relinf(gpu.get_diag_sigma(w, tau), oracle.diag_sigma(w, tau)) < 1e-13
+    B = np.column_stack([setup_binary["X"], np.random.default_rng(4).standard_normal((fx.n_samp, 2))])
+    X, iters = gpu.PCG_diag_sigma(w, tau, B)
+    for k in range(B.shape[1]):
+        xo, ito = oracle.pcg(w, tau, B[:, k])
+        assert iters[k] == ito                               # same iterate sequence
+        assert relinf(X[:, k], xo) < 1e-10
+    x0, it0 = gpu.PCG_diag_sigma(w, np.array([1.0, 0.0]), B[:, 0])   # tau[1] == 0 skips the GRM product (:568)
+    xo, ito = oracle.pcg(w, [1.0, 0.0], B[:, 0])
+    assert it0 == ito and relinf(x0, xo) < 1e-12
+
+
+# ---------------------------------------------------------------- full fits against the reference's goldens
+def test_binary_fit_matches_reference_golden(gpu, fx, setup_binary):
+    gpu.saige_store_2b_geno(fx.packed, fx.n_samp)
+    s, g = setup_binary, fx.model
+    gpu.reset_stats()
+    r = gpu.saige_fit_AI_PCG_binary(s["fit0"], s["X"], s["tau"])
+    assert r["tau"][0] == 1.0 and abs(r["tau"][1] - g["tau"][1]) / g["tau"][1] < FIT_TOL
+    coef = np.linalg.solve(s["R"], r["coefficients"] * np.sqrt(fx.n_samp))
+    assert relinf(coef, g["coefficients"]) < FIT_TOL
+    assert relinf(r["cov"], g["cov"]) < FIT_TOL
+    assert relinf(r["fitted_values"], g["fitted_values"]) < FIT_TOL
+    assert relinf(r["linear_predictors"], g["linear_predictors"]) < FIT_TOL
+    assert relinf(r["residuals"], g["residuals"]) < FIT_TOL
+    assert r["converged"]
+    st = gpu.stats()
+    # 898 products in the reference; 180 of them (GRM u_i, identical in every AI step) are cached here
+    assert 0 < st["n_products"] <= 898
+
+
+def test_quant_fit_matches_reference_golden(gpu, fx, setup_quant):
+    gpu.saige_store_2b_geno(fx.packed, fx.n_samp)
+    s, g = setup_quant, fx.model_quant
+    r = gpu.saige_fit_AI_PCG_quant(s["fit0"], s["noK"].X1, s["tau"])
+    assert abs(r["tau"][0] - g["tau"][0]) / g["tau"][0] < FIT_TOL and r["tau"][1] == 0
+    assert relinf(r["cov"], g["cov"]) < FIT_TOL
+    assert relinf(r["fitted_values"], g["fitted_values"]) < FIT_TOL
+    assert r["converged"]
+
+
+@pytest.mark.parametrize("trait", ["binary", "quantitative"])
+def test_var_ratio_matches_reference_golden(gpu, fx, setup_binary, setup_quant, trait):
+    import saigegds_b200 as sg
+    gpu.saige_store_2b_geno(fx.packed, fx.n_samp)
+    s, g = (setup_binary, fx.model) if trait == "binary" else (setup_quant, fx.model_quant)
+    gpu.set_seed(200)
+    ml = gpu.sample_int(len(fx.packed))
+    fn = gpu.saige_calc_var_ratio_binary if trait == "binary" else gpu.saige_calc_var_ratio_quant
+    vr = fn(s["fit0"], {"tau": g["tau"]}, s["noK"], sg.make_param(), ml)
+    order = np.argsort(vr["id"])
+    assert np.array_equal(fx.variant_id[vr["id"][order] - 1], g["vr_id"])           # same 30 markers
+    assert np.array_equal(vr["mac"][order], g["vr_mac"]) and np.array_equal(vr["maf"][order], g["vr_maf"])
+    for k in ("var1", "var2", "ratio"):
+        assert relinf(vr[k][order], g["vr_" + k]) < FIT_TOL, k
+
+
+def test_driver_end_to_end_like_the_reference_test(fx):
+    """test.saige_fit_null_model (inst/unitTests/test_SAIGE.R:44-76), tolerance 1e-6 instead of 1e-4."""
+    import saigegds_b200 as sg
+    for trait, col, g in (("binary", "y", fx.model), ("quantitative", "yy", fx.model_quant)):
+        data = dict(fx.pheno)
+        glmm = sg.seqFitNullGLMM_SPA("%s ~ x1 + x2" % col, data, fx.packed, trait_type=trait, variant_id=fx.variant_id)
+        assert np.allclose(glmm.tau, g["tau"], rtol=FIT_TOL, atol=0)
+        assert np.allclose(glmm.coefficients, g["coefficients"], rtol=1e-5, atol=1e-9)
+        assert np.array_equal(glmm.var_ratio["id"], g["vr_id"])
+        assert np.allclose(glmm.var_ratio["ratio"], g["vr_ratio"], rtol=FIT_TOL)
+        assert np.allclose(glmm.fitted_values, g["fitted_values"], rtol=FIT_TOL, atol=1e-12)
+
+
+def test_fit_matches_oracle_with_missing_data(gpu):
+    """A fit on synthetic data with missing genotypes and N % 4 != 0 (never exercised by the reference's tests)."""
+    from oracle.oracle import Oracle, default_params
+    import saigegds_b200 as sg
+    from saigegds_b200 import rsetup
+    rng = np.random.default_rng(10)
+    n, m = 603, 1500
+    packed = random_packed(rng, n, m, missing=0.03, maf_lo=0.05)
+    x1 = rng.standard_normal(n)
+    y = (rng.random(n) < 1 / (1 + np.exp(-(-1 + 0.5 * x1)))).astype(np.float64)
+    X, _ = rsetup.qr_transform(rsetup.model_matrix({"x1": x1}, ["x1"]))
+    fit0 = rsetup.glm_binomial(X, y)
+    o = Oracle(); o.store_2b_geno(packed, n)
+    ro = o.fit_AI_PCG("binary", fit0, X, [1.0, 0.5], default_params(nrun=10, maxiter=6))
+    gpu.saige_store_2b_geno(packed, n)
+    rg = gpu.saige_fit_AI_PCG_binary(fit0, X, [1.0, 0.5], sg.make_param(nrun=10, maxiter=6))
+    assert np.allclose(rg["tau"], ro["tau"], rtol=FIT_TOL, atol=1e-12)
+    assert relinf(rg["fitted_values"], ro["fitted_values"]) < FIT_TOL
+    assert relinf(rg["cov"], ro["cov"]) < FIT_TOL
+
+
+# ---------------------------------------------------------------- RNG and error behaviour
+def test_r_rng_matches_oracle(gpu, oracle):
+    gpu.set_seed(42); oracle.set_seed(42)
+    assert np.array_equal(gpu.runif(1000), oracle.unif_rand(1000))
+    gpu.set_seed(200); oracle.set_seed(200)
+    assert np.array_equal(gpu.sample_int(9976), oracle.sample_int(9976))
+
+
+def test_error_behaviour(gpu, fx):
+    import saigegds_b200 as sg
+    c = sg.Context(0)
+    with pytest.raises(sg.SgbError):                       # product before store
+        c.n_samp = 4
+        c.get_crossprod_b_grm(np.zeros(4))
+    with pytest.raises(sg.InvalidArgument):                # wrong bytes-per-variant
+        c.saige_store_2b_geno(np.zeros((3, 5), dtype=np.uint8), 100)
+    with pytest.raises(sg.SgbError):
+        c.set_kernel("imma") or c.saige_store_2b_geno(fx.packed[:10], fx.n_samp) or c.get_crossprod_b_grm(np.ones(fx.n_samp))
+    c.close()

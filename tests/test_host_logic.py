@@ -1,0 +1,115 @@
+"""CPU tests of the host-side logic: R set-up restatement, C-ABI surface, sharding (gloo, world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.max(np.abs(b)))
+
+
+def test_rsetup_reproduces_golden_obj_noK(fx, setup_binary, setup_quant):
+    for s, g in ((setup_binary, fx.model), (setup_quant, fx.model_quant)):
+        noK = s["noK"]
+        for k in ("y", "mu", "res", "V", "X1", "XV", "XXVX_inv"):
+            assert rel(getattr(noK, k), g["noK_" + k]) < 1e-10, k
+
+
+def test_initial_tau(setup_binary, setup_quant):
+    assert list(setup_binary["tau"]) == [1.0, 0.5]
+    t = setup_quant["tau"]
+    assert t[0] == t[1] and t[0] > 0
+
+
+def test_parse_formula():
+    from saigegds_b200.rsetup import parse_formula
+    assert parse_formula("y ~ x1 + x2") == ("y", ["x1", "x2"], True)
+    assert parse_formula("y ~ x_0 + x_1 -1") == ("y", ["x_0", "x_1"], False)
+
+
+def test_shard_range_covers_everything():
+    from saigegds_b200 import shard_range
+    for m, w in ((10, 3), (100000, 8), (7, 8), (9976, 2)):
+        r = [shard_range(m, k, w) for k in range(w)]
+        assert r[0][0] == 0 and r[-1][1] == m
+        assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+        sizes = [b - a for a, b in r]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_library_exports_every_declared_symbol():
+    """The shared library must export exactly what include/saigegds_b200.h declares."""
+    from saigegds_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "saigegds_b200.h")).read()
+    declared = set(re.findall(r"\b(sgb_[a-zA-Z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in declared:
+        assert hasattr(lib, s), s
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import saigegds_b200 as sg
+    with pytest.raises(sg.SgbError) as e:
+        sg.Context(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "saigegds_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "saige_oracle" not in src, fn
+
+
+_WORKER = r"""
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, {root!r})
+from saigegds_b200 import shard_range
+from saigegds_b200.dist import allreduce_sum_numpy, broadcast_bytes
+from oracle.oracle import Oracle
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+d = np.load(os.path.join({root!r}, "tests", "golden", "grm1k_10k.npz"))
+packed = d["packed_all"][d["keep"]][:2001]; n = int(d["n_samp"]); m = len(packed)
+uid = broadcast_bytes(bytes(range(128)) if rank == 0 else None, 128, 0)
+assert uid == bytes(range(128))
+a, b = shard_range(m, rank, 2)
+o = Oracle(); o.store_2b_geno(packed[a:b], n)
+vec = np.random.default_rng(5).standard_normal(n)
+part = o.grm_mv(vec) * ((b - a) / m)          # local (1/M_local) -> contribution to (1/M_total)
+full = allreduce_sum_numpy(part)
+ref = Oracle(); ref.store_2b_geno(packed, n)
+want = ref.grm_mv(vec)
+err = np.max(np.abs(full - want)) / np.max(np.abs(want))
+assert err < 1e-12, err
+print("rank", rank, "ok", err)
+"""
+
+
+def test_sharded_product_equals_full_product_gloo(tmp_path):
+    """world_size-2 gloo run: variant shards + sum all-reduce reproduce the unsharded product."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=300)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o

@@ -1,0 +1,114 @@
+"""CPU tests: the oracle against the reference's own golden fixtures.
+
+These pin the oracle: tolerance 1e-10 (the reference's own RUnit tolerance is 1e-4,
+inst/unitTests/test_SAIGE.R:68-75).
+"""
+import numpy as np
+import pytest
+
+TOL = 1e-10
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def test_r_rng_known_answers(oracle):
+    # set.seed(42); runif(3) in R >= 3.6 with the default Mersenne-Twister
+    oracle.set_seed(42)
+    np.testing.assert_allclose(oracle.unif_rand(3), [0.914806043496355, 0.937075413297862, 0.286139534786344], rtol=1e-12)
+    oracle.set_seed(1)
+    np.testing.assert_allclose(oracle.unif_rand(2), [0.2655086631421, 0.3721238996368], rtol=1e-9)
+
+
+def test_allele_counts_and_af_match_golden(oracle, fx):
+    nv, sm = oracle.allele_counts()
+    assert np.all(nv == fx.n_samp)                     # the fixture has no missing calls
+    af = sm / (2.0 * nv)
+    assert np.max(np.abs(af - fx.af_alt_all[fx.keep])) == 0.0    # golden AF.alt of saige_pval.rds
+    assert len(nv) == 9976 == len(fx.model["variant_id"])
+
+
+def test_lut_definition(oracle, fx):
+    nv, sm = oracle.allele_counts()
+    af = sm / (2.0 * nv)
+    inv = 1 / np.sqrt(2 * af * (1 - af))
+    for k in range(3):
+        np.testing.assert_array_equal(oracle.lut[:, k], (k - 2 * af) * inv)
+    assert np.all(oracle.lut[:, 3] == 0)
+
+
+def test_product_matches_dense_algebra(oracle, fx):
+    rng = np.random.default_rng(0)
+    b = rng.standard_normal(fx.n_samp)
+    codes = np.stack([(fx.packed >> s) & 3 for s in (0, 2, 4, 6)], axis=2).reshape(len(fx.packed), -1)[:, :fx.n_samp]
+    G = np.take_along_axis(oracle.lut, codes.astype(np.int64), axis=1)      # [M][N] standardised
+    ref = G.T @ (G @ b) / len(G)
+    assert rel(oracle.grm_mv(b), ref) < 1e-12
+    assert rel(oracle.diag, (G * G).sum(axis=0) / len(G)) < 1e-12
+
+
+@pytest.fixture(scope="module")
+def fit_binary(oracle, setup_binary):
+    s = setup_binary
+    n0 = oracle.num_products
+    r = oracle.fit_AI_PCG("binary", s["fit0"], s["X"], s["tau"])
+    r["n_products"] = oracle.num_products - n0
+    return r
+
+
+@pytest.fixture(scope="module")
+def fit_quant(oracle, setup_quant):
+    s = setup_quant
+    n0 = oracle.num_products
+    r = oracle.fit_AI_PCG("quantitative", s["fit0"], s["X"], s["tau"])
+    r["n_products"] = oracle.num_products - n0
+    return r
+
+
+def test_binary_fit_matches_golden(fit_binary, setup_binary, fx):
+    g, r = fx.model, fit_binary
+    assert abs(r["tau"][0] - 1.0) == 0 and abs(r["tau"][1] - 0.33220628660290813) / 0.33220628660290813 < TOL
+    coef = np.linalg.solve(setup_binary["R"], r["coefficients"] * np.sqrt(fx.n_samp))
+    assert rel(coef, g["coefficients"]) < TOL
+    assert rel(r["cov"], g["cov"]) < TOL
+    assert rel(r["linear_predictors"], g["linear_predictors"]) < TOL
+    assert rel(r["fitted_values"], g["fitted_values"]) < TOL
+    assert rel(r["residuals"], g["residuals"]) < TOL
+    assert r["converged"]
+    assert r["n_products"] == 898
+
+
+def test_quant_fit_matches_golden(fit_quant, setup_quant, fx):
+    g, r = fx.model_quant, fit_quant
+    assert abs(r["tau"][0] - 0.9701726766660272) / 0.9701726766660272 < TOL and r["tau"][1] == 0
+    coef = np.linalg.solve(setup_quant["R"], r["coefficients"] * np.sqrt(fx.n_samp))
+    assert np.max(np.abs(coef - g["coefficients"])) < 1e-12
+    assert rel(r["cov"], g["cov"]) < TOL
+    assert rel(r["fitted_values"], g["fitted_values"]) < TOL
+    assert r["n_products"] == 1332
+
+
+@pytest.mark.parametrize("trait", ["binary", "quantitative"])
+def test_var_ratio_matches_golden(oracle, fx, setup_binary, setup_quant, trait):
+    s, g = (setup_binary, fx.model) if trait == "binary" else (setup_quant, fx.model_quant)
+    oracle.set_seed(200)
+    ml = oracle.sample_int(len(fx.packed))
+    vr = oracle.calc_var_ratio(trait, s["fit0"], g["tau"], s["noK"], ml)
+    order = np.argsort(vr["id"])
+    assert np.array_equal(fx.variant_id[vr["id"][order] - 1], g["vr_id"])
+    for k in ("maf", "mac", "var1", "var2", "ratio"):
+        assert rel(vr[k][order], g["vr_" + k]) < TOL, k
+    if trait == "binary":
+        assert abs(np.mean(vr["ratio"]) - 0.9410506662340412) < 1e-12
+
+
+def test_pcg_iteration_counts(oracle, fx, setup_binary):
+    """PCG stops on the absolute test sum(r*r) <= tolPCG (saige_fitnull.cpp:595): 3-4 iterations on the fixture."""
+    mu = setup_binary["fit0"].fitted_values
+    w = mu * (1 - mu)
+    x, it = oracle.pcg(w, [1.0, 0.5], setup_binary["X"][:, 1])
+    assert 2 <= it <= 6
+    Ax = 1.0 * x / w + 0.5 * oracle.grm_mv(x)
+    assert np.sum((Ax - setup_binary["X"][:, 1]) ** 2) <= 1e-5
