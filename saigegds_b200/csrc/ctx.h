@@ -85,7 +85,7 @@ struct Context {
     int64_t M = 0;        // local variants
     int64_t M_total = 0;  // Geno_NumVariant across all ranks
     int64_t var_offset = 0;
-    size_t pitch = 0;     // bytes per variant row on the device (NB rounded up to 16)
+    size_t pitch = 0;     // bytes per variant row on the device (NB rounded up to 256)
     DevBuf<uint8_t> packed;   // [M][pitch], pad samples and pitch padding = code 3
     DevBuf<double> lut;       // buf_std_geno [M][4]
     DevBuf<double> diag;      // buf_diag_grm [N]

@@ -1,15 +1,703 @@
-// int8 tensor-core (Ozaki-sliced, exact integer) implementation of get_crossprod_b_grm.
-// Placeholder until the kernel lands: reports "not available" so that SGB_KERNEL_AUTO uses the
-// FP64 CUDA-core path; asking for SGB_KERNEL_IMMA explicitly is an error, never a silent fallback.
+// int8 tensor-core implementation of get_crossprod_b_grm (saige_fitnull.cpp:435-536), exact-integer
+// ("Ozaki"-sliced) arithmetic.  Why: the product costs 2 FP64 FMAs per genotype, the HBM roofline
+// allows ~98 genotypes/clk/SM, the FP64 pipe 64 FMA/clk/SM and the issue ports 128 lanes/clk/SM
+// (tools/microbench.cu, profiles/r01_microbench_b200.txt) -- a one-instruction-per-genotype kernel
+// cannot get past ~30 % of the roofline.  Tensor cores consume 512 genotypes per instruction.
+//
+// Algebra.  With counts c in {0,1,2} (code 3 = missing), lut_j[c] = c*inv_j + lut0_j for valid calls:
+//   dot_j = sum_n lut_j[c_nj] b_n         = inv_j * T_j + lut0_j * (Sb - U_j)
+//   out_n = (1/M) sum_j dot_j lut_j[c_nj] = sum_j e_j c_nj + H - sum_{j in miss(n)} h_j
+//   T_j = sum_n c_nj b_n, U_j = sum_{n in miss(j)} b_n, Sb = sum_n b_n,
+//   e_j = dot_j inv_j / M, h_j = dot_j lut0_j / M, H = sum_j h_j.
+// T = C'b and R = C e are integer-matrix x FP64-vector products.  b (resp. e) is quantised to a 56-bit
+// fixed-point integer relative to its largest element and cut into eight signed base-128 digits; each
+// digit plane is an exact u8 x s8 -> s32 tensor-core GEMM (mma.sync.m16n8k32, SASS IMMA.16832.U8.S8)
+// with N = 8 digit planes.  The result equals the FP64 product of the quantised vector exactly; the
+// quantisation error (2^-55 of the largest element) is below the rounding error of any FP64 dot product.
+// Everything is integer and therefore order-independent and bit-reproducible.
+//
+// Operand formation costs one LOP3 per four genotypes: a packed 32-bit word holds 16 genotypes, and
+// `w & (0x03030303 << 2t)` leaves four bytes each holding one genotype times 4^t -- a valid u8 operand.
+// The factor 4^t is removed exactly from the int32 accumulator (one accumulator set per t).  Code 3 is
+// NOT masked out: it contributes 3*b_n (resp. 3*e_j), which the sparse missing-genotype correction
+// subtracts together with the mean-imputation terms (U_j and h_j above).
+//
+//   phase A (imma_dots_kernel):  CTA = 256 variants x a sample range; packed rows staged with cp.async;
+//       A fragments straight from 128-bit shared loads; accumulators stay in registers over the sweep.
+//   phase B (imma_apply_kernel): CTA = 1024 samples x a variant range; the same packed rows are read
+//       through ldmatrix.m16n16.trans.b8 (SASS LDSM.8.MT1616), which transposes bytes in hardware so that
+//       a register holds four *variants* of one sample byte.
+// Two HBM passes over the packed matrix per product in this version (the fused single-pass kernel is
+// the next step).
+#include <algorithm>
+#include <cmath>
+
 #include "ctx.h"
 
 namespace sgb {
 
-void imma_prepare(Context &) {}
-void imma_release(Context &) {}
-bool imma_available(const Context &) { return false; }
-void imma_grm_mv(Context &, const double *, double *, int) {
-    throw Error(SGB_ERR_STATE, "the IMMA product kernel is not built in this version");
+struct ImmaPlan {
+    // sparse lists of missing genotypes (samples < N only)
+    DevBuf<int64_t> mv_ptr;  // [M+1] by variant -> sample ids
+    DevBuf<int32_t> mv_idx;
+    DevBuf<int64_t> ms_ptr;  // [N+1] by sample -> local variant ids
+    DevBuf<int32_t> ms_idx;
+    int64_t nnz = 0;
+    int64_t ksteps = 0;      // ceil(N / 256)
+    int64_t kblocks = 0;     // ceil(M / 32)
+    int split_a = 1, split_b = 1;
+    DevBuf<int8_t> dfrag;    // [ksteps][2048]  digits of b in phase-A fragment order
+    DevBuf<int8_t> efrag;    // [kblocks][256]  digits of e in phase-B fragment order
+    DevBuf<double> tq;       // [split_a][M]   T'_j partials in units of unit_b
+    DevBuf<double> u, e, hm; // [M]
+    DevBuf<double> rpart;    // [split_b][N]   R_n partials in units of unit_e
+    DevBuf<double> scal;     // [16] device scalars
+    DevBuf<double> red;      // reduction partials
+    DevBuf<unsigned int> counter;
+};
+
+namespace {
+
+// scal slots
+enum { S_MAXB = 0, S_SUMB = 1, S_UNITB = 2, S_MAXE = 3, S_H = 4, S_UNITE = 5 };
+
+constexpr int kAThreads = 128;   // phase A: 4 warps x 4 row-blocks x 16 variants
+constexpr int kARB = 4;
+constexpr int kAVar = 4 * kARB * 16;          // 256 variants per CTA
+constexpr int kAStageSteps = 2;               // K-steps (256 samples = 64 B per row) per pipeline stage
+constexpr int kAStages = 3;
+constexpr int kARowBytes = 64 * kAStageSteps; // 128 B per row per stage
+constexpr int kAStageBytes = kAVar * kARowBytes + 2048 * kAStageSteps;
+
+constexpr int kBThreads = 128;   // phase B: 4 warps x 4 row-blocks x 64 samples
+constexpr int kBRB = 4;
+constexpr int kBSamp = 4 * kBRB * 64;         // 1024 samples = 256 packed bytes per variant
+constexpr int kBRowBytes = kBSamp / 4;        // 256
+constexpr int kBPitch = kBRowBytes + 16;      // 272: 8 consecutive rows hit 8 different 16-byte bank groups
+constexpr int kBStageVar = 64;                // variants per pipeline stage (2 K-blocks)
+constexpr int kBStages = 4;
+constexpr int kBStageBytes = kBStageVar * kBPitch + 256 * (kBStageVar / 32);
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void imma_u8s8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                          uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// 56-bit fixed point -> eight signed base-128 digits (d_l in [-64, 63], top digit takes the rest)
+__device__ __forceinline__ void to_digits(double v, int shift, int8_t (&d)[8]) {
+    long long B = __double2ll_rn(scalbn(v, shift));
+#pragma unroll
+    for (int l = 0; l < 7; l++) {
+        int dl = (int)(((B & 127) ^ 64) - 64);
+        d[l] = (int8_t)dl;
+        B = (B - dl) >> 7;
+    }
+    d[7] = (int8_t)B;
+}
+
+// shift so that |v| * 2^shift <= 2^55 for |v| <= maxabs; unit = 2^-shift (0 when the vector is all zero, NaN if not finite)
+__device__ __forceinline__ int quant_shift(double maxabs, double *unit) {
+    if (!(maxabs > 0) || !isfinite(maxabs)) {
+        *unit = (maxabs == 0) ? 0.0 : __longlong_as_double(0x7ff8000000000000LL);
+        return 0;
+    }
+    int sh = 54 - ilogb(maxabs);
+    *unit = scalbn(1.0, -sh);
+    return sh;
+}
+
+// ------------------------------------------------------------------------------------------------
+// deterministic block reductions (fixed tree + last block adds partials in order)
+template <int T>
+__device__ __forceinline__ double block_reduce_sum(double v, double *sm) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0;
+    if (threadIdx.x == 0) for (int w = 0; w < T / 32; w++) t += sm[w];
+    __syncthreads();
+    return t;
+}
+template <int T>
+__device__ __forceinline__ double block_reduce_max(double v, double *sm) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0;
+    if (threadIdx.x == 0) for (int w = 0; w < T / 32; w++) t = fmax(t, sm[w]);
+    __syncthreads();
+    return t;
+}
+
+// max|b| (NaN-propagating through the sum) and sum(b): partial[0][G] = max, partial[1][G] = sum
+__global__ void __launch_bounds__(256) absmax_sum_kernel(const double *__restrict__ b, int64_t N, double *partial,
+                                                         unsigned int *counter, double *scal) {
+    __shared__ double sm[8];
+    __shared__ bool last;
+    double mx = 0, s = 0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < N; i += (int64_t)gridDim.x * 256) {
+        double v = b[i];
+        mx = fmax(mx, fabs(v));
+        s += v;
+    }
+    mx = block_reduce_max<256>(mx, sm);
+    s = block_reduce_sum<256>(s, sm);
+    const int G = gridDim.x;
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = mx;
+        partial[G + blockIdx.x] = s;
+        __threadfence();
+        last = atomicInc(counter, G - 1) == (unsigned)(G - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        const volatile double *p = partial;
+        double m = 0, t = 0;
+        for (int i = 0; i < G; i++) { m = fmax(m, p[i]); t += p[G + i]; }
+        if (!isfinite(t)) m = t;     // NaN / Inf anywhere in b poisons the product like it does in the reference
+        scal[S_MAXB] = m;
+        scal[S_SUMB] = t;
+        double unit;
+        quant_shift(m, &unit);
+        scal[S_UNITB] = unit;
+    }
+}
+
+// digits of b in phase-A fragment order: [kstep][lane = l*4+tq][(pi*4+t0)*2+h][beta]
+__global__ void digits_b_kernel(const double *__restrict__ b, int64_t N, int64_t Npad, const double *__restrict__ scal,
+                                int8_t *__restrict__ dfrag) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= Npad) return;
+    double unit;
+    const int sh = quant_shift(scal[S_MAXB], &unit);
+    int8_t d[8];
+    const double v = (n < N && unit > 0) ? b[n] : 0.0;
+    to_digits(v, sh, d);
+    const int64_t ks = n >> 8;
+    const int r = (int)(n & 255), tq = r >> 6, r2 = r & 63, pi = r2 >> 5, h = (r2 >> 4) & 1, beta = (r2 >> 2) & 3, t0 = r2 & 3;
+    int8_t *base = dfrag + ks * 2048 + tq * 64 + ((pi * 4 + t0) * 2 + h) * 4 + beta;
+#pragma unroll
+    for (int l = 0; l < 8; l++) base[l * 256] = d[l];
+}
+
+// digits of e in phase-B fragment order: [kblock][lane = l*4+tq][h][beta]
+__global__ void digits_e_kernel(const double *__restrict__ e, int64_t M, int64_t Mpad, const double *__restrict__ scal,
+                                int8_t *__restrict__ efrag) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Mpad) return;
+    double unit;
+    const int sh = quant_shift(scal[S_MAXE], &unit);
+    int8_t d[8];
+    const double v = (j < M && unit > 0) ? e[j] : 0.0;
+    to_digits(v, sh, d);
+    const int64_t kb = j >> 5;
+    const int jj = (int)(j & 31), h = jj >> 4, tq = (jj >> 2) & 3, beta = jj & 3;
+    int8_t *base = efrag + kb * 256 + tq * 8 + h * 4 + beta;
+#pragma unroll
+    for (int l = 0; l < 8; l++) base[l * 32] = d[l];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Phase A: T'_j = sum_n c'_nj * B_n  (c' = raw 2-bit code, B_n = quantised b) for 256 variants x a K-step range.
+__global__ void __launch_bounds__(kAThreads, 2) imma_dots_kernel(const uint8_t *__restrict__ packed, size_t pitch, int64_t M,
+                                                                 int64_t ksteps, int split, const int8_t *__restrict__ dfrag,
+                                                                 double *__restrict__ tq_out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
+    const int64_t j0 = (int64_t)blockIdx.x * kAVar;
+    const int sp = blockIdx.y;
+    const int64_t ks_per = (ksteps + split - 1) / split;
+    const int64_t ks_begin = (int64_t)sp * ks_per, ks_end = min(ksteps, ks_begin + ks_per);
+    const int64_t n_stage = (ks_end > ks_begin) ? (ks_end - ks_begin + kAStageSteps - 1) / kAStageSteps : 0;
+
+    auto issue = [&](int64_t st) {
+        if (st < n_stage) {
+            uint8_t *buf = smem + (size_t)(st % kAStages) * kAStageBytes;
+            const int64_t ks0 = ks_begin + st * kAStageSteps;
+            // packed rows: 256 rows x 8 granules of 16 B; granule index swizzled by 4*(row&1)
+            for (int i = tid; i < kAVar * (kARowBytes / 16); i += kAThreads) {
+                const int r = i >> 3, gran = i & 7;
+                const int64_t j = min(j0 + r, M - 1);
+                const int64_t ks = ks0 + (gran >> 2);
+                const size_t off = (size_t)min(ks, ksteps - 1) * 64 + (size_t)(gran & 3) * 16;
+                cp_async16(buf + r * kARowBytes + ((gran ^ ((r & 1) << 2)) << 4), packed + (size_t)j * pitch + off);
+            }
+            uint8_t *dbuf = buf + kAVar * kARowBytes;
+            for (int i = tid; i < 128 * kAStageSteps; i += kAThreads) {
+                const int64_t ks = min(ks0 + (i >> 7), ksteps - 1);
+                cp_async16(dbuf + i * 16, dfrag + ks * 2048 + (size_t)(i & 127) * 16);
+            }
+        }
+        cp_async_commit();
+    };
+
+    int acc[kARB][4][4];
+#pragma unroll
+    for (int rb = 0; rb < kARB; rb++)
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[rb][t][q] = 0;
+    // FP64 running totals (flushed from the int32 accumulators well before they can overflow)
+    double tot[kARB][2];
+#pragma unroll
+    for (int rb = 0; rb < kARB; rb++) tot[rb][0] = tot[rb][1] = 0;
+
+    auto flush = [&]() {
+        // value of this thread's two digit columns (2tq, 2tq+1) for rows g and g+8, with the 4^t factor removed
+        const double w0 = scalbn(1.0, 14 * tq), w1 = scalbn(1.0, 14 * tq + 7);
+#pragma unroll
+        for (int rb = 0; rb < kARB; rb++) {
+            double lo = 0, hi = 0;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                lo += w0 * (double)(acc[rb][t][0] >> (2 * t)) + w1 * (double)(acc[rb][t][1] >> (2 * t));
+                hi += w0 * (double)(acc[rb][t][2] >> (2 * t)) + w1 * (double)(acc[rb][t][3] >> (2 * t));
+                acc[rb][t][0] = acc[rb][t][1] = acc[rb][t][2] = acc[rb][t][3] = 0;
+            }
+            tot[rb][0] += lo;
+            tot[rb][1] += hi;
+        }
+    };
+
+    for (int s = 0; s < kAStages - 1; s++) issue(s);
+    int since_flush = 0;
+    for (int64_t st = 0; st < n_stage; st++) {
+        cp_async_wait<kAStages - 2>();
+        __syncthreads();
+        issue(st + kAStages - 1);
+        const uint8_t *buf = smem + (size_t)(st % kAStages) * kAStageBytes;
+        const uint8_t *dbuf = buf + kAVar * kARowBytes;
+        const int64_t ks0 = ks_begin + st * kAStageSteps;
+#pragma unroll
+        for (int s = 0; s < kAStageSteps; s++) {
+            if (ks0 + s >= ks_end) break;
+            // B fragments: 64 contiguous bytes per lane
+            uint4 bf[4];
+            const uint4 *bp = reinterpret_cast<const uint4 *>(dbuf + s * 2048 + lane * 64);
+#pragma unroll
+            for (int i = 0; i < 4; i++) bf[i] = bp[i];
+            const uint32_t *bw = reinterpret_cast<const uint32_t *>(bf);   // [(pi*4+t0)*2+h]
+#pragma unroll
+            for (int rb = 0; rb < kARB; rb++) {
+                const int r0 = warp * (kARB * 16) + rb * 16 + g;
+                const int gran = (s * 4 + tq) ^ ((r0 & 1) << 2);   // r0 and r0+8 have the same parity
+                const uint4 wa = *reinterpret_cast<const uint4 *>(buf + r0 * kARowBytes + (gran << 4));
+                const uint4 wb = *reinterpret_cast<const uint4 *>(buf + (r0 + 8) * kARowBytes + (gran << 4));
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const uint32_t m = 0x03030303u << (2 * t);
+                    imma_u8s8(acc[rb][t], wa.x & m, wb.x & m, wa.y & m, wb.y & m, bw[(0 * 4 + t) * 2], bw[(0 * 4 + t) * 2 + 1]);
+                    imma_u8s8(acc[rb][t], wa.z & m, wb.z & m, wa.w & m, wb.w & m, bw[(1 * 4 + t) * 2], bw[(1 * 4 + t) * 2 + 1]);
+                }
+            }
+        }
+        // one accumulator sees 64 terms of at most 192*64 per K-step: flush every 1024 K-steps (< 2^30)
+        since_flush += kAStageSteps;
+        if (since_flush >= 1024) { flush(); since_flush = 0; }
+    }
+    cp_async_wait<0>();
+    flush();
+    // add the four digit-column groups (tq = 0..3) of each row; lanes tq == 0 write
+#pragma unroll
+    for (int rb = 0; rb < kARB; rb++) {
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+            double v = tot[rb][hh];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            const int64_t j = j0 + warp * (kARB * 16) + rb * 16 + g + hh * 8;
+            if (tq == 0 && j < M) tq_out[(size_t)sp * M + j] = v;
+        }
+    }
+}
+
+// U_j = sum of b over the missing samples of variant j (one warp per variant, fixed order)
+__global__ void miss_dots_kernel(const int64_t *__restrict__ mv_ptr, const int32_t *__restrict__ mv_idx,
+                                 const double *__restrict__ b, int64_t M, double *__restrict__ u) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= M) return;
+    double s = 0;
+    for (int64_t i = mv_ptr[j] + lane; i < mv_ptr[j + 1]; i += 32) s += b[mv_idx[i]];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) u[j] = s;
+}
+
+// dot_j, e_j, hm_j = h_j + 3 e_j;  max|e| and H = sum h_j (deterministic)
+__global__ void __launch_bounds__(256) finalize_dots_kernel(const double *__restrict__ tq, int split, const double *__restrict__ u,
+                                                            const double *__restrict__ lut, int64_t M, double inv_mtotal,
+                                                            double *__restrict__ e, double *__restrict__ hm, double *partial,
+                                                            unsigned int *counter, double *scal) {
+    __shared__ double sm[8];
+    __shared__ bool last;
+    const double unit_b = scal[S_UNITB], sumb = scal[S_SUMB];
+    double mx = 0, hs = 0;
+    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < M; j += (int64_t)gridDim.x * 256) {
+        double t = 0;
+        for (int s = 0; s < split; s++) t += tq[(size_t)s * M + j];
+        const double l0 = lut[4 * j], inv = lut[4 * j + 1] - l0;
+        const double uj = u[j];
+        const double T = (unit_b == 0 ? 0.0 : unit_b * t) - 3.0 * uj;
+        const double dot = inv * T + l0 * (sumb - uj);
+        const double ej = dot * inv * inv_mtotal, hj = dot * l0 * inv_mtotal;
+        e[j] = ej;
+        hm[j] = hj + 3.0 * ej;
+        mx = fmax(mx, fabs(ej));
+        hs += hj;
+        if (!isfinite(ej)) mx = ej;
+    }
+    // NaN-safe max: propagate non-finite values through the sum channel
+    mx = block_reduce_max<256>(mx, sm);
+    hs = block_reduce_sum<256>(hs, sm);
+    const int G = gridDim.x;
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = mx;
+        partial[G + blockIdx.x] = hs;
+        __threadfence();
+        last = atomicInc(counter, G - 1) == (unsigned)(G - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        const volatile double *p = partial;
+        double m = 0, t = 0;
+        for (int i = 0; i < G; i++) { m = fmax(m, p[i]); t += p[G + i]; }
+        if (!isfinite(t)) m = t;
+        scal[S_MAXE] = m;
+        scal[S_H] = t;
+        double unit;
+        quant_shift(m, &unit);
+        scal[S_UNITE] = unit;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Phase B: R_n = sum_j c'_nj * E_j for 1024 samples x a K-block range.
+__global__ void __launch_bounds__(kBThreads, 2) imma_apply_kernel(const uint8_t *__restrict__ packed, size_t pitch, int64_t M,
+                                                                  int64_t N, int64_t kblocks, int split,
+                                                                  const int8_t *__restrict__ efrag, double *__restrict__ rpart) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
+    const size_t byte0 = (size_t)blockIdx.x * kBRowBytes;
+    const int sp = blockIdx.y;
+    const int64_t kb_per = (kblocks + split - 1) / split;
+    const int64_t kb_begin = (int64_t)sp * kb_per, kb_end = min(kblocks, kb_begin + kb_per);
+    constexpr int kKbPerStage = kBStageVar / 32;
+    const int64_t n_stage = (kb_end > kb_begin) ? (kb_end - kb_begin + kKbPerStage - 1) / kKbPerStage : 0;
+
+    auto issue = [&](int64_t st) {
+        if (st < n_stage) {
+            uint8_t *buf = smem + (size_t)(st % kBStages) * kBStageBytes;
+            const int64_t v0 = (kb_begin + st * kKbPerStage) * 32;
+            for (int i = tid; i < kBStageVar * (kBRowBytes / 16); i += kBThreads) {
+                const int r = i >> 4, gran = i & 15;
+                const int64_t j = min(v0 + r, M - 1);
+                cp_async16(buf + r * kBPitch + gran * 16, packed + (size_t)j * pitch + byte0 + (size_t)gran * 16);
+            }
+            uint8_t *ebuf = buf + kBStageVar * kBPitch;
+            for (int i = tid; i < 16 * kKbPerStage; i += kBThreads) {
+                const int64_t kb = min(kb_begin + st * kKbPerStage + (i >> 4), kblocks - 1);
+                cp_async16(ebuf + i * 16, efrag + kb * 256 + (size_t)(i & 15) * 16);
+            }
+        }
+        cp_async_commit();
+    };
+
+    int acc[kBRB][4][4];
+#pragma unroll
+    for (int rb = 0; rb < kBRB; rb++)
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[rb][t][q] = 0;
+    double tot[kBRB][4][2];   // [row-block][t0][row g / g+8]
+#pragma unroll
+    for (int rb = 0; rb < kBRB; rb++)
+#pragma unroll
+        for (int t = 0; t < 4; t++) tot[rb][t][0] = tot[rb][t][1] = 0;
+
+    auto flush = [&]() {
+        const double w0 = scalbn(1.0, 14 * tq), w1 = scalbn(1.0, 14 * tq + 7);
+#pragma unroll
+        for (int rb = 0; rb < kBRB; rb++)
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                tot[rb][t][0] += w0 * (double)(acc[rb][t][0] >> (2 * t)) + w1 * (double)(acc[rb][t][1] >> (2 * t));
+                tot[rb][t][1] += w0 * (double)(acc[rb][t][2] >> (2 * t)) + w1 * (double)(acc[rb][t][3] >> (2 * t));
+                acc[rb][t][0] = acc[rb][t][1] = acc[rb][t][2] = acc[rb][t][3] = 0;
+            }
+    };
+
+    // ldmatrix row addresses: lanes 0-15 -> variants 0..15 of the K-block, lanes 16-31 -> variants 16..31
+    const int ld_row = lane;   // 0..31
+    for (int s = 0; s < kBStages - 1; s++) issue(s);
+    int since_flush = 0;
+    for (int64_t st = 0; st < n_stage; st++) {
+        cp_async_wait<kBStages - 2>();
+        __syncthreads();
+        issue(st + kBStages - 1);
+        const uint8_t *buf = smem + (size_t)(st % kBStages) * kBStageBytes;
+        const uint8_t *ebuf = buf + kBStageVar * kBPitch;
+#pragma unroll
+        for (int kk = 0; kk < kKbPerStage; kk++) {
+            if (kb_begin + st * kKbPerStage + kk >= kb_end) break;
+            const uint2 bf = *reinterpret_cast<const uint2 *>(ebuf + kk * 256 + lane * 8);
+#pragma unroll
+            for (int rb = 0; rb < kBRB; rb++) {
+                // 16 byte positions (64 samples) of this row-block, 32 variants of this K-block
+                const uint8_t *src = buf + (kk * 32 + ld_row) * kBPitch + (warp * kBRB + rb) * 16;
+                const unsigned addr = (unsigned)__cvta_generic_to_shared(src);
+                uint32_t x0, x1, x2, x3;   // x0/x1: variants 0-15 at byte g / g+8; x2/x3: variants 16-31
+                asm volatile("ldmatrix.sync.aligned.m16n16.x2.trans.shared.b8 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(addr));
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const uint32_t m = 0x03030303u << (2 * t);
+                    imma_u8s8(acc[rb][t], x0 & m, x1 & m, x2 & m, x3 & m, bf.x, bf.y);
+                }
+            }
+        }
+        // one accumulator sees 32 terms of at most 192*64 per K-block: flush every 2048 K-blocks (< 2^30)
+        since_flush += kKbPerStage;
+        if (since_flush >= 2048) { flush(); since_flush = 0; }
+    }
+    cp_async_wait<0>();
+    flush();
+#pragma unroll
+    for (int rb = 0; rb < kBRB; rb++)
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                double v = tot[rb][t][hh];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                const int64_t n = ((int64_t)byte0 + (warp * kBRB + rb) * 16 + g + hh * 8) * 4 + t;
+                if (tq == 0 && n < N) rpart[(size_t)sp * N + n] = v;
+            }
+}
+
+// out_n = unit_e * sum_s R_n[s] + H - sum_{j in miss(n)} hm_j
+__global__ void combine_kernel(const double *__restrict__ rpart, int split, int64_t N, const int64_t *__restrict__ ms_ptr,
+                               const int32_t *__restrict__ ms_idx, const double *__restrict__ hm,
+                               const double *__restrict__ scal, double *__restrict__ out) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double r = 0;
+    for (int s = 0; s < split; s++) r += rpart[(size_t)s * N + n];
+    const double unit_e = scal[S_UNITE];
+    double corr = 0;
+    for (int64_t i = ms_ptr[n]; i < ms_ptr[n + 1]; i++) corr += hm[ms_idx[i]];
+    out[n] = (unit_e == 0 ? 0.0 : unit_e * r) + scal[S_H] - corr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sparse lists of missing genotypes
+// by variant: one warp per variant, ascending sample order
+__global__ void fill_mv_kernel(const uint8_t *__restrict__ packed, size_t pitch, int64_t M, int64_t N,
+                               const int64_t *__restrict__ mv_ptr, int32_t *__restrict__ mv_idx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= M) return;
+    const uint32_t *row = reinterpret_cast<const uint32_t *>(packed + (size_t)j * pitch);
+    const int64_t n_words = (N + 15) / 16;
+    int64_t pos = mv_ptr[j];
+    for (int64_t w0 = 0; w0 < n_words; w0 += 32) {
+        const int64_t wi = w0 + lane;
+        uint32_t m = 0;
+        if (wi < n_words) {
+            const uint32_t w = row[wi];
+            m = w & (w >> 1) & 0x55555555u;
+            const int64_t rem = N - wi * 16;               // samples of this word that are < N
+            if (rem < 16) m &= (rem <= 0) ? 0u : ((1u << (2 * rem)) - 1u);
+        }
+        const int cnt = __popc(m);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        int64_t p = pos + incl - cnt;
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            mv_idx[p++] = (int32_t)(wi * 16 + (bit >> 1));
+        }
+        pos += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+// by sample: thread <-> one packed byte (4 samples); pass 0 counts, pass 1 fills in ascending variant order
+__global__ void miss_by_sample_kernel(const uint8_t *__restrict__ packed, size_t pitch, int64_t M, int64_t N, int64_t NB,
+                                      int32_t *__restrict__ counts, const int64_t *__restrict__ ms_ptr,
+                                      int32_t *__restrict__ ms_idx, int fill) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= NB) return;
+    int cnt[4] = {0, 0, 0, 0};
+    int64_t pos[4] = {0, 0, 0, 0};
+    if (fill)
+        for (int k = 0; k < 4; k++) if (q * 4 + k < N) pos[k] = ms_ptr[q * 4 + k];
+    for (int64_t j = 0; j < M; j++) {
+        const uint32_t v = packed[(size_t)j * pitch + q];
+        uint32_t m = v & (v >> 1) & 0x55u;
+        while (m) {
+            const int k = (__ffs(m) - 1) >> 1;
+            m &= m - 1;
+            if (q * 4 + k < N) {
+                if (fill) ms_idx[pos[k]++] = (int32_t)j; else cnt[k]++;
+            }
+        }
+    }
+    if (!fill)
+        for (int k = 0; k < 4; k++) if (q * 4 + k < N) counts[q * 4 + k] = cnt[k];
+}
+
+int pick_split(int64_t tiles, int slots, int max_split) {
+    int best = 1;
+    double best_eff = 0;
+    for (int s = 1; s <= max_split; s++) {
+        const int64_t t = tiles * s;
+        const double eff = (double)t / (double)(((t + slots - 1) / slots) * slots);
+        if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+    }
+    return best;
+}
+
+}  // namespace
+
+bool imma_available(const Context &c) { return c.imma != nullptr; }
+
+void imma_release(Context &c) {
+    delete c.imma;
+    c.imma = nullptr;
+}
+
+void imma_prepare(Context &c) {
+    imma_release(c);
+    ImmaPlan *p = new ImmaPlan();
+    try {
+        const int64_t M = c.M, N = c.N;
+        p->ksteps = (N + 255) / 256;
+        p->kblocks = (M + 31) / 32;
+        if ((size_t)p->ksteps * 64 > c.pitch) throw Error(SGB_ERR_STATE, "row pitch too small for the IMMA kernels");
+        // ---- missing lists by variant (counts are known from the store pass: N - cnt_num) ----
+        std::vector<int64_t> ptr(M + 1, 0);
+        for (int64_t j = 0; j < M; j++) ptr[j + 1] = ptr[j] + (N - c.h_cnt_num[j]);
+        p->nnz = ptr[M];
+        p->mv_ptr.ensure(M + 1);
+        p->mv_idx.ensure(std::max<int64_t>(p->nnz, 1));
+        c.h2d(p->mv_ptr.get(), ptr.data(), sizeof(int64_t) * (M + 1));
+        fill_mv_kernel<<<(unsigned)((M + 7) / 8), 256, 0, c.stream>>>(c.packed.get(), c.pitch, M, N, p->mv_ptr.get(),
+                                                                     p->mv_idx.get());
+        SGB_CHECK_LAUNCH();
+        c.sync();
+        // ---- by sample ----
+        DevBuf<int32_t> counts;
+        counts.ensure(N);
+        p->ms_ptr.ensure(N + 1);
+        p->ms_idx.ensure(std::max<int64_t>(p->nnz, 1));
+        miss_by_sample_kernel<<<(unsigned)((c.NB + 127) / 128), 128, 0, c.stream>>>(c.packed.get(), c.pitch, M, N, c.NB,
+                                                                                   counts.get(), nullptr, nullptr, 0);
+        SGB_CHECK_LAUNCH();
+        std::vector<int32_t> hc(N);
+        c.d2h(hc.data(), counts.get(), sizeof(int32_t) * N);
+        c.sync();
+        std::vector<int64_t> sp(N + 1, 0);
+        for (int64_t n = 0; n < N; n++) sp[n + 1] = sp[n] + hc[n];
+        if (sp[N] != p->nnz) throw Error(SGB_ERR_STATE, "missing-genotype lists disagree");
+        c.h2d(p->ms_ptr.get(), sp.data(), sizeof(int64_t) * (N + 1));
+        miss_by_sample_kernel<<<(unsigned)((c.NB + 127) / 128), 128, 0, c.stream>>>(c.packed.get(), c.pitch, M, N, c.NB,
+                                                                                   nullptr, p->ms_ptr.get(), p->ms_idx.get(), 1);
+        SGB_CHECK_LAUNCH();
+        c.sync();
+        c.stats.n_kernel_launches += 3;
+        // ---- work buffers ----
+        const int slots = 2 * c.sm_count;
+        p->split_a = pick_split((M + kAVar - 1) / kAVar, slots, 8);
+        p->split_b = pick_split((N + kBSamp - 1) / kBSamp, slots, 8);
+        p->dfrag.ensure((size_t)p->ksteps * 2048);
+        p->efrag.ensure((size_t)p->kblocks * 256);
+        p->tq.ensure((size_t)p->split_a * M);
+        p->u.ensure(M); p->e.ensure(M); p->hm.ensure(M);
+        p->rpart.ensure((size_t)p->split_b * N);
+        p->scal.ensure(16);
+        p->red.ensure(4 * 1024);
+        p->counter.ensure(8);
+        SGB_CUDA(cudaMemsetAsync(p->counter.get(), 0, sizeof(unsigned int) * 8, c.stream));
+        SGB_CUDA(cudaMemsetAsync(p->scal.get(), 0, sizeof(double) * 16, c.stream));
+        SGB_CUDA(cudaFuncSetAttribute(imma_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAStages * kAStageBytes));
+        SGB_CUDA(cudaFuncSetAttribute(imma_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBStages * kBStageBytes));
+        c.sync();
+    } catch (...) {
+        delete p;
+        throw;
+    }
+    c.imma = p;
+}
+
+void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
+    ImmaPlan *p = c.imma;
+    if (!p) throw Error(SGB_ERR_STATE, "the IMMA product kernel is not prepared");
+    const int64_t M = c.M, N = c.N;
+    const int G = (int)std::min<int64_t>(1024, std::max<int64_t>(1, (N + 2047) / 2048));
+    const int Gm = (int)std::min<int64_t>(1024, std::max<int64_t>(1, (M + 1023) / 1024));
+    for (int col = 0; col < k; col++) {
+        const double *b = b_all + (size_t)col * N;
+        double *out = out_all + (size_t)col * N;
+        c.prof_begin();
+        absmax_sum_kernel<<<G, 256, 0, c.stream>>>(b, N, p->red.get(), p->counter.get(), p->scal.get());
+        SGB_CHECK_LAUNCH();
+        digits_b_kernel<<<(unsigned)((p->ksteps * 256 + 255) / 256), 256, 0, c.stream>>>(b, N, p->ksteps * 256, p->scal.get(),
+                                                                                       p->dfrag.get());
+        SGB_CHECK_LAUNCH();
+        c.prof_end("imma_prep_b (absmax+digits)");
+        c.prof_begin();
+        imma_dots_kernel<<<dim3((unsigned)((M + kAVar - 1) / kAVar), p->split_a), kAThreads, kAStages * kAStageBytes, c.stream>>>(
+            c.packed.get(), c.pitch, M, p->ksteps, p->split_a, p->dfrag.get(), p->tq.get());
+        SGB_CHECK_LAUNCH();
+        c.prof_end("imma_dots_kernel");
+        c.prof_begin();
+        miss_dots_kernel<<<(unsigned)((M + 7) / 8), 256, 0, c.stream>>>(p->mv_ptr.get(), p->mv_idx.get(), b, M, p->u.get());
+        SGB_CHECK_LAUNCH();
+        c.prof_end("miss_dots_kernel");
+        c.prof_begin();
+        finalize_dots_kernel<<<Gm, 256, 0, c.stream>>>(p->tq.get(), p->split_a, p->u.get(), c.lut.get(), M,
+                                                       1.0 / (double)c.M_total, p->e.get(), p->hm.get(), p->red.get() + 2048,
+                                                       p->counter.get() + 1, p->scal.get());
+        SGB_CHECK_LAUNCH();
+        digits_e_kernel<<<(unsigned)((p->kblocks * 32 + 255) / 256), 256, 0, c.stream>>>(p->e.get(), M, p->kblocks * 32,
+                                                                                      p->scal.get(), p->efrag.get());
+        SGB_CHECK_LAUNCH();
+        c.prof_end("imma_finalize+digits_e");
+        c.prof_begin();
+        imma_apply_kernel<<<dim3((unsigned)((N + kBSamp - 1) / kBSamp), p->split_b), kBThreads, kBStages * kBStageBytes,
+                            c.stream>>>(c.packed.get(), c.pitch, M, N, p->kblocks, p->split_b, p->efrag.get(), p->rpart.get());
+        SGB_CHECK_LAUNCH();
+        c.prof_end("imma_apply_kernel");
+        c.prof_begin();
+        combine_kernel<<<(unsigned)((N + 255) / 256), 256, 0, c.stream>>>(p->rpart.get(), p->split_b, N, p->ms_ptr.get(),
+                                                                        p->ms_idx.get(), p->hm.get(), p->scal.get(), out);
+        SGB_CHECK_LAUNCH();
+        c.prof_end("combine_kernel");
+        c.stats.n_kernel_launches += 8;
+        c.stats.n_product_launches += 1;
+    }
 }
 
 }  // namespace sgb

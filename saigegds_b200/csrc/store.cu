@@ -1,8 +1,8 @@
 // Genotype store: device layout, allele counts, standardised look-up table, diag(GRM), decode.
 // Replaces saige_store_2b_geno (saige_fitnull.cpp:159-230) and get_geno_ds (:394-427).
 //
-// HBM layout: one row per variant, `pitch` = ceil(N/4) rounded up to 16 bytes so that every row
-// starts 16-byte aligned (uint4 / TMA friendly).  Sample 4j+k sits in bits 2k..2k+1 of byte j
+// HBM layout: one row per variant, `pitch` = ceil(N/4) rounded up to 256 bytes so that every row
+// starts 256-byte aligned (uint4 / cp.async / TMA friendly, whole sample tiles).  Sample 4j+k sits in bits 2k..2k+1 of byte j
 // (the reference's format, unchanged).  Samples >= N of the last byte and the pitch padding are
 // rewritten to code 3 (missing), whose standardised value is 0, so product kernels never need a
 // tail branch.  The reference's allele counts sweep the raw pad bits (:188-192), so the counts are
@@ -135,7 +135,7 @@ __global__ void synth_kernel(uint8_t *__restrict__ out, int64_t N, int64_t NB, i
 
 void store_device_layout(Context &c, const uint8_t *src, size_t src_pitch) {
     const int64_t M = c.M, N = c.N, NB = c.NB;
-    c.pitch = (size_t)((NB + 15) / 16) * 16;
+    c.pitch = (size_t)((NB + 255) / 256) * 256;   // 256-byte multiple: whole 1024-sample tiles for the IMMA kernels
     c.packed.ensure((size_t)M * c.pitch);
     c.lut.ensure((size_t)4 * M);
     c.diag.ensure((size_t)N);

@@ -67,8 +67,13 @@ def test_ragged_shapes_missing_and_pad_codes(gpu, n_samp, n_var, missing):
         assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(np.nan_to_num(a), np.nan_to_num(b))
     b = rng.standard_normal(n_samp)
     want = o.grm_mv(b)
-    got = gpu.get_crossprod_b_grm(b)
-    assert np.max(np.abs(got - want)) <= PROD_TOL * max(np.max(np.abs(want)), 1e-300) + 1e-300
+    for kernel in ("simt", "imma"):
+        gpu.set_kernel(kernel)
+        try:
+            got = gpu.get_crossprod_b_grm(b)
+        finally:
+            gpu.set_kernel("auto")
+        assert np.max(np.abs(got - want)) <= PROD_TOL * max(np.max(np.abs(want)), 1e-300) + 1e-300, kernel
 
 
 # ---------------------------------------------------------------- product
@@ -86,6 +91,33 @@ def test_product_matches_oracle_on_fixture(gpu, gstore, oracle, fx):
     assert relinf(gpu.get_crossprod_b_grm(spike), oracle.grm_mv(spike)) < PROD_TOL
 
 
+@pytest.mark.parametrize("kernel", ["simt", "imma"])
+def test_both_kernels_match_oracle_on_fixture(gpu, fx, oracle, kernel):
+    gpu.saige_store_2b_geno(fx.packed, fx.n_samp)
+    gpu.set_kernel(kernel)
+    try:
+        rng = np.random.default_rng(21)
+        for scale in (1.0, 1e-9, 1e9):
+            b = rng.standard_normal(fx.n_samp) * scale
+            assert relinf(gpu.get_crossprod_b_grm(b), oracle.grm_mv(b)) < PROD_TOL
+        b = rng.standard_normal(fx.n_samp) * 10.0 ** rng.uniform(-12, 12, fx.n_samp)    # 24 decades of dynamic range
+        assert relinf(gpu.get_crossprod_b_grm(b), oracle.grm_mv(b)) < PROD_TOL
+    finally:
+        gpu.set_kernel("auto")
+
+
+def test_imma_is_bit_reproducible(gpu, fx):
+    """Exact integer arithmetic: repeated products are bit-identical."""
+    gpu.saige_store_2b_geno(fx.packed, fx.n_samp)
+    gpu.set_kernel("imma")
+    try:
+        b = np.random.default_rng(22).standard_normal(fx.n_samp)
+        a1, a2 = gpu.get_crossprod_b_grm(b), gpu.get_crossprod_b_grm(b)
+        assert np.array_equal(a1, a2)
+    finally:
+        gpu.set_kernel("auto")
+
+
 def test_product_multi_rhs_equals_single(gpu, fx, oracle):
     gpu.saige_store_2b_geno(fx.packed, fx.n_samp)
     rng = np.random.default_rng(2)
@@ -95,7 +127,7 @@ def test_product_multi_rhs_equals_single(gpu, fx, oracle):
         assert relinf(out[:, k], oracle.grm_mv(B[:, k])) < PROD_TOL
 
 
-@pytest.mark.parametrize("kernel", ["simt", "auto"])
+@pytest.mark.parametrize("kernel", ["simt", "imma"])
 def test_product_properties_at_scale(gpu, kernel):
     """N=50K, M=4K synthetic (too big for the scalar oracle in seconds): linearity, symmetry, PSD, and a
     column-sampled check against the definition."""
@@ -119,6 +151,9 @@ def test_product_properties_at_scale(gpu, kernel):
         e = np.zeros(n); e[12345] = 1.0
         assert abs(gpu.get_crossprod_b_grm(e)[12345] - diag[12345]) / diag[12345] < 1e-11
         assert np.isfinite(tot)
+        if kernel == "imma":                                                 # the two kernels agree at scale
+            gpu.set_kernel("simt")
+            assert relinf(Ax, gpu.get_crossprod_b_grm(x)) < PROD_TOL
     finally:
         gpu.set_kernel("auto")
 
@@ -245,6 +280,12 @@ def test_error_behaviour(gpu, fx):
         c.get_crossprod_b_grm(np.zeros(4))
     with pytest.raises(sg.InvalidArgument):                # wrong bytes-per-variant
         c.saige_store_2b_geno(np.zeros((3, 5), dtype=np.uint8), 100)
-    with pytest.raises(sg.SgbError):
-        c.set_kernel("imma") or c.saige_store_2b_geno(fx.packed[:10], fx.n_samp) or c.get_crossprod_b_grm(np.ones(fx.n_samp))
+    with pytest.raises(sg.InvalidArgument):                # unknown kernel id
+        from saigegds_b200 import _lib
+        _lib.check(_lib.lib().sgb_set_kernel(c._h, 99))
+    with pytest.raises(sg.InvalidArgument):                # fit with the wrong number of samples
+        c.saige_store_2b_geno(fx.packed[:10], fx.n_samp)
+        from saigegds_b200 import rsetup
+        X = np.ones((5, 1))
+        c.saige_fit_AI_PCG_binary(rsetup.Fit0(np.zeros(5), np.zeros(1), np.zeros(5), np.full(5, .5), "binomial"), X, [1, .5])
     c.close()
