@@ -243,7 +243,7 @@ class Context:
         L.check(L.lib().sgb_kernel_times(self._h, buf, C.c_int64(len(buf))))
         out = {}
         for line in buf.value.decode().splitlines():
-            name, ms, cnt = line.split()
+            name, ms, cnt = line.rsplit(" ", 2)
             out[name] = (float(ms), int(cnt))
         return out
 

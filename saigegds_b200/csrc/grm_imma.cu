@@ -29,6 +29,9 @@
 //       a register holds four *variants* of one sample byte.
 // Two HBM passes over the packed matrix per product in this version (the fused single-pass kernel is
 // the next step).
+#include <thrust/execution_policy.h>
+#include <thrust/scan.h>
+
 #include <algorithm>
 #include <cmath>
 
@@ -49,8 +52,21 @@ struct ImmaPlan {
     DevBuf<int8_t> dfrag;    // [ksteps][2048]  digits of b in phase-A fragment order
     DevBuf<int8_t> efrag;    // [kblocks][256]  digits of e in phase-B fragment order
     DevBuf<double> tq;       // [split_a][M]   T'_j partials in units of unit_b
-    DevBuf<double> u, e, hm; // [M]
+    DevBuf<double> e, hm;    // [M]
     DevBuf<double> rpart;    // [split_b][N]   R_n partials in units of unit_e
+    DevBuf<int64_t> mv_pos;  // [n_stiles * M + 1] tile-major start of (sample tile, variant)
+    DevBuf<uint16_t> mv_i16; // [nnz] sample offset inside the tile
+    DevBuf<int64_t> ms_pos;  // [n_vtiles * N + 1] tile-major start of (variant tile, sample)
+    DevBuf<uint16_t> ms_i16; // [nnz] variant offset inside the tile
+    int n_stiles = 0, n_vtiles = 0;
+    DevBuf<double> upart;    // [n_stiles][M] U_j per sample tile
+    DevBuf<double> cpart;    // [n_vtiles][N] output correction per variant tile
+    cudaStream_t side = nullptr;   // the sparse corrections run beside the tensor-core kernels
+    cudaEvent_t ev_in = nullptr, ev_u = nullptr, ev_hm = nullptr, ev_corr = nullptr;
+    ~ImmaPlan() {
+        if (side) cudaStreamDestroy(side);
+        for (cudaEvent_t e : {ev_in, ev_u, ev_hm, ev_corr}) if (e) cudaEventDestroy(e);
+    }
     DevBuf<double> scal;     // [16] device scalars
     DevBuf<double> red;      // reduction partials
     DevBuf<unsigned int> counter;
@@ -64,8 +80,8 @@ enum { S_MAXB = 0, S_SUMB = 1, S_UNITB = 2, S_MAXE = 3, S_H = 4, S_UNITE = 5 };
 constexpr int kAThreads = 128;   // phase A: 4 warps x 4 row-blocks x 16 variants
 constexpr int kARB = 4;
 constexpr int kAVar = 4 * kARB * 16;          // 256 variants per CTA
-constexpr int kAStageSteps = 2;               // K-steps (256 samples = 64 B per row) per pipeline stage
-constexpr int kAStages = 3;
+constexpr int kAStageSteps = 1;               // K-steps (256 samples = 64 B per row) per pipeline stage
+constexpr int kAStages = 4;                   // 4 x 18 KB x 2 CTAs/SM = 144 KB: leaves room for a sparse-correction CTA
 constexpr int kARowBytes = 64 * kAStageSteps; // 128 B per row per stage
 constexpr int kAStageBytes = kAVar * kARowBytes + 2048 * kAStageSteps;
 
@@ -227,13 +243,17 @@ __global__ void __launch_bounds__(kAThreads, 2) imma_dots_kernel(const uint8_t *
         if (st < n_stage) {
             uint8_t *buf = smem + (size_t)(st % kAStages) * kAStageBytes;
             const int64_t ks0 = ks_begin + st * kAStageSteps;
-            // packed rows: 256 rows x 8 granules of 16 B; granule index swizzled by 4*(row&1)
-            for (int i = tid; i < kAVar * (kARowBytes / 16); i += kAThreads) {
-                const int r = i >> 3, gran = i & 7;
+            // packed rows: 256 rows x (4 * kAStageSteps) granules of 16 B.  A quarter-warp reads 4 granules of two
+            // adjacent rows: with 64-byte rows that is one contiguous 128-byte line; with 128-byte rows the granule
+            // index of odd rows is flipped by 4 so that the two rows use different bank halves.
+            constexpr int kGran = kARowBytes / 16;
+            for (int i = tid; i < kAVar * kGran; i += kAThreads) {
+                const int r = i / kGran, gran = i % kGran;
                 const int64_t j = min(j0 + r, M - 1);
                 const int64_t ks = ks0 + (gran >> 2);
                 const size_t off = (size_t)min(ks, ksteps - 1) * 64 + (size_t)(gran & 3) * 16;
-                cp_async16(buf + r * kARowBytes + ((gran ^ ((r & 1) << 2)) << 4), packed + (size_t)j * pitch + off);
+                const int sw = (kAStageSteps == 2) ? (gran ^ ((r & 1) << 2)) : gran;
+                cp_async16(buf + r * kARowBytes + (sw << 4), packed + (size_t)j * pitch + off);
             }
             uint8_t *dbuf = buf + kAVar * kARowBytes;
             for (int i = tid; i < 128 * kAStageSteps; i += kAThreads) {
@@ -294,7 +314,7 @@ __global__ void __launch_bounds__(kAThreads, 2) imma_dots_kernel(const uint8_t *
 #pragma unroll
             for (int rb = 0; rb < kARB; rb++) {
                 const int r0 = warp * (kARB * 16) + rb * 16 + g;
-                const int gran = (s * 4 + tq) ^ ((r0 & 1) << 2);   // r0 and r0+8 have the same parity
+                const int gran = (kAStageSteps == 2) ? ((s * 4 + tq) ^ ((r0 & 1) << 2)) : (s * 4 + tq);   // r0, r0+8: same parity
                 const uint4 wa = *reinterpret_cast<const uint4 *>(buf + r0 * kARowBytes + (gran << 4));
                 const uint4 wb = *reinterpret_cast<const uint4 *>(buf + (r0 + 8) * kARowBytes + (gran << 4));
 #pragma unroll
@@ -325,22 +345,90 @@ __global__ void __launch_bounds__(kAThreads, 2) imma_dots_kernel(const uint8_t *
     }
 }
 
-// U_j = sum of b over the missing samples of variant j (one warp per variant, fixed order)
-__global__ void miss_dots_kernel(const int64_t *__restrict__ mv_ptr, const int32_t *__restrict__ mv_idx,
-                                 const double *__restrict__ b, int64_t M, double *__restrict__ u) {
-    const int lane = threadIdx.x & 31;
-    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (j >= M) return;
-    double s = 0;
-    for (int64_t i = mv_ptr[j] + lane; i < mv_ptr[j + 1]; i += 32) s += b[mv_idx[i]];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) u[j] = s;
+// Sparse missing-genotype sums, tiled so that the gathered vector sits in shared memory:
+//   part[t][r] = sum over the entries of row r whose column lies in tile t of vec[column]
+// Rows are variants (vec = b, result U_j) or samples (vec = hm, result corr_n).  The entries are stored
+// tile-major -- [tile][row][ascending column] -- as 16-bit column offsets inside the tile, so a warp working
+// on 32 consecutive rows of one tile reads one contiguous stretch of memory, and the gathers hit shared
+// memory (8 bytes per value) instead of L2 (a 32-byte sector per value).  pos[t * R + r] is the start of
+// (tile t, row r); pos has n_tiles * R + 1 entries.
+constexpr int kSpTile = 8192;      // columns per tile: 64 KB of doubles
+constexpr int kSpRows = 2048;      // rows per CTA
+constexpr int kSpThreads = 512;
+// Persistent: at most one CTA per SM, so that the tensor-core kernel running beside it keeps its two CTAs per SM.
+__global__ void __launch_bounds__(kSpThreads) sparse_tile_sum_kernel(const int64_t *__restrict__ pos, const uint16_t *__restrict__ idx16,
+                                                                     const double *__restrict__ vec, int64_t R, int64_t C,
+                                                                     int n_tiles, double *__restrict__ part) {
+    extern __shared__ __align__(16) uint8_t smem_sp[];
+    double *sv = reinterpret_cast<double *>(smem_sp);
+    const int64_t n_chunks = (R + kSpRows - 1) / kSpRows;
+    const int64_t n_work = n_chunks * n_tiles;
+    const int sub = threadIdx.x & 7;
+    for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int t = (int)(w / n_chunks);
+        const int64_t chunk = w % n_chunks;
+        const int64_t c0 = (int64_t)t * kSpTile;
+        __syncthreads();
+        for (int i = threadIdx.x; i < kSpTile; i += kSpThreads) sv[i] = (c0 + i < C) ? vec[c0 + i] : 0.0;
+        __syncthreads();
+        const int64_t r0 = chunk * kSpRows, r1 = min(R, r0 + kSpRows);
+        const int64_t *pp = pos + (size_t)t * R;
+        // 8 lanes per row: a warp reads 4 contiguous stretches of indices; a fixed 3-step butterfly adds the partials
+        for (int64_t base = r0; base < r1; base += kSpThreads / 8) {     // uniform trip count: the shuffles need all lanes
+            const int64_t rb = base + (threadIdx.x >> 3);
+            const bool ok = rb < r1;
+            double s = 0;
+            if (ok) {
+                const int64_t hi = pp[rb + 1];
+                for (int64_t i = pp[rb] + sub; i < hi; i += 8) s += sv[idx16[i]];
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            if (ok && sub == 0) part[(size_t)t * R + rb] = s;
+        }
+    }
+}
+
+// cnt[t * R + r] = number of entries of row r (sorted list idx[ptr[r] .. ptr[r+1])) with column in tile t
+__global__ void sparse_tile_count_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx, int64_t R,
+                                         int64_t *__restrict__ cnt) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    if (r >= R) return;
+    const int64_t lo0 = ptr[r], hi0 = ptr[r + 1];
+    int64_t b[2];
+    for (int e = 0; e < 2; e++) {
+        int64_t lo = lo0, hi = hi0;
+        const int64_t key = (int64_t)(t + e) * kSpTile;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (idx[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        b[e] = lo;
+    }
+    cnt[(size_t)t * R + r] = b[1] - b[0];
+}
+
+// scatter the row-major lists into the tile-major 16-bit layout
+__global__ void sparse_tile_fill_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx, int64_t R,
+                                        const int64_t *__restrict__ pos, uint16_t *__restrict__ idx16) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    if (r >= R) return;
+    int64_t lo = ptr[r], hi = ptr[r + 1];
+    const int64_t key = (int64_t)t * kSpTile;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (idx[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    const int64_t o = pos[(size_t)t * R + r], n = pos[(size_t)t * R + r + 1] - o;
+    for (int64_t i = 0; i < n; i++) idx16[o + i] = (uint16_t)(idx[lo + i] - key);
 }
 
 // dot_j, e_j, hm_j = h_j + 3 e_j;  max|e| and H = sum h_j (deterministic)
-__global__ void __launch_bounds__(256) finalize_dots_kernel(const double *__restrict__ tq, int split, const double *__restrict__ u,
-                                                            const double *__restrict__ lut, int64_t M, double inv_mtotal,
+__global__ void __launch_bounds__(256) finalize_dots_kernel(const double *__restrict__ tq, int split, const double *__restrict__ upart,
+                                                            int n_utiles, const double *__restrict__ lut, int64_t M, double inv_mtotal,
                                                             double *__restrict__ e, double *__restrict__ hm, double *partial,
                                                             unsigned int *counter, double *scal) {
     __shared__ double sm[8];
@@ -351,7 +439,8 @@ __global__ void __launch_bounds__(256) finalize_dots_kernel(const double *__rest
         double t = 0;
         for (int s = 0; s < split; s++) t += tq[(size_t)s * M + j];
         const double l0 = lut[4 * j], inv = lut[4 * j + 1] - l0;
-        const double uj = u[j];
+        double uj = 0;
+        for (int t = 0; t < n_utiles; t++) uj += upart[(size_t)t * M + j];
         const double T = (unit_b == 0 ? 0.0 : unit_b * t) - 3.0 * uj;
         const double dot = inv * T + l0 * (sumb - uj);
         const double ej = dot * inv * inv_mtotal, hj = dot * l0 * inv_mtotal;
@@ -425,22 +514,29 @@ __global__ void __launch_bounds__(kBThreads, 2) imma_apply_kernel(const uint8_t 
         for (int t = 0; t < 4; t++)
 #pragma unroll
             for (int q = 0; q < 4; q++) acc[rb][t][q] = 0;
-    double tot[kBRB][4][2];   // [row-block][t0][row g / g+8]
-#pragma unroll
-    for (int rb = 0; rb < kBRB; rb++)
-#pragma unroll
-        for (int t = 0; t < 4; t++) tot[rb][t][0] = tot[rb][t][1] = 0;
-
+    // The int32 accumulators are turned into FP64 and written (first time) or added (later) to the CTA's own
+    // slice of rpart; no FP64 running totals are kept in registers (keeps the kernel at <= 168 registers so that a
+    // sparse-correction CTA fits beside two of these CTAs on an SM).
+    bool first_flush = true;
     auto flush = [&]() {
         const double w0 = scalbn(1.0, 14 * tq), w1 = scalbn(1.0, 14 * tq + 7);
 #pragma unroll
         for (int rb = 0; rb < kBRB; rb++)
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
-                tot[rb][t][0] += w0 * (double)(acc[rb][t][0] >> (2 * t)) + w1 * (double)(acc[rb][t][1] >> (2 * t));
-                tot[rb][t][1] += w0 * (double)(acc[rb][t][2] >> (2 * t)) + w1 * (double)(acc[rb][t][3] >> (2 * t));
-                acc[rb][t][0] = acc[rb][t][1] = acc[rb][t][2] = acc[rb][t][3] = 0;
-            }
+            for (int t = 0; t < 4; t++)
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    double v = w0 * (double)(acc[rb][t][2 * hh] >> (2 * t)) + w1 * (double)(acc[rb][t][2 * hh + 1] >> (2 * t));
+                    acc[rb][t][2 * hh] = acc[rb][t][2 * hh + 1] = 0;
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    const int64_t n = ((int64_t)byte0 + (warp * kBRB + rb) * 16 + g + hh * 8) * 4 + t;
+                    if (tq == 0 && n < N) {
+                        double *dst = rpart + (size_t)sp * N + n;
+                        *dst = first_flush ? v : (*dst + v);
+                    }
+                }
+        first_flush = false;
     };
 
     // ldmatrix row addresses: lanes 0-15 -> variants 0..15 of the K-block, lanes 16-31 -> variants 16..31
@@ -478,31 +574,18 @@ __global__ void __launch_bounds__(kBThreads, 2) imma_apply_kernel(const uint8_t 
     }
     cp_async_wait<0>();
     flush();
-#pragma unroll
-    for (int rb = 0; rb < kBRB; rb++)
-#pragma unroll
-        for (int t = 0; t < 4; t++)
-#pragma unroll
-            for (int hh = 0; hh < 2; hh++) {
-                double v = tot[rb][t][hh];
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                const int64_t n = ((int64_t)byte0 + (warp * kBRB + rb) * 16 + g + hh * 8) * 4 + t;
-                if (tq == 0 && n < N) rpart[(size_t)sp * N + n] = v;
-            }
 }
 
-// out_n = unit_e * sum_s R_n[s] + H - sum_{j in miss(n)} hm_j
-__global__ void combine_kernel(const double *__restrict__ rpart, int split, int64_t N, const int64_t *__restrict__ ms_ptr,
-                               const int32_t *__restrict__ ms_idx, const double *__restrict__ hm,
-                               const double *__restrict__ scal, double *__restrict__ out) {
+// out_n = unit_e * sum_s R_n[s] + H - corr_n
+__global__ void combine_kernel(const double *__restrict__ rpart, int split, int64_t N, const double *__restrict__ cpart,
+                               int n_ctiles, const double *__restrict__ scal, double *__restrict__ out) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     double r = 0;
     for (int s = 0; s < split; s++) r += rpart[(size_t)s * N + n];
-    const double unit_e = scal[S_UNITE];
     double corr = 0;
-    for (int64_t i = ms_ptr[n]; i < ms_ptr[n + 1]; i++) corr += hm[ms_idx[i]];
+    for (int t = 0; t < n_ctiles; t++) corr += cpart[(size_t)t * N + n];
+    const double unit_e = scal[S_UNITE];
     out[n] = (unit_e == 0 ? 0.0 : unit_e * r) + scal[S_H] - corr;
 }
 
@@ -634,8 +717,37 @@ void imma_prepare(Context &c) {
         p->dfrag.ensure((size_t)p->ksteps * 2048);
         p->efrag.ensure((size_t)p->kblocks * 256);
         p->tq.ensure((size_t)p->split_a * M);
-        p->u.ensure(M); p->e.ensure(M); p->hm.ensure(M);
+        p->e.ensure(M); p->hm.ensure(M);
+        p->n_stiles = (int)((N + kSpTile - 1) / kSpTile);
+        p->n_vtiles = (int)((M + kSpTile - 1) / kSpTile);
+        p->upart.ensure((size_t)p->n_stiles * M);
+        p->cpart.ensure((size_t)p->n_vtiles * N);
+        auto tile_major = [&](const DevBuf<int64_t> &ptr, const DevBuf<int32_t> &idx, int64_t R, int nt, DevBuf<int64_t> &pos,
+                              DevBuf<uint16_t> &i16) {
+            const size_t cells = (size_t)nt * R;
+            pos.ensure(cells + 1);
+            i16.ensure(std::max<int64_t>(p->nnz, 1));
+            SGB_CUDA(cudaMemsetAsync(pos.get() + cells, 0, sizeof(int64_t), c.stream));
+            sparse_tile_count_kernel<<<dim3((unsigned)((R + 255) / 256), nt), 256, 0, c.stream>>>(ptr.get(), idx.get(), R, pos.get());
+            SGB_CHECK_LAUNCH();
+            thrust::exclusive_scan(thrust::cuda::par.on(c.stream), pos.get(), pos.get() + cells + 1, pos.get());
+            sparse_tile_fill_kernel<<<dim3((unsigned)((R + 255) / 256), nt), 256, 0, c.stream>>>(ptr.get(), idx.get(), R, pos.get(),
+                                                                                               i16.get());
+            SGB_CHECK_LAUNCH();
+        };
+        tile_major(p->mv_ptr, p->mv_idx, M, p->n_stiles, p->mv_pos, p->mv_i16);
+        tile_major(p->ms_ptr, p->ms_idx, N, p->n_vtiles, p->ms_pos, p->ms_i16);
+        c.sync();
+        // the row-major 32-bit lists are only needed to build the tile-major ones
+        p->mv_idx.release(); p->ms_idx.release();
+        SGB_CUDA(cudaFuncSetAttribute(sparse_tile_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpTile * 8));
         p->rpart.ensure((size_t)p->split_b * N);
+        {
+            int lo_prio = 0, hi_prio = 0;
+            SGB_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+            SGB_CUDA(cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, hi_prio));
+        }
+        for (cudaEvent_t *e : {&p->ev_in, &p->ev_u, &p->ev_hm, &p->ev_corr}) SGB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         p->scal.ensure(16);
         p->red.ensure(4 * 1024);
         p->counter.ensure(8);
@@ -656,10 +768,23 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
     if (!p) throw Error(SGB_ERR_STATE, "the IMMA product kernel is not prepared");
     const int64_t M = c.M, N = c.N;
     const int G = (int)std::min<int64_t>(1024, std::max<int64_t>(1, (N + 2047) / 2048));
-    const int Gm = (int)std::min<int64_t>(1024, std::max<int64_t>(1, (M + 1023) / 1024));
+    const int Gm = (int)std::min<int64_t>(1024, std::max<int64_t>(1, (M + 255) / 256));
+    // In profiling mode everything runs serially on the main stream so that each kernel can be timed.
+    cudaStream_t side = c.profiling ? c.stream : p->side;
+    const bool fork = side != c.stream;
     for (int col = 0; col < k; col++) {
         const double *b = b_all + (size_t)col * N;
         double *out = out_all + (size_t)col * N;
+        if (fork) {
+            SGB_CUDA(cudaEventRecord(p->ev_in, c.stream));
+            SGB_CUDA(cudaStreamWaitEvent(side, p->ev_in, 0));
+        }
+        c.prof_begin();
+        sparse_tile_sum_kernel<<<c.sm_count, kSpThreads, kSpTile * 8, side>>>(p->mv_pos.get(), p->mv_i16.get(), b, M, N,
+                                                                                p->n_stiles, p->upart.get());
+        SGB_CHECK_LAUNCH();
+        c.prof_end("sparse_tile_sum_kernel (U_j)");
+        if (fork) SGB_CUDA(cudaEventRecord(p->ev_u, side));
         c.prof_begin();
         absmax_sum_kernel<<<G, 256, 0, c.stream>>>(b, N, p->red.get(), p->counter.get(), p->scal.get());
         SGB_CHECK_LAUNCH();
@@ -672,30 +797,38 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
             c.packed.get(), c.pitch, M, p->ksteps, p->split_a, p->dfrag.get(), p->tq.get());
         SGB_CHECK_LAUNCH();
         c.prof_end("imma_dots_kernel");
+        if (fork) SGB_CUDA(cudaStreamWaitEvent(c.stream, p->ev_u, 0));
         c.prof_begin();
-        miss_dots_kernel<<<(unsigned)((M + 7) / 8), 256, 0, c.stream>>>(p->mv_ptr.get(), p->mv_idx.get(), b, M, p->u.get());
-        SGB_CHECK_LAUNCH();
-        c.prof_end("miss_dots_kernel");
-        c.prof_begin();
-        finalize_dots_kernel<<<Gm, 256, 0, c.stream>>>(p->tq.get(), p->split_a, p->u.get(), c.lut.get(), M,
+        finalize_dots_kernel<<<Gm, 256, 0, c.stream>>>(p->tq.get(), p->split_a, p->upart.get(), p->n_stiles, c.lut.get(), M,
                                                        1.0 / (double)c.M_total, p->e.get(), p->hm.get(), p->red.get() + 2048,
                                                        p->counter.get() + 1, p->scal.get());
         SGB_CHECK_LAUNCH();
+        if (fork) {
+            SGB_CUDA(cudaEventRecord(p->ev_hm, c.stream));
+            SGB_CUDA(cudaStreamWaitEvent(side, p->ev_hm, 0));
+        }
         digits_e_kernel<<<(unsigned)((p->kblocks * 32 + 255) / 256), 256, 0, c.stream>>>(p->e.get(), M, p->kblocks * 32,
                                                                                       p->scal.get(), p->efrag.get());
         SGB_CHECK_LAUNCH();
         c.prof_end("imma_finalize+digits_e");
         c.prof_begin();
+        sparse_tile_sum_kernel<<<c.sm_count, kSpThreads, kSpTile * 8, side>>>(p->ms_pos.get(), p->ms_i16.get(), p->hm.get(), N,
+                                                                                M, p->n_vtiles, p->cpart.get());
+        SGB_CHECK_LAUNCH();
+        c.prof_end("sparse_tile_sum_kernel (corr_n)");
+        if (fork) SGB_CUDA(cudaEventRecord(p->ev_corr, side));
+        c.prof_begin();
         imma_apply_kernel<<<dim3((unsigned)((N + kBSamp - 1) / kBSamp), p->split_b), kBThreads, kBStages * kBStageBytes,
                             c.stream>>>(c.packed.get(), c.pitch, M, N, p->kblocks, p->split_b, p->efrag.get(), p->rpart.get());
         SGB_CHECK_LAUNCH();
         c.prof_end("imma_apply_kernel");
+        if (fork) SGB_CUDA(cudaStreamWaitEvent(c.stream, p->ev_corr, 0));
         c.prof_begin();
-        combine_kernel<<<(unsigned)((N + 255) / 256), 256, 0, c.stream>>>(p->rpart.get(), p->split_b, N, p->ms_ptr.get(),
-                                                                        p->ms_idx.get(), p->hm.get(), p->scal.get(), out);
+        combine_kernel<<<(unsigned)((N + 255) / 256), 256, 0, c.stream>>>(p->rpart.get(), p->split_b, N, p->cpart.get(),
+                                                                        p->n_vtiles, p->scal.get(), out);
         SGB_CHECK_LAUNCH();
         c.prof_end("combine_kernel");
-        c.stats.n_kernel_launches += 8;
+        c.stats.n_kernel_launches += 9;
         c.stats.n_product_launches += 1;
     }
 }
