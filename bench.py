@@ -32,6 +32,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# NCCL_DEBUG=VERSION makes NCCL print a banner on stdout; rank 0 must print exactly one JSON line.
+if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 N_SAMP = int(os.environ.get("SGB_BENCH_N", 430000))
 N_VAR = int(os.environ.get("SGB_BENCH_M", 100000))
@@ -60,7 +63,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -182,8 +185,13 @@ def run_gpu(args):
         ctx.set_kernel(args.kernel)
 
     def barrier():
+        # torch's NCCL communicator and the library's own one must never have kernels in flight at the same time
+        # (two communicators progressing in different orders on different ranks can deadlock): drain both sides.
         if dist is not None:
+            import torch
+            torch.cuda.synchronize()
             dist.barrier()
+            torch.cuda.synchronize()
 
     def max_over_ranks(x):
         if dist is None:
@@ -193,6 +201,11 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def note(msg):
+        if os.environ.get("SGB_BENCH_VERBOSE"):
+            print("[bench rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
+
+    note("stored %d variants" % m_local)
     rng = np.random.default_rng(1)
     b_host = rng.standard_normal(N_SAMP)
     d_b = ctx.device_vector(b_host)
@@ -201,6 +214,7 @@ def run_gpu(args):
     # ---- device-resident throughput (value) ----
     for _ in range(max(3, args.warmup)):
         ctx.grm_mv_device(d_b, d_out, 1)
+    note("warm-up done")
     ctx.reset_stats()
     sampler = ClockSampler(local_rank)
     barrier()
@@ -209,6 +223,7 @@ def run_gpu(args):
     ms = ctx.time_products_device(d_b, d_out, 1, args.steps)       # CUDA events on the launching stream, synced both sides
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    note("timed region done: %.3f ms" % ms)
     ms = max_over_ranks(ms)
     st = ctx.stats()
     launches = int(st["n_kernel_launches"])
@@ -224,6 +239,7 @@ def run_gpu(args):
         out_host = ctx.get_crossprod_b_grm(b_host)
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    note("e2e done")
 
     # ---- per-kernel event timing (separate, untimed pass) ----
     ctx.set_profiling(True)
@@ -231,7 +247,15 @@ def run_gpu(args):
         ctx.grm_mv_device(d_b, d_out, 1)
     ktimes = ctx.kernel_times()
     ctx.set_profiling(False)
+    note("profiling pass done")
 
+    # orderly teardown on every rank: library communicator first, then torch's process group
+    d_b.free(); d_out.free()
+    ctx.close()
+    if dist is not None:
+        barrier()
+        dist.destroy_process_group()
+    note("teardown done")
     if rank != 0:
         return
     peak, peak_src = measured_peaks()
@@ -261,14 +285,12 @@ def run_gpu(args):
         cb, _ = cpu_product_rate(3, 1)
         line["cpu_baseline"] = cb
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", default=None, choices=[None, "auto", "simt", "imma"])

@@ -289,3 +289,18 @@ def test_error_behaviour(gpu, fx):
         X = np.ones((5, 1))
         c.saige_fit_AI_PCG_binary(rsetup.Fit0(np.zeros(5), np.zeros(1), np.zeros(5), np.full(5, .5), "binomial"), X, [1, .5])
     c.close()
+
+
+def test_two_gpu_sharding_matches_single_gpu():
+    """Variant-sharded product / PCG / fit over NCCL on 2 GPUs (skipped on a 1-GPU box)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(root, "tests", "multi_gpu_check.py")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    assert r.returncode == 0, r.stdout.decode()[-3000:]
