@@ -59,6 +59,7 @@ struct ImmaPlan {
     DevBuf<int64_t> ms_pos;  // [n_vtiles * N + 1] tile-major start of (variant tile, sample)
     DevBuf<uint16_t> ms_i16; // [nnz] variant offset inside the tile
     int n_stiles = 0, n_vtiles = 0;
+    int opt_fork = 1, opt_grid_mult = 2, opt_stages = 3;   // tuning knobs (env: SGB_SPARSE_FORK, SGB_SPARSE_GRID_MULT, SGB_DOTS_STAGES)
     DevBuf<double> upart;    // [n_stiles][M] U_j per sample tile
     DevBuf<double> cpart;    // [n_vtiles][N] output correction per variant tile
     cudaStream_t side = nullptr;   // the sparse corrections run beside the tensor-core kernels
@@ -80,8 +81,8 @@ enum { S_MAXB = 0, S_SUMB = 1, S_UNITB = 2, S_MAXE = 3, S_H = 4, S_UNITE = 5 };
 constexpr int kAThreads = 128;   // phase A: 4 warps x 4 row-blocks x 16 variants
 constexpr int kARB = 4;
 constexpr int kAVar = 4 * kARB * 16;          // 256 variants per CTA
-constexpr int kAStageSteps = 1;               // K-steps (256 samples = 64 B per row) per pipeline stage
-constexpr int kAStages = 4;                   // 4 x 18 KB x 2 CTAs/SM = 144 KB: leaves room for a sparse-correction CTA
+constexpr int kAStageSteps = 2;               // K-steps (256 samples = 64 B per row) per pipeline stage
+// pipeline depth is a template parameter (3 stages of 36 KB x 2 CTAs/SM = 221 KB is the default)
 constexpr int kARowBytes = 64 * kAStageSteps; // 128 B per row per stage
 constexpr int kAStageBytes = kAVar * kARowBytes + 2048 * kAStageSteps;
 
@@ -228,6 +229,7 @@ __global__ void digits_e_kernel(const double *__restrict__ e, int64_t M, int64_t
 
 // ------------------------------------------------------------------------------------------------
 // Phase A: T'_j = sum_n c'_nj * B_n  (c' = raw 2-bit code, B_n = quantised b) for 256 variants x a K-step range.
+template <int kAStages>
 __global__ void __launch_bounds__(kAThreads, 2) imma_dots_kernel(const uint8_t *__restrict__ packed, size_t pitch, int64_t M,
                                                                  int64_t ksteps, int split, const int8_t *__restrict__ dfrag,
                                                                  double *__restrict__ tq_out) {
@@ -352,40 +354,66 @@ __global__ void __launch_bounds__(kAThreads, 2) imma_dots_kernel(const uint8_t *
 // on 32 consecutive rows of one tile reads one contiguous stretch of memory, and the gathers hit shared
 // memory (8 bytes per value) instead of L2 (a 32-byte sector per value).  pos[t * R + r] is the start of
 // (tile t, row r); pos has n_tiles * R + 1 entries.
-constexpr int kSpTile = 8192;      // columns per tile: 64 KB of doubles
-constexpr int kSpRows = 2048;      // rows per CTA
+constexpr int kSpTile = 4096;      // columns per tile: 32 KB of doubles
+constexpr int kSpRows = 1024;      // rows per work item
 constexpr int kSpThreads = 512;
-// Persistent: at most one CTA per SM, so that the tensor-core kernel running beside it keeps its two CTAs per SM.
+constexpr int kSpCap = 24576;      // index entries staged per piece (48 KB); a work item holds ~ kSpRows * 20 at 0.5 % missing
+constexpr int kSpSmem = kSpTile * 8 + kSpCap * 2 + (kSpRows + 1) * 8;
+// Persistent (grid <= number of SMs).  Per work item (tile t, kSpRows rows): the vector tile, the rows' start
+// offsets and the whole contiguous index range of those rows are streamed into shared memory with coalesced
+// 16-byte cp.async copies (deep memory-level parallelism, no dependent global loads); then thread <-> row walks its
+// own segment out of shared memory.  Summation order inside a row is fixed (four interleaved partial sums).
 __global__ void __launch_bounds__(kSpThreads) sparse_tile_sum_kernel(const int64_t *__restrict__ pos, const uint16_t *__restrict__ idx16,
                                                                      const double *__restrict__ vec, int64_t R, int64_t C,
                                                                      int n_tiles, double *__restrict__ part) {
     extern __shared__ __align__(16) uint8_t smem_sp[];
     double *sv = reinterpret_cast<double *>(smem_sp);
+    uint16_t *sidx = reinterpret_cast<uint16_t *>(smem_sp + kSpTile * 8);
+    int64_t *spos = reinterpret_cast<int64_t *>(smem_sp + kSpTile * 8 + kSpCap * 2);
     const int64_t n_chunks = (R + kSpRows - 1) / kSpRows;
     const int64_t n_work = n_chunks * n_tiles;
-    const int sub = threadIdx.x & 7;
     for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
         const int t = (int)(w / n_chunks);
         const int64_t chunk = w % n_chunks;
         const int64_t c0 = (int64_t)t * kSpTile;
-        __syncthreads();
-        for (int i = threadIdx.x; i < kSpTile; i += kSpThreads) sv[i] = (c0 + i < C) ? vec[c0 + i] : 0.0;
-        __syncthreads();
         const int64_t r0 = chunk * kSpRows, r1 = min(R, r0 + kSpRows);
-        const int64_t *pp = pos + (size_t)t * R;
-        // 8 lanes per row: a warp reads 4 contiguous stretches of indices; a fixed 3-step butterfly adds the partials
-        for (int64_t base = r0; base < r1; base += kSpThreads / 8) {     // uniform trip count: the shuffles need all lanes
-            const int64_t rb = base + (threadIdx.x >> 3);
-            const bool ok = rb < r1;
-            double s = 0;
-            if (ok) {
-                const int64_t hi = pp[rb + 1];
-                for (int64_t i = pp[rb] + sub; i < hi; i += 8) s += sv[idx16[i]];
+        const int nrow = (int)(r1 - r0);
+        const int64_t *pp = pos + (size_t)t * R + r0;
+        __syncthreads();                                   // previous work item fully consumed
+        for (int i = threadIdx.x; i <= nrow; i += kSpThreads) spos[i] = pp[i];
+        for (int i = threadIdx.x; i < kSpTile; i += kSpThreads) sv[i] = (c0 + i < C) ? vec[c0 + i] : 0.0;
+        const int64_t e0 = pp[0], e1 = pp[nrow];
+        const int64_t a0 = e0 & ~(int64_t)7;               // 16-byte aligned start of the index range
+        double acc[kSpRows / kSpThreads];
+#pragma unroll
+        for (int k = 0; k < kSpRows / kSpThreads; k++) acc[k] = 0;
+        for (int64_t pc = a0; pc < e1; pc += kSpCap) {     // almost always a single piece
+            const int64_t pe = min(e1, pc + kSpCap);
+            const int ngran = (int)((pe - pc + 7) >> 3);
+            __syncthreads();
+            for (int i = threadIdx.x; i < ngran; i += kSpThreads) cp_async16(sidx + i * 8, idx16 + pc + (int64_t)i * 8);
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < kSpRows / kSpThreads; k++) {
+                const int r = threadIdx.x + k * kSpThreads;
+                if (r < nrow) {
+                    const int64_t lo = max(spos[r], pc), hi = min(spos[r + 1], pe);
+                    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+                    int64_t i = lo;
+                    for (; i + 4 <= hi; i += 4) {
+                        s0 += sv[sidx[i - pc]]; s1 += sv[sidx[i - pc + 1]]; s2 += sv[sidx[i - pc + 2]]; s3 += sv[sidx[i - pc + 3]];
+                    }
+                    for (; i < hi; i++) s0 += sv[sidx[i - pc]];
+                    if (hi > lo) acc[k] += (s0 + s1) + (s2 + s3);
+                }
             }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
-            if (ok && sub == 0) part[(size_t)t * R + rb] = s;
+        }
+#pragma unroll
+        for (int k = 0; k < kSpRows / kSpThreads; k++) {
+            const int r = threadIdx.x + k * kSpThreads;
+            if (r < nrow) part[(size_t)t * R + r0 + r] = acc[k];
         }
     }
 }
@@ -726,7 +754,7 @@ void imma_prepare(Context &c) {
                               DevBuf<uint16_t> &i16) {
             const size_t cells = (size_t)nt * R;
             pos.ensure(cells + 1);
-            i16.ensure(std::max<int64_t>(p->nnz, 1));
+            i16.ensure((size_t)p->nnz + 16);   // +16: the staged copy rounds the range up to 16-byte granules
             SGB_CUDA(cudaMemsetAsync(pos.get() + cells, 0, sizeof(int64_t), c.stream));
             sparse_tile_count_kernel<<<dim3((unsigned)((R + 255) / 256), nt), 256, 0, c.stream>>>(ptr.get(), idx.get(), R, pos.get());
             SGB_CHECK_LAUNCH();
@@ -740,7 +768,7 @@ void imma_prepare(Context &c) {
         c.sync();
         // the row-major 32-bit lists are only needed to build the tile-major ones
         p->mv_idx.release(); p->ms_idx.release();
-        SGB_CUDA(cudaFuncSetAttribute(sparse_tile_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpTile * 8));
+        SGB_CUDA(cudaFuncSetAttribute(sparse_tile_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmem));
         p->rpart.ensure((size_t)p->split_b * N);
         {
             int lo_prio = 0, hi_prio = 0;
@@ -753,7 +781,12 @@ void imma_prepare(Context &c) {
         p->counter.ensure(8);
         SGB_CUDA(cudaMemsetAsync(p->counter.get(), 0, sizeof(unsigned int) * 8, c.stream));
         SGB_CUDA(cudaMemsetAsync(p->scal.get(), 0, sizeof(double) * 16, c.stream));
-        SGB_CUDA(cudaFuncSetAttribute(imma_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAStages * kAStageBytes));
+        SGB_CUDA(cudaFuncSetAttribute(imma_dots_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kAStageBytes));
+        if (4 * kAStageBytes <= 227 * 1024)
+            SGB_CUDA(cudaFuncSetAttribute(imma_dots_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kAStageBytes));
+        if (const char *e = getenv("SGB_SPARSE_FORK")) p->opt_fork = atoi(e);
+        if (const char *e = getenv("SGB_SPARSE_GRID_MULT")) p->opt_grid_mult = std::max(1, atoi(e));
+        if (const char *e = getenv("SGB_DOTS_STAGES")) p->opt_stages = (atoi(e) == 4) ? 4 : 3;
         SGB_CUDA(cudaFuncSetAttribute(imma_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBStages * kBStageBytes));
         c.sync();
     } catch (...) {
@@ -770,7 +803,8 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
     const int G = (int)std::min<int64_t>(1024, std::max<int64_t>(1, (N + 2047) / 2048));
     const int Gm = (int)std::min<int64_t>(1024, std::max<int64_t>(1, (M + 255) / 256));
     // In profiling mode everything runs serially on the main stream so that each kernel can be timed.
-    cudaStream_t side = c.profiling ? c.stream : p->side;
+    cudaStream_t side = (c.profiling || !p->opt_fork) ? c.stream : p->side;
+    const int sp_grid = c.sm_count * p->opt_grid_mult;
     const bool fork = side != c.stream;
     for (int col = 0; col < k; col++) {
         const double *b = b_all + (size_t)col * N;
@@ -780,7 +814,7 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
             SGB_CUDA(cudaStreamWaitEvent(side, p->ev_in, 0));
         }
         c.prof_begin();
-        sparse_tile_sum_kernel<<<c.sm_count, kSpThreads, kSpTile * 8, side>>>(p->mv_pos.get(), p->mv_i16.get(), b, M, N,
+        sparse_tile_sum_kernel<<<sp_grid, kSpThreads, kSpSmem, side>>>(p->mv_pos.get(), p->mv_i16.get(), b, M, N,
                                                                                 p->n_stiles, p->upart.get());
         SGB_CHECK_LAUNCH();
         c.prof_end("sparse_tile_sum_kernel (U_j)");
@@ -793,8 +827,12 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
         SGB_CHECK_LAUNCH();
         c.prof_end("imma_prep_b (absmax+digits)");
         c.prof_begin();
-        imma_dots_kernel<<<dim3((unsigned)((M + kAVar - 1) / kAVar), p->split_a), kAThreads, kAStages * kAStageBytes, c.stream>>>(
-            c.packed.get(), c.pitch, M, p->ksteps, p->split_a, p->dfrag.get(), p->tq.get());
+        if (p->opt_stages == 3)
+            imma_dots_kernel<3><<<dim3((unsigned)((M + kAVar - 1) / kAVar), p->split_a), kAThreads, 3 * kAStageBytes, c.stream>>>(
+                c.packed.get(), c.pitch, M, p->ksteps, p->split_a, p->dfrag.get(), p->tq.get());
+        else
+            imma_dots_kernel<4><<<dim3((unsigned)((M + kAVar - 1) / kAVar), p->split_a), kAThreads, 4 * kAStageBytes, c.stream>>>(
+                c.packed.get(), c.pitch, M, p->ksteps, p->split_a, p->dfrag.get(), p->tq.get());
         SGB_CHECK_LAUNCH();
         c.prof_end("imma_dots_kernel");
         if (fork) SGB_CUDA(cudaStreamWaitEvent(c.stream, p->ev_u, 0));
@@ -812,7 +850,7 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
         SGB_CHECK_LAUNCH();
         c.prof_end("imma_finalize+digits_e");
         c.prof_begin();
-        sparse_tile_sum_kernel<<<c.sm_count, kSpThreads, kSpTile * 8, side>>>(p->ms_pos.get(), p->ms_i16.get(), p->hm.get(), N,
+        sparse_tile_sum_kernel<<<sp_grid, kSpThreads, kSpSmem, side>>>(p->ms_pos.get(), p->ms_i16.get(), p->hm.get(), N,
                                                                                 M, p->n_vtiles, p->cpart.get());
         SGB_CHECK_LAUNCH();
         c.prof_end("sparse_tile_sum_kernel (corr_n)");
