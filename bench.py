@@ -287,6 +287,68 @@ def run_gpu(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------ null-model fit (secondary metric)
+def synth_phenotype(ctx, n, m, seed=7, n_causal=1000):
+    """x1 ~ N(0,1), x2 ~ Bernoulli(0.5), g = sqrt(0.3) * standardised sum of causal columns."""
+    rng = np.random.default_rng(seed)
+    x1, x2 = rng.standard_normal(n), (rng.random(n) < 0.5).astype(np.float64)
+    g = np.zeros(n)
+    for j in rng.choice(m, size=min(n_causal, m), replace=False):
+        ds = ctx.get_geno_ds(int(j))
+        ds = np.where(np.isnan(ds), np.nanmean(ds), ds)
+        sd = ds.std()
+        if sd > 0:
+            g += (ds - ds.mean()) / sd * rng.standard_normal()
+    g = np.sqrt(0.3) * (g - g.mean()) / g.std()
+    y = (rng.random(n) < 1 / (1 + np.exp(-(-2 + 0.5 * x1 + 0.5 * x2 + g)))).astype(np.float64)
+    yy = x1 + x2 + g + rng.standard_normal(n)
+    return dict(x1=x1, x2=x2, y=y, yy=yy)
+
+
+def run_fit(args):
+    """Null-model fit wall time (saige_fit_AI_PCG_* + saige_calc_var_ratio_*) on synthetic data, one GPU."""
+    import saigegds_b200 as sg
+    from saigegds_b200 import rsetup
+    n, m = args.fit_n, args.fit_m
+    ctx = sg.Context(0)
+    t0 = time.perf_counter()
+    ctx.store_synthetic(n, m, seed=200, missing_rate=MISSING)
+    t_store = time.perf_counter() - t0
+    ph = synth_phenotype(ctx, n, m)
+    X, _ = rsetup.qr_transform(rsetup.model_matrix(ph, ["x1", "x2"]))
+    param = sg.make_param(verbose=bool(os.environ.get("SGB_BENCH_VERBOSE")))
+    out = {}
+    for trait in args.fit_traits.split(","):
+        ctx.reset_stats()
+        t0 = time.perf_counter()
+        if trait == "binary":
+            fit0 = rsetup.glm_binomial(X, ph["y"])
+            noK = rsetup.null_model_binary(X, fit0)
+            glmm = ctx.saige_fit_AI_PCG_binary(fit0, X, rsetup.initial_tau_binary(), param)
+        else:
+            f = rsetup.glm_gaussian(X, ph["yy"])
+            fit0 = rsetup.glm_gaussian(X, rsetup.rank_norm(f.residuals) * rsetup.sd(f.residuals))
+            noK = rsetup.null_model_quant(X, fit0)
+            glmm = ctx.saige_fit_AI_PCG_quant(fit0, noK.X1, rsetup.initial_tau_quant(fit0), param)
+        t_fit = time.perf_counter() - t0
+        st_fit = ctx.stats()
+        t0 = time.perf_counter()
+        ctx.set_seed(200)
+        fn = ctx.saige_calc_var_ratio_binary if trait == "binary" else ctx.saige_calc_var_ratio_quant
+        vr = fn(fit0, glmm, noK, param, ctx.sample_int(m))
+        t_vr = time.perf_counter() - t0
+        st = ctx.stats()
+        out[trait] = {"fit_s": t_fit, "var_ratio_s": t_vr, "tau": [float(x) for x in glmm["tau"]],
+                      "converged": glmm["converged"], "products_fit": int(st_fit["n_products"]),
+                      "products_total": int(st["n_products"]), "pcg_solves": int(st["n_pcg_solves"]),
+                      "pcg_iterations": int(st["n_pcg_iterations"]), "var_ratio_mean": float(np.mean(vr["ratio"])),
+                      "n_markers": int(len(vr["ratio"]))}
+    line = {"metric": "null_model_fit_wall_s", "unit": "s", "n_gpus": 1, "higher_is_better": False, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": "synthetic N=%d M=%d null fit + variance ratio" % (n, m)},
+            "store_s": t_store, "traits": out}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -295,9 +357,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", default=None, choices=[None, "auto", "simt", "imma"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--mode", default="product", choices=["product", "fit"],
+                    help="product: the headline metric; fit: null-model fit wall time (secondary metric)")
+    ap.add_argument("--fit-n", type=int, default=50000)
+    ap.add_argument("--fit-m", type=int, default=100000)
+    ap.add_argument("--fit-traits", default="binary,quantitative")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "fit":
+        run_fit(args)
     else:
         run_gpu(args)
 
