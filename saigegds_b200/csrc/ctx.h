@@ -149,7 +149,14 @@ struct Context {
     void require_stored() const {
         if (!stored) throw Error(SGB_ERR_STATE, "no genotypes stored: call sgb_store_2b_geno first");
     }
-    void sync() { SGB_CUDA(cudaStreamSynchronize(stream)); }
+    volatile int *async_err = nullptr;   // pinned flag copied back after every fused-kernel launch
+    void sync() {
+        SGB_CUDA(cudaStreamSynchronize(stream));
+        if (async_err && *async_err) {
+            *async_err = 0;
+            throw Error(SGB_ERR_CUDA, "the fused GRM kernel timed out waiting for another CTA (bounded spin)");
+        }
+    }
     void h2d(void *dst, const void *src, size_t bytes) {
         SGB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
     }

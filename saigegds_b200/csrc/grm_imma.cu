@@ -33,6 +33,7 @@
 #include <thrust/scan.h>
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 
 #include "ctx.h"
@@ -59,7 +60,17 @@ struct ImmaPlan {
     DevBuf<int64_t> ms_pos;  // [n_vtiles * N + 1] tile-major start of (variant tile, sample)
     DevBuf<uint16_t> ms_i16; // [nnz] variant offset inside the tile
     int n_stiles = 0, n_vtiles = 0;
-    int opt_fork = 1, opt_grid_mult = 2, opt_stages = 3;   // tuning knobs (env: SGB_SPARSE_FORK, SGB_SPARSE_GRID_MULT, SGB_DOTS_STAGES)
+    int opt_fork = 1, opt_grid_mult = 2, opt_stages = 3;
+    // fused single-pass kernel (grm_fused.cuh)
+    bool fused_ok = false;
+    int f_ks_per_cta = 0, f_grid = 0;
+    int64_t f_tiles = 0;
+    DevBuf<int8_t> dfrag128;
+    DevBuf<unsigned long long> f_acc;
+    DevBuf<unsigned int> f_counter;
+    DevBuf<double> f_rout, f_htotal, f_u;
+    DevBuf<int> f_err;
+    PinBuf<int> f_herr;   // tuning knobs (env: SGB_SPARSE_FORK, SGB_SPARSE_GRID_MULT, SGB_DOTS_STAGES)
     DevBuf<double> upart;    // [n_stiles][M] U_j per sample tile
     DevBuf<double> cpart;    // [n_vtiles][N] output correction per variant tile
     cudaStream_t side = nullptr;   // the sparse corrections run beside the tensor-core kernels
@@ -679,6 +690,8 @@ __global__ void miss_by_sample_kernel(const uint8_t *__restrict__ packed, size_t
         for (int k = 0; k < 4; k++) if (q * 4 + k < N) counts[q * 4 + k] = cnt[k];
 }
 
+#include "grm_fused.cuh"
+
 int pick_split(int64_t tiles, int slots, int max_split) {
     int best = 1;
     double best_eff = 0;
@@ -695,6 +708,7 @@ int pick_split(int64_t tiles, int slots, int max_split) {
 bool imma_available(const Context &c) { return c.imma != nullptr; }
 
 void imma_release(Context &c) {
+    c.async_err = nullptr;   // points into the plan's pinned flag
     delete c.imma;
     c.imma = nullptr;
 }
@@ -784,6 +798,33 @@ void imma_prepare(Context &c) {
         SGB_CUDA(cudaFuncSetAttribute(imma_dots_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kAStageBytes));
         if (4 * kAStageBytes <= 227 * 1024)
             SGB_CUDA(cudaFuncSetAttribute(imma_dots_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kAStageBytes));
+        {
+            const int ks_per = (int)((p->ksteps + c.sm_count - 1) / c.sm_count);
+            int coop = 0;
+            SGB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.dev));
+            const char *fe = getenv("SGB_FUSED");
+            if (coop && ks_per >= 1 && ks_per <= kFMaxKs && !(fe && atoi(fe) == 0)) {
+                SGB_CUDA(cudaFuncSetAttribute(imma_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmemBytes));
+                int per_sm = 0;
+                SGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, imma_fused_kernel, kFThreads, kFSmemBytes));
+                p->f_ks_per_cta = ks_per;
+                p->f_grid = (int)((p->ksteps + ks_per - 1) / ks_per);
+                p->f_tiles = (M + kFV - 1) / kFV;
+                if (per_sm >= 1 && p->f_grid <= per_sm * c.sm_count) {
+                    p->dfrag128.ensure((size_t)p->ksteps * 2048);
+                    p->f_acc.ensure((size_t)p->f_tiles * kFV * 2);
+                    p->f_counter.ensure((size_t)p->f_tiles);
+                    p->f_rout.ensure(N);
+                    p->f_u.ensure(M);
+                    p->f_htotal.ensure(1);
+                    p->f_err.ensure(1);
+                    p->f_herr.ensure(1);
+                    *p->f_herr.p = 0;
+                    SGB_CUDA(cudaMemsetAsync(p->f_err.get(), 0, sizeof(int), c.stream));
+                    p->fused_ok = true;
+                }
+            }
+        }
         if (const char *e = getenv("SGB_SPARSE_FORK")) p->opt_fork = atoi(e);
         if (const char *e = getenv("SGB_SPARSE_GRID_MULT")) p->opt_grid_mult = std::max(1, atoi(e));
         if (const char *e = getenv("SGB_DOTS_STAGES")) p->opt_stages = (atoi(e) == 4) ? 4 : 3;
@@ -805,6 +846,54 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
     // In profiling mode everything runs serially on the main stream so that each kernel can be timed.
     cudaStream_t side = (c.profiling || !p->opt_fork) ? c.stream : p->side;
     const int sp_grid = c.sm_count * p->opt_grid_mult;
+    if (p->fused_ok && c.kernel != SGB_KERNEL_IMMA_TWOPASS) {
+        c.async_err = p->f_herr.p;
+        for (int col = 0; col < k; col++) {
+            const double *b = b_all + (size_t)col * N;
+            double *out = out_all + (size_t)col * N;
+            c.prof_begin();
+            sparse_tile_sum_kernel<<<sp_grid, kSpThreads, kSpSmem, c.stream>>>(p->mv_pos.get(), p->mv_i16.get(), b, M, N,
+                                                                            p->n_stiles, p->upart.get());
+            SGB_CHECK_LAUNCH();
+            c.prof_end("sparse_tile_sum_kernel (U_j)");
+            c.prof_begin();
+            sum_tiles_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c.stream>>>(p->upart.get(), p->n_stiles, M, p->f_u.get());
+            SGB_CHECK_LAUNCH();
+            absmax_sum_kernel<<<G, 256, 0, c.stream>>>(b, N, p->red.get(), p->counter.get(), p->scal.get());
+            SGB_CHECK_LAUNCH();
+            digits_b128_kernel<<<(unsigned)((p->ksteps * 256 + 255) / 256), 256, 0, c.stream>>>(b, N, p->ksteps * 256, p->scal.get(),
+                                                                                              p->dfrag128.get());
+            SGB_CHECK_LAUNCH();
+            SGB_CUDA(cudaMemsetAsync(p->f_acc.get(), 0, sizeof(unsigned long long) * p->f_tiles * kFV * 2, c.stream));
+            SGB_CUDA(cudaMemsetAsync(p->f_counter.get(), 0, sizeof(unsigned int) * p->f_tiles, c.stream));
+            c.prof_end("imma_prep_b (absmax+digits+memset)");
+            FusedArgs fa;
+            fa.packed = c.packed.get(); fa.pitch = c.pitch; fa.M = M; fa.N = N; fa.ksteps = p->ksteps;
+            fa.ks_per_cta = p->f_ks_per_cta; fa.n_tiles = p->f_tiles; fa.dfrag128 = p->dfrag128.get();
+            fa.acc_t = p->f_acc.get(); fa.counter = p->f_counter.get(); fa.u = p->f_u.get();
+            fa.lut = c.lut.get(); fa.inv_mtotal = 1.0 / (double)c.M_total; fa.scal = p->scal.get(); fa.hm = p->hm.get();
+            fa.h_total = p->f_htotal.get(); fa.rout = p->f_rout.get(); fa.err = p->f_err.get();
+            void *kargs[] = {&fa};
+            c.prof_begin();
+            SGB_CUDA(cudaLaunchCooperativeKernel((const void *)imma_fused_kernel, dim3(p->f_grid), dim3(kFThreads), kargs,
+                                                 (size_t)kFSmemBytes, c.stream));
+            c.prof_end("imma_fused_kernel");
+            SGB_CUDA(cudaMemcpyAsync(p->f_herr.p, p->f_err.get(), sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+            c.prof_begin();
+            sparse_tile_sum_kernel<<<sp_grid, kSpThreads, kSpSmem, c.stream>>>(p->ms_pos.get(), p->ms_i16.get(), p->hm.get(), N, M,
+                                                                            p->n_vtiles, p->cpart.get());
+            SGB_CHECK_LAUNCH();
+            c.prof_end("sparse_tile_sum_kernel (corr_n)");
+            c.prof_begin();
+            combine_fused_kernel<<<(unsigned)((N + 255) / 256), 256, 0, c.stream>>>(p->f_rout.get(), N, p->cpart.get(), p->n_vtiles,
+                                                                                  p->f_htotal.get(), out);
+            SGB_CHECK_LAUNCH();
+            c.prof_end("combine_kernel");
+            c.stats.n_kernel_launches += 7;
+            c.stats.n_product_launches += 1;
+        }
+        return;
+    }
     const bool fork = side != c.stream;
     for (int col = 0; col < k; col++) {
         const double *b = b_all + (size_t)col * N;
