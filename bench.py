@@ -355,7 +355,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--kernel", default=None, choices=[None, "auto", "simt", "imma"])
+    ap.add_argument("--kernel", default=None, choices=[None, "auto", "simt", "imma", "imma2"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--mode", default="product", choices=["product", "fit"],
                     help="product: the headline metric; fit: null-model fit wall time (secondary metric)")

@@ -150,11 +150,15 @@ struct Context {
         if (!stored) throw Error(SGB_ERR_STATE, "no genotypes stored: call sgb_store_2b_geno first");
     }
     volatile int *async_err = nullptr;   // pinned flag copied back after every fused-kernel launch
+    int *async_err_dev = nullptr;        // its device-side source (cleared after an error was reported)
     void sync() {
         SGB_CUDA(cudaStreamSynchronize(stream));
         if (async_err && *async_err) {
+            const int code = *async_err;
             *async_err = 0;
-            throw Error(SGB_ERR_CUDA, "the fused GRM kernel timed out waiting for another CTA (bounded spin)");
+            if (async_err_dev) cudaMemsetAsync(async_err_dev, 0, sizeof(int), stream);
+            throw Error(SGB_ERR_CUDA, code == 2 ? "the fused GRM kernel found |e_j| above its a-priori bound (internal error)"
+                                                : "the fused GRM kernel timed out waiting for another CTA (bounded spin)");
         }
     }
     void h2d(void *dst, const void *src, size_t bytes) {

@@ -1,50 +1,57 @@
 // Fused single-HBM-pass GRM product (included by grm_imma.cu inside its anonymous namespace).
 //
 // One persistent CTA per SM owns a slice of <= 3072 samples (12 K-steps of 256) for the whole product and walks the
-// variants in tiles of 32.  A packed tile [32 variants x 768 B] is fetched ONCE from HBM (cp.async.bulk + mbarrier),
-// used for phase A (partial dots over the CTA's samples), kept in shared memory while the partial dots of all CTAs
-// are summed through exact 64-bit integer atomics in L2, and then used again for phase B (apply) -- the int32
-// accumulators of phase B live in registers for the whole product.
+// variants in tiles of 32.  A packed tile [32 variants x 768 B] is fetched ONCE from HBM (cp.async.bulk + mbarrier,
+// L2 evict-first), used for phase A (partial dots over the CTA's samples), kept in shared memory while the partial
+// dots of all CTAs are summed through exact 64-bit integer reductions in L2, and then used again for phase B
+// (apply); the int32 accumulators of phase B live in registers for the whole product.
 //
-//   compute warps 0..7 : step s: wait full[s] -> phase A(tile s) -> shared int32 atomics -> arrive acc_done[s]
-//                                wait ready[s-3] -> phase B(tile s-3) -> arrive empty[s-3]
+//   compute warps 0..7 : step s: wait full[s] -> phase A(tile s) -> per-warp partial dots into shared memory
+//                                wait ready[s-lag] -> phase B(tile s-lag) -> arrive empty[s-lag]
 //   loader warp 8      : wait empty -> arm full with expect_tx -> one bulk copy per row (lane <-> variant)
-//   service warp 9     : wait acc_done[s] -> 64 global red.add.u64 (two limbs per variant) -> fence -> counter[s]++
-//                        spin until counter[s-2] == #CTAs -> dot, e, hm for the tile (lane <-> variant) -> base-128
-//                        digits of e in MMA fragment order -> ready[s-2]
+//   publisher warp 9   : wait part_full[s] -> add the 8 warps' partials (lane <-> variant) -> two red.add.u64 per
+//                        variant.  Every CTA adds 2^52 on top of its value, so a limb carries its own arrival count
+//                        in bits 52.. and needs no fence, flag or second round trip.
+//   finaliser warps 10, 11 (alternate tiles): poll the tile's limbs until all CTAs have arrived -> dot, e, hm
+//                        (lane <-> variant) -> base-128 digits of e in MMA fragment order -> ready[tile]
 //
-// All cross-warp synchronisation is mbarrier based; there is no CTA-wide barrier in the main loop.  The digit
-// exponent of e is adaptive (the global max |e_j| is not known in advance): every CTA sees the same e_j and takes the
-// same decision, so all CTAs switch exponent at the same tile; a switch flushes the int32 accumulators to FP64.
-// Everything that crosses CTAs is integer, so the result is independent of timing and bit-reproducible.
-// Spin loops are bounded: on time-out an error flag is raised and the kernel drains instead of hanging the GPU.
+// All cross-warp synchronisation is mbarrier based; there is no CTA-wide barrier in the main loop.  The fixed-point
+// exponent of e is chosen BEFORE the launch from a rigorous bound: |e_j| <= |inv_j| sqrt(sum_n lut_j[c_nj]^2) |b|_2 / M
+// (Cauchy-Schwarz; the maximum over j of the first two factors is computed once at prepare time from the allele
+// counts).  For random b the bound is ~sqrt(N) above the largest |e_j|, i.e. ~12 of the 56 fixed-point bits are head
+// room and e is still resolved to ~2^-43 of its largest element; in exchange every tile is independent of all
+// others.  Everything that crosses warps or CTAs is integer, so the result is independent of timing and
+// bit-reproducible.  Spin loops are bounded: on time-out an error flag is raised and the kernel drains.
 #pragma once
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 constexpr int kFV = 32;                 // variants per tile
 constexpr int kFComputeWarps = 8;
-constexpr int kFThreads = (kFComputeWarps + 2) * 32;
+constexpr int kFNFin = 2;               // finaliser warps
+constexpr int kFWarps = kFComputeWarps + 2 + kFNFin;
+constexpr int kFThreads = kFWarps * 32;
 constexpr int kFMaxKs = 12;             // K-steps (256 samples) per CTA slice
 constexpr int kFRowBytes = kFMaxKs * 64;          // 768
-constexpr int kFPitch = kFRowBytes + 16;          // 784 = 16 (mod 128): conflict-free for both ldmatrix patterns
-constexpr int kFTileBytes = kFV * kFPitch;        // 25,088
-constexpr int kFNBuf = 7;               // tile ring: 3 ahead of phase A + 3 waiting for phase B + 1
-constexpr int kFLag = 3;                // phase B runs 3 tiles behind phase A
-constexpr int kFFinLag = 2;             // the service warp finalises tile s-2 at step s
-constexpr int kFNE = 4;                 // e-digit ring
-constexpr int kFNAcc = 4;               // shared partial-dot ring
+constexpr int kFPanels = kFRowBytes / 128;        // a tile is 6 panels of [32 variants x 128 B], each written by one 2-D TMA copy
+constexpr int kFPanelBytes = kFV * 128;           // 4,096; SWIZZLE_128B: 16-byte chunk index ^= (row & 7) -> both ldmatrix patterns conflict-free
+constexpr int kFTileBytes = kFPanels * kFPanelBytes;   // 24,576
+constexpr int kFNBuf = 8;               // tile ring: (kFNBuf - lag - 1) in flight + phase A + lag waiting / in phase B
+constexpr int kFMaxLag = kFNBuf - 2;
+constexpr int kFNE = 8;                 // e-digit ring (>= lag + 2)
+constexpr int kFNPart = 2;              // partial-dot slots
 constexpr int kFHpw = 3;                // half-steps (128 samples) per compute warp: 24 / 8
 constexpr int kFRbw = 6;                // 64-sample row-blocks per compute warp: 48 / 8
-constexpr int kFHead = 6;               // head-room bits of the adaptive exponent
-constexpr long long kFSpinMax = 1ll << 24;
+constexpr long long kFSpinMax = 1ll << 22;
+constexpr unsigned long long kFArrive = 1ull << 52;   // arrival count lives above bit 52 of a limb
 
 struct FusedSmem {
-    unsigned long long full[kFNBuf], empty[kFNBuf], acc_done[kFNAcc], ready[kFNE];
-    int esh[kFNE];                      // digit shift of the tile in this slot (INT_MIN: all e are zero)
-    int eflag[kFNE];
-    int accum[kFNAcc][kFV * 8];         // partial dots of this CTA: [variant][digit plane]
-    unsigned char efrag[kFNE][256];
+    unsigned long long full[kFNBuf], empty[kFNBuf], part_full[kFNPart], part_free[kFNPart], ready[kFNE];
+    double hsum[kFNFin];
+    alignas(16) int part[kFNPart][kFComputeWarps][kFV * 8];   // per-warp partial dots x 64: [variant][digit plane]
+    alignas(16) unsigned char efrag[kFNE][256];
 };
-constexpr int kFSmemBytes = kFNBuf * kFTileBytes + (int)sizeof(FusedSmem) + 128;
+constexpr int kFSmemBytes = kFNBuf * kFTileBytes + (int)sizeof(FusedSmem) + 1024;   // + slack to align the tiles to 1 KB
+static_assert(kFSmemBytes <= 227 * 1024, "fused kernel shared memory");
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *b, int count) {
@@ -69,142 +76,192 @@ __device__ __forceinline__ bool mbar_wait(unsigned long long *b, unsigned parity
     *err = 1;
     return false;
 }
-__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive_a(unsigned a) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ bool mbar_wait_a(unsigned a, unsigned parity, volatile int *err) {
+    for (long long it = 0; it < kFSpinMax; it++) {
+        unsigned ok;
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return true;
+        if ((it & 1023) == 1023 && *err) return false;
+    }
+    *err = 1;
+    return false;
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tmap, int x, int y, unsigned long long *bar,
+                                            unsigned long long policy) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void red_add_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// register re-allocation between the warp groups (sm_90a+): the compute warps take what the service warps give up
+template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+constexpr int kFRegsCompute = 216, kFRegsService = 72;   // 256 x 216 + 128 x 72 = 384 x 168
+// same instruction as imma_u8s8 but not volatile: a pure register operation the scheduler may interleave freely
+__device__ __forceinline__ void imma_nv(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], unsigned addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_t8(uint32_t (&r)[4], unsigned addr) {
+    asm volatile("ldmatrix.sync.aligned.m16n16.x2.trans.shared.b8 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
 }
 
 struct FusedArgs {
     const uint8_t *packed; size_t pitch; int64_t M, N, ksteps;
     int ks_per_cta;                     // K-steps per CTA (<= kFMaxKs)
+    int lag;                            // phase B runs `lag` tiles behind phase A (1 .. kFMaxLag)
     int64_t n_tiles;
     const int8_t *dfrag128;             // [half-step][lane][t0][h][beta]: digits of b, 1 KB per 128 samples
-    unsigned long long *acc_t;          // [n_tiles * 32][2] exact integer T'_j limbs (zeroed before the launch)
-    unsigned int *counter;              // [n_tiles] arrivals (zeroed before the launch)
+    unsigned long long *acc_t;          // [64 = variant-in-tile x limb][acc_stride] exact integer T'_j limbs + arrival counts (zeroed before
+                                        // the launch).  Limb-major: the 64 limbs of one tile sit in 64 different L2 lines / slices, because every
+                                        // CTA hits them at about the same time and the L2 atomic unit serialises per line
+    int64_t acc_stride;
     const double *u;                    // [M] U_j = sum of b over the missing samples of variant j
     const double *lut;
     double inv_mtotal;
-    const double *scal;                 // S_UNITB, S_SUMB
+    const double *scal;                 // S_UNITB, S_SUMB, S_FESH, S_FUNITE, S_FEBOUND
     double *hm;                         // [M] out: h_j + 3 e_j for the sparse output correction
     double *h_total;                    // out: H = sum_j h_j
     double *rout;                       // [N] out: sum_j e_j c'_nj in real units (this CTA's slice)
     int *err;
 };
 
-__global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(FusedArgs A) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
+__global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_constant__ CUtensorMap tmap, FusedArgs A) {
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t *smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     uint8_t *tiles = smem_raw;
     FusedSmem &S = *reinterpret_cast<FusedSmem *>(smem_raw + kFNBuf * kFTileBytes);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
     const int n_cta = gridDim.x;
     const int64_t ks0 = (int64_t)blockIdx.x * A.ks_per_cta;
     const int ks_n = (int)min((int64_t)A.ks_per_cta, A.ksteps - ks0);        // >= 1 by construction of the grid
-    const unsigned row_bytes = (unsigned)min((size_t)kFRowBytes, A.pitch - (size_t)ks0 * 64);
     const int64_t T = A.n_tiles;
+    const int lag = A.lag;
     volatile int *err = A.err;
 
     if (tid == 0) {
         for (int i = 0; i < kFNBuf; i++) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], kFComputeWarps); }
-        for (int i = 0; i < kFNAcc; i++) mbar_init(&S.acc_done[i], kFComputeWarps);
+        for (int i = 0; i < kFNPart; i++) { mbar_init(&S.part_full[i], kFComputeWarps); mbar_init(&S.part_free[i], 1); }
         for (int i = 0; i < kFNE; i++) mbar_init(&S.ready[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < kFNAcc * kFV * 8; i += kFThreads) (&S.accum[0][0])[i] = 0;
-    // the tile buffers may be read before every byte was ever written (short rows of the last CTA): clear once
-    for (int i = tid; i < kFNBuf * kFTileBytes / 16; i += kFThreads) reinterpret_cast<uint4 *>(tiles)[i] = make_uint4(0, 0, 0, 0);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
-    if (warp == kFComputeWarps) {
+    if (warp >= kFComputeWarps) {
+      reg_dec<kFRegsService>();
+      if (warp == kFComputeWarps) {
         // ------------------------------------------------------------------ loader: lane <-> variant row
+        unsigned long long policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
         for (int64_t t = 0; t < T; t++) {
             const int b = (int)(t % kFNBuf);
             if (t >= kFNBuf && !mbar_wait(&S.empty[b], (unsigned)(((t / kFNBuf) - 1) & 1), err)) break;
-            if (lane == 0) mbar_expect_tx(&S.full[b], row_bytes * kFV);
+            if (lane == 0) mbar_expect_tx(&S.full[b], kFTileBytes);     // out-of-bounds rows / columns are zero-filled and counted
             __syncwarp();
-            const int64_t j = min(t * kFV + lane, A.M - 1);
-            bulk_copy_g2s(tiles + (size_t)b * kFTileBytes + lane * kFPitch, A.packed + (size_t)j * A.pitch + (size_t)ks0 * 64,
-                          row_bytes, &S.full[b]);
+            if (lane < kFPanels)
+                tma_load_2d(tiles + (size_t)b * kFTileBytes + lane * kFPanelBytes, &tmap, (int)(ks0 * 64) + lane * 128, (int)(t * kFV),
+                            &S.full[b], policy);
         }
-    } else if (warp == kFComputeWarps + 1) {
-        // ------------------------------------------------------------------ service: publish partial dots, finalise e
-        const double unit_b = A.scal[S_UNITB], sumb = A.scal[S_SUMB];
-        int sh_cur = INT_MIN;            // adaptive exponent state, identical on every CTA
+      } else if (warp == kFComputeWarps + 1) {
+        // ------------------------------------------------------------------ publisher: lane <-> variant
+        for (int64_t s = 0; s < T; s++) {
+            const int a = (int)(s % kFNPart);
+            if (!mbar_wait(&S.part_full[a], (unsigned)((s / kFNPart) & 1), err)) break;
+            int x[8];
+#pragma unroll
+            for (int l = 0; l < 8; l++) x[l] = 0;
+#pragma unroll
+            for (int w = 0; w < kFComputeWarps; w++) {
+                const int4 v0 = *reinterpret_cast<const int4 *>(&S.part[a][w][lane * 8]);
+                const int4 v1 = *reinterpret_cast<const int4 *>(&S.part[a][w][lane * 8 + 4]);
+                x[0] += v0.x; x[1] += v0.y; x[2] += v0.z; x[3] += v0.w;
+                x[4] += v1.x; x[5] += v1.y; x[6] += v1.z; x[7] += v1.w;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.part_free[a]);
+            // two exact limbs  L = sum_{l<4} I_l 128^l,  Hh = sum_{l>=4} I_l 128^(l-4)   (the partials carry a factor 64)
+            long long lo = 0, hi = 0;
+#pragma unroll
+            for (int l = 3; l >= 0; l--) { lo = lo * 128 + (x[l] >> 6); hi = hi * 128 + (x[l + 4] >> 6); }
+            unsigned long long *dst = A.acc_t + (size_t)(2 * lane) * A.acc_stride + s;
+            red_add_u64(dst, (unsigned long long)lo + kFArrive);
+            red_add_u64(dst + A.acc_stride, (unsigned long long)hi + kFArrive);
+        }
+      } else {
+        // ------------------------------------------------------------------ finalisers: tiles f, f + 2, ...
+        const int f = warp - (kFComputeWarps + 2);
+        const double unit_b = A.scal[S_UNITB], sumb = A.scal[S_SUMB], ebound = A.scal[S_FEBOUND], eunit = A.scal[S_FUNITE];
+        const int esh = (int)A.scal[S_FESH];
+        const bool e_on = eunit > 0 && isfinite(eunit);
+        const unsigned long long want = (unsigned long long)n_cta;
         double hsum = 0;                 // lane-wise partial of H (fixed order: tile order, then a butterfly)
-        for (int64_t s = 0; s < T + kFFinLag; s++) {
-            if (s < T) {
-                const int a = (int)(s % kFNAcc);
-                if (!mbar_wait(&S.acc_done[a], (unsigned)((s / kFNAcc) & 1), err)) break;
-                // lane <-> variant: two exact limbs  L = sum_{l<4} I_l 128^l,  Hh = sum_{l>=4} I_l 128^(l-4)
-                int *acc = &S.accum[a][lane * 8];
-                long long lo = 0, hi = 0;
-#pragma unroll
-                for (int l = 3; l >= 0; l--) { lo = lo * 128 + acc[l]; hi = hi * 128 + acc[l + 4]; }
-#pragma unroll
-                for (int l = 0; l < 8; l++) acc[l] = 0;
-                unsigned long long *dst = A.acc_t + ((size_t)s * kFV + lane) * 2;
-                atomicAdd(dst, (unsigned long long)lo);
-                atomicAdd(dst + 1, (unsigned long long)hi);
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) atomicAdd(A.counter + s, 1u);
+        for (int64_t tb = f; tb < T; tb += kFNFin) {
+            const int64_t j = tb * kFV + lane;
+            const int64_t jc = min(j, A.M - 1);
+            const double uj = __ldg(A.u + jc);
+            const double l0 = __ldg(A.lut + 4 * jc), l1 = __ldg(A.lut + 4 * jc + 1);
+            const unsigned long long *src = A.acc_t + (size_t)(2 * lane) * A.acc_stride + tb;
+            unsigned long long x0 = 0, x1 = 0;
+            bool ok = true;
+            for (long long it = 0;; it++) {
+                x0 = ld_relaxed_u64(src);
+                x1 = ld_relaxed_u64(src + A.acc_stride);
+                const bool done = ((x0 + (kFArrive >> 1)) >> 52) == want && ((x1 + (kFArrive >> 1)) >> 52) == want;
+                if (__all_sync(0xffffffffu, done)) break;
+                int bad = (it >= kFSpinMax) ? 1 : 0;
+                if ((it & 255) == 255 && *err) bad = 1;
+                if (__any_sync(0xffffffffu, bad)) { *err = 1; ok = false; break; }
             }
-            const int64_t tb = s - kFFinLag;
-            if (tb >= 0) {
-                // wait until every CTA has published tile tb
-                bool ok = true;
-                if (lane == 0) {
-                    long long it = 0;
-                    while (*((volatile unsigned int *)(A.counter + tb)) < (unsigned)n_cta) {
-                        if (++it > kFSpinMax || ((it & 1023) == 0 && *err)) { *err = 1; ok = false; break; }
-                    }
-                }
-                ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
-                if (!ok) break;
-                __threadfence();
-                const int64_t j = tb * kFV + lane;
-                double ej = 0, hmj = 0, hj = 0;
-                if (j < A.M) {
-                    const long long lo = (long long)__ldcg(A.acc_t + (size_t)j * 2), hi = (long long)__ldcg(A.acc_t + (size_t)j * 2 + 1);
-                    const double uj = __ldg(A.u + j);
-                    const double tsum = (double)lo + 268435456.0 * (double)hi;          // 128^4 = 2^28
-                    const double Tj = (unit_b == 0 ? 0.0 : unit_b * tsum) - 3.0 * uj;
-                    const double l0 = A.lut[4 * j], inv = A.lut[4 * j + 1] - l0;
-                    const double dot = inv * Tj + l0 * (sumb - uj);
-                    ej = dot * inv * A.inv_mtotal;
-                    hj = dot * l0 * A.inv_mtotal;
-                    hmj = hj + 3.0 * ej;
-                    if ((int)(tb % n_cta) == (int)blockIdx.x) A.hm[j] = hmj;
-                }
-                hsum += hj;
-                double mx = fabs(ej);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                int flag = 0;
-                if (mx > 0 && isfinite(mx)) {
-                    const int need = ilogb(mx);
-                    if (sh_cur == INT_MIN || need + sh_cur > 54) { sh_cur = 54 - need - kFHead; flag = 1; }
-                }
-                const int e = (int)(tb % kFNE);
-                // (the slot is free: its previous tile tb-4 finished phase B before the compute warps could arrive at
-                //  acc_done for step tb+2, which this warp has already passed)
-                int8_t d[8];
-                to_digits((sh_cur == INT_MIN || !isfinite(ej)) ? 0.0 : ej, sh_cur == INT_MIN ? 0 : sh_cur, d);
-                const int hh = lane >> 4, vq = (lane >> 2) & 3, beta = lane & 3;
-#pragma unroll
-                for (int l = 0; l < 8; l++) S.efrag[e][(l * 4 + vq) * 8 + hh * 4 + beta] = (unsigned char)d[l];
-                if (lane == 0) { S.esh[e] = sh_cur; S.eflag[e] = flag; }
-                __syncwarp();
-                __threadfence_block();
-                if (lane == 0) mbar_arrive(&S.ready[e]);
+            if (!ok) break;
+            double ej = 0, hj = 0;
+            if (j < A.M) {
+                const long long lo = (long long)(x0 - want * kFArrive), hi = (long long)(x1 - want * kFArrive);
+                const double tsum = (double)lo + 268435456.0 * (double)hi;          // 128^4 = 2^28
+                const double Tj = (unit_b == 0 ? 0.0 : unit_b * tsum) - 3.0 * uj;
+                const double inv = l1 - l0;
+                const double dot = inv * Tj + l0 * (sumb - uj);
+                ej = dot * inv * A.inv_mtotal;
+                hj = dot * l0 * A.inv_mtotal;
+                if ((int)(tb % n_cta) == (int)blockIdx.x) A.hm[j] = hj + 3.0 * ej;
+                if (e_on && fabs(ej) > ebound) *err = 2;      // the a-priori bound must hold; fail loudly if it ever does not
             }
+            hsum += hj;
+            const int e = (int)(tb % kFNE);
+            // (the slot is free: its previous tile tb-8 finished phase B before this CTA's phase A of tile tb completed,
+            //  which the arrival count of tile tb includes)
+            int8_t d[8];
+            to_digits((e_on && isfinite(ej)) ? ej : 0.0, esh, d);
+            const int hh = lane >> 4, vq = (lane >> 2) & 3, beta = lane & 3;
+#pragma unroll
+            for (int l = 0; l < 8; l++) S.efrag[e][(l * 4 + vq) * 8 + hh * 4 + beta] = (unsigned char)d[l];
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) mbar_arrive(&S.ready[e]);
         }
-        // H: every CTA holds the same lane-wise partials; CTA 0 publishes the butterfly sum
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) hsum += __shfl_xor_sync(0xffffffffu, hsum, o);
-        if (blockIdx.x == 0 && lane == 0) *A.h_total = hsum;
+        if (lane == 0) S.hsum[f] = hsum;
+      }
     } else {
         // ------------------------------------------------------------------ compute warps
+        reg_inc<kFRegsCompute>();
         // B fragments of phase A (digits of b for this warp's half-steps) stay in registers for the whole product
         uint32_t bfr[kFHpw][8];
 #pragma unroll
@@ -217,6 +274,8 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(FusedArgs A) {
             bfr[i][0] = v0.x; bfr[i][1] = v0.y; bfr[i][2] = v0.z; bfr[i][3] = v0.w;
             bfr[i][4] = v1.x; bfr[i][5] = v1.y; bfr[i][6] = v1.z; bfr[i][7] = v1.w;
         }
+        // phase-B accumulators: [row-block][t][fragment]; t = 0 holds the UNMASKED bytes (c0 + 4 c1 + 16 c2 + 64 c3),
+        // i.e. the sum of all four planes -- plane 0 is recovered exactly by subtraction when flushing
         int accB[kFRbw][4][4];
 #pragma unroll
         for (int r = 0; r < kFRbw; r++)
@@ -224,122 +283,155 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(FusedArgs A) {
             for (int t = 0; t < 4; t++)
 #pragma unroll
                 for (int q = 0; q < 4; q++) accB[r][t][q] = 0;
-        int sh_mine = INT_MIN;
-        bool first_flush = true;
-        int tiles_since_flush = 0;
-        auto flush = [&]() {
-            if (sh_mine != INT_MIN) {
-                const double unit = scalbn(1.0, -sh_mine);
-                const double w0 = scalbn(unit, 14 * tq), w1 = scalbn(unit, 14 * tq + 7);
+        // swizzled fragment addresses inside a tile.  Phase A, half-step hs = warp + 8 i, row-block r: byte x = 32 hs + 16 (lane >> 4)
+        // of row 16 r + (lane & 15): panel x >> 7, chunk ((x >> 4) & 7) ^ (row & 7).  Phase B, row-block g = 6 warp + r: 16-byte
+        // chunk g of row `lane`.
+        const unsigned a_off = (unsigned)((warp >> 2) * kFPanelBytes + (lane & 15) * 128 + (((((warp & 3) << 1) | (lane >> 4)) ^ (lane & 7)) << 4));
+        unsigned b_off[kFRbw];
 #pragma unroll
-                for (int r = 0; r < kFRbw; r++)
-#pragma unroll
-                    for (int t = 0; t < 4; t++)
-#pragma unroll
-                        for (int hh = 0; hh < 2; hh++) {
-                            double v = w0 * (double)(accB[r][t][2 * hh] >> (2 * t)) + w1 * (double)(accB[r][t][2 * hh + 1] >> (2 * t));
-                            accB[r][t][2 * hh] = accB[r][t][2 * hh + 1] = 0;
-                            v += __shfl_xor_sync(0xffffffffu, v, 1);
-                            v += __shfl_xor_sync(0xffffffffu, v, 2);
-                            const int64_t n = (ks0 * 64 + (warp * kFRbw + r) * 16 + g + hh * 8) * 4 + t;
-                            if (tq == 0 && n < A.N && (warp * kFRbw + r) < 4 * ks_n) {
-                                double *dst = A.rout + n;
-                                *dst = first_flush ? v : (*dst + v);
-                            }
-                        }
-                first_flush = false;
-            }
-            tiles_since_flush = 0;
-        };
-        for (int64_t s = 0; s < T + kFLag; s++) {
-            if (s < T) {
-                // ---------------- phase A on tile s
-                const int b = (int)(s % kFNBuf);
-                if (!mbar_wait(&S.full[b], (unsigned)((s / kFNBuf) & 1), err)) break;
-                const uint8_t *tile = tiles + (size_t)b * kFTileBytes;
-                int accA[2][4][4];
-#pragma unroll
-                for (int r = 0; r < 2; r++)
-#pragma unroll
-                    for (int t = 0; t < 4; t++)
-#pragma unroll
-                        for (int q = 0; q < 4; q++) accA[r][t][q] = 0;
-#pragma unroll
-                for (int i = 0; i < kFHpw; i++) {
-                    const int hs = warp + i * kFComputeWarps;
-                    if (hs < 2 * ks_n) {
-#pragma unroll
-                        for (int r = 0; r < 2; r++) {
-                            // A fragment of [16 variants x 32 bytes]: matrices (rows 0-7 | 8-15) x (bytes 0-15 | 16-31)
-                            const uint8_t *src = tile + (r * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kFPitch + hs * 32 + (lane >> 4) * 16;
-                            uint32_t a0, a1, a2, a3;
-                            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                                         : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(smem_u32(src)));
-#pragma unroll
-                            for (int t = 0; t < 4; t++) {
-                                const uint32_t m = 0x03030303u << (2 * t);
-                                imma_u8s8(accA[r][t], a0 & m, a1 & m, a2 & m, a3 & m, bfr[i][t * 2], bfr[i][t * 2 + 1]);
-                            }
-                        }
-                    }
-                }
-                // partial dots -> shared int32 atomics: rows g / g+8 of each row-block, digit planes 2tq, 2tq+1
-                int *accS = S.accum[s % kFNAcc];
-#pragma unroll
-                for (int r = 0; r < 2; r++)
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const int v = (accA[r][0][q]) + (accA[r][1][q] >> 2) + (accA[r][2][q] >> 4) + (accA[r][3][q] >> 6);
-                        const int row = r * 16 + g + (q >> 1) * 8, plane = 2 * tq + (q & 1);
-                        atomicAdd(accS + row * 8 + plane, v);
-                    }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.acc_done[s % kFNAcc]);
-            }
-            const int64_t tb = s - kFLag;
-            if (tb >= 0) {
-                // ---------------- phase B on tile tb
-                const int e = (int)(tb % kFNE);
-                if (!mbar_wait(&S.ready[e], (unsigned)((tb / kFNE) & 1), err)) break;
-                const int sh_tile = S.esh[e];
-                if (sh_tile != sh_mine || tiles_since_flush >= 2048) {
-                    if (sh_tile != sh_mine) { flush(); sh_mine = sh_tile; } else flush();
-                }
-                const uint2 bf = *reinterpret_cast<const uint2 *>(&S.efrag[e][lane * 8]);
-                const int b = (int)(tb % kFNBuf);
-                const uint8_t *tile = tiles + (size_t)b * kFTileBytes;
-#pragma unroll
-                for (int r = 0; r < kFRbw; r++) {
-                    if ((warp * kFRbw + r) < 4 * ks_n) {
-                        const uint8_t *src = tile + lane * kFPitch + (warp * kFRbw + r) * 16;
-                        uint32_t x0, x1, x2, x3;
-                        asm volatile("ldmatrix.sync.aligned.m16n16.x2.trans.shared.b8 {%0,%1,%2,%3}, [%4];"
-                                     : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(smem_u32(src)));
-#pragma unroll
-                        for (int t = 0; t < 4; t++) {
-                            const uint32_t m = 0x03030303u << (2 * t);
-                            imma_u8s8(accB[r][t], x0 & m, x1 & m, x2 & m, x3 & m, bf.x, bf.y);
-                        }
-                    }
-                }
-                tiles_since_flush++;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.empty[b]);
-            }
+        for (int r = 0; r < kFRbw; r++) {
+            const int gch = warp * kFRbw + r;
+            b_off[r] = (unsigned)((gch >> 3) * kFPanelBytes + lane * 128 + (((gch & 7) ^ (lane & 7)) << 4));
         }
-        flush();
-        // slices that never saw a non-zero e still have to define their output
-        if (first_flush) {
+        const double eunit = A.scal[S_FUNITE];
+        const bool e_on = eunit > 0 && isfinite(eunit);
+        bool first_flush = true;
+        auto flush = [&]() {
+            const double w0 = scalbn(e_on ? eunit : 0.0, 14 * tq), w1 = scalbn(e_on ? eunit : 0.0, 14 * tq + 7);
 #pragma unroll
             for (int r = 0; r < kFRbw; r++)
 #pragma unroll
                 for (int t = 0; t < 4; t++)
 #pragma unroll
                     for (int hh = 0; hh < 2; hh++) {
+                        int s0, s1;
+                        if (t == 0) {
+                            s0 = accB[r][0][2 * hh] - accB[r][1][2 * hh] - accB[r][2][2 * hh] - accB[r][3][2 * hh];
+                            s1 = accB[r][0][2 * hh + 1] - accB[r][1][2 * hh + 1] - accB[r][2][2 * hh + 1] - accB[r][3][2 * hh + 1];
+                        } else {
+                            s0 = accB[r][t][2 * hh] >> (2 * t);
+                            s1 = accB[r][t][2 * hh + 1] >> (2 * t);
+                        }
+                        double v = w0 * (double)s0 + w1 * (double)s1;
+                        v += __shfl_xor_sync(0xffffffffu, v, 1);
+                        v += __shfl_xor_sync(0xffffffffu, v, 2);
                         const int64_t n = (ks0 * 64 + (warp * kFRbw + r) * 16 + g + hh * 8) * 4 + t;
-                        if (tq == 0 && n < A.N && (warp * kFRbw + r) < 4 * ks_n) A.rout[n] = 0.0;
+                        if (tq == 0 && n < A.N && (warp * kFRbw + r) < 4 * ks_n) {
+                            double *dst = A.rout + n;
+                            *dst = first_flush ? v : (*dst + v);
+                        }
                     }
+#pragma unroll
+            for (int r = 0; r < kFRbw; r++)
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) accB[r][t][q] = 0;
+            first_flush = false;
+        };
+        // everything inside the tile loop uses 32-bit shared-window addresses and incrementally maintained ring indices
+        const unsigned sb = smem_u32(smem_raw), so = sb + kFNBuf * kFTileBytes;
+        const unsigned full0 = so + (unsigned)offsetof(FusedSmem, full), empty0 = so + (unsigned)offsetof(FusedSmem, empty);
+        const unsigned pfull0 = so + (unsigned)offsetof(FusedSmem, part_full), pfree0 = so + (unsigned)offsetof(FusedSmem, part_free);
+        const unsigned ready0 = so + (unsigned)offsetof(FusedSmem, ready);
+        unsigned part_w = so + (unsigned)offsetof(FusedSmem, part) + warp * (kFV * 8 * 4) + (g * 8 + 2 * tq) * 4;   // this thread's first int2
+        unsigned efrag_l = so + (unsigned)offsetof(FusedSmem, efrag) + lane * 8;
+        unsigned a_addr = sb + a_off;
+        // keep the addresses in registers (the compiler would otherwise re-derive them from %tid in every tile)
+        asm volatile("" : "+r"(part_w), "+r"(efrag_l), "+r"(a_addr));
+#pragma unroll
+        for (int r = 0; r < kFRbw; r++) { b_off[r] += sb; asm volatile("" : "+r"(b_off[r])); }
+        const int Ti = (int)T;
+        int bA = 0, phA = 0;            // tile ring slot / parity of tile s
+        int bB = 0;                     // tile ring slot of tile tb
+        int pA = 0, phP = 1;            // partial-dot slot of tile s; parity of the part_free wait (first use of a slot: no wait)
+        int eB = 0, phE = 0;            // e-digit slot / parity of tile tb
+        bool alive = true;
+        for (int s0 = 0; s0 < Ti + lag && alive; s0 += 2048) {
+            const int s1 = min(Ti + lag, s0 + 2048);
+            for (int s = s0; s < s1; s++) {
+                if (s < Ti) {
+                    // ---------------- phase A on tile s
+                    if (!mbar_wait_a(full0 + bA * 8, (unsigned)phA, err)) { alive = false; break; }
+                    // all six A fragments first ([16 variants x 32 bytes]: matrices (rows 0-7 | 8-15) x (bytes 0-15 | 16-31)),
+                    // then the 24 tensor-core instructions.  Half-steps beyond the slice see zeros (TMA zero fill, zero digits).
+                    const unsigned a_base = a_addr + bA * kFTileBytes;
+                    uint32_t fa[2][kFHpw][4];
+#pragma unroll
+                    for (int r = 0; r < 2; r++)
+#pragma unroll
+                        for (int i = 0; i < kFHpw; i++) ldsm_x4(fa[r][i], a_base + r * 16 * 128 + i * 2 * kFPanelBytes);
+                    int accA[2][4][4];
+#pragma unroll
+                    for (int r = 0; r < 2; r++)
+#pragma unroll
+                        for (int t = 0; t < 4; t++)
+#pragma unroll
+                            for (int q = 0; q < 4; q++) accA[r][t][q] = 0;
+#pragma unroll
+                    for (int i = 0; i < kFHpw; i++)
+#pragma unroll
+                        for (int r = 0; r < 2; r++)
+#pragma unroll
+                            for (int t = 0; t < 4; t++) {
+                                const uint32_t m = 0x03030303u << (2 * t);
+                                imma_nv(accA[r][t], fa[r][i][0] & m, fa[r][i][1] & m, fa[r][i][2] & m, fa[r][i][3] & m, bfr[i][t * 2],
+                                        bfr[i][t * 2 + 1]);
+                            }
+                    // partial dots -> this warp's slot: rows g / g+8 of each row-block, digit planes 2tq, 2tq+1.
+                    // ((a0*4 + a1)*4 + a2)*4 + a3 = 64 * (sum of the four planes with their 4^t factors removed)
+                    if (s >= kFNPart && !mbar_wait_a(pfree0 + pA * 8, (unsigned)phP, err)) { alive = false; break; }
+#pragma unroll
+                    for (int r = 0; r < 2; r++)
+#pragma unroll
+                        for (int hh = 0; hh < 2; hh++) {
+                            int v[2];
+#pragma unroll
+                            for (int c = 0; c < 2; c++) {
+                                const int q = 2 * hh + c;
+                                v[c] = ((accA[r][0][q] * 4 + accA[r][1][q]) * 4 + accA[r][2][q]) * 4 + accA[r][3][q];
+                            }
+                            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(part_w + pA * (kFComputeWarps * kFV * 8 * 4) + (r * 16 + hh * 8) * 32),
+                                         "r"(v[0]), "r"(v[1]) : "memory");
+                        }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_a(pfull0 + pA * 8);
+                    if (++bA == kFNBuf) { bA = 0; phA ^= 1; }
+                    if (++pA == kFNPart) { pA = 0; phP ^= 1; }
+                }
+                if (s >= lag) {
+                    // ---------------- phase B on tile tb = s - lag
+                    if (!mbar_wait_a(ready0 + eB * 8, (unsigned)phE, err)) { alive = false; break; }
+                    uint32_t bfx, bfy;
+                    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(bfx), "=r"(bfy) : "r"(efrag_l + eB * 256) : "memory");
+                    const unsigned tb_base = bB * kFTileBytes;
+                    uint32_t fb[kFRbw][4];
+#pragma unroll
+                    for (int r = 0; r < kFRbw; r++) ldsm_t8(fb[r], b_off[r] + tb_base);
+#pragma unroll
+                    for (int r = 0; r < kFRbw; r++) {
+                        imma_nv(accB[r][0], fb[r][0], fb[r][1], fb[r][2], fb[r][3], bfx, bfy);
+#pragma unroll
+                        for (int t = 1; t < 4; t++) {
+                            const uint32_t m = 0x03030303u << (2 * t);
+                            imma_nv(accB[r][t], fb[r][0] & m, fb[r][1] & m, fb[r][2] & m, fb[r][3] & m, bfx, bfy);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_a(empty0 + bB * 8);
+                    if (++bB == kFNBuf) bB = 0;
+                    if (++eB == kFNE) { eB = 0; phE ^= 1; }
+                }
+            }
+            // at most 2048 tiles went into the int32 accumulators (unmasked plane: 255 * 64 * 32 per tile < 2^31 / 2048)
+            flush();
         }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && tid == 0) {
+        double h = 0;
+        for (int f = 0; f < kFNFin; f++) h += S.hsum[f];
+        *A.h_total = h;
     }
 }
 

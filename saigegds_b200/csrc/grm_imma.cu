@@ -36,6 +36,8 @@
 #include <climits>
 #include <cmath>
 
+#include <cuda.h>
+
 #include "ctx.h"
 
 namespace sgb {
@@ -60,17 +62,20 @@ struct ImmaPlan {
     DevBuf<int64_t> ms_pos;  // [n_vtiles * N + 1] tile-major start of (variant tile, sample)
     DevBuf<uint16_t> ms_i16; // [nnz] variant offset inside the tile
     int n_stiles = 0, n_vtiles = 0;
-    int opt_fork = 1, opt_grid_mult = 2, opt_stages = 3;
+    int opt_fork = 1, opt_grid_mult = 2, opt_stages = 3;   // tuning knobs (env: SGB_SPARSE_FORK, SGB_SPARSE_GRID_MULT, SGB_DOTS_STAGES)
     // fused single-pass kernel (grm_fused.cuh)
     bool fused_ok = false;
     int f_ks_per_cta = 0, f_grid = 0;
     int64_t f_tiles = 0;
     DevBuf<int8_t> dfrag128;
     DevBuf<unsigned long long> f_acc;
-    DevBuf<unsigned int> f_counter;
+    CUtensorMap f_tmap;      // packed matrix as a 2-D byte tensor [M][pitch], box 128 B x 32 rows, SWIZZLE_128B
+    double f_efactor = 0;    // max_j |inv_j| sqrt(sum_n lut_j[c_nj]^2) / M_total (bound on |e_j| / |b|_2)
+    int f_lag = 4;
+    int64_t f_acc_stride = 0;
     DevBuf<double> f_rout, f_htotal, f_u;
     DevBuf<int> f_err;
-    PinBuf<int> f_herr;   // tuning knobs (env: SGB_SPARSE_FORK, SGB_SPARSE_GRID_MULT, SGB_DOTS_STAGES)
+    PinBuf<int> f_herr;
     DevBuf<double> upart;    // [n_stiles][M] U_j per sample tile
     DevBuf<double> cpart;    // [n_vtiles][N] output correction per variant tile
     cudaStream_t side = nullptr;   // the sparse corrections run beside the tensor-core kernels
@@ -87,7 +92,7 @@ struct ImmaPlan {
 namespace {
 
 // scal slots
-enum { S_MAXB = 0, S_SUMB = 1, S_UNITB = 2, S_MAXE = 3, S_H = 4, S_UNITE = 5 };
+enum { S_MAXB = 0, S_SUMB = 1, S_UNITB = 2, S_MAXE = 3, S_H = 4, S_UNITE = 5, S_FESH = 6, S_FUNITE = 7, S_FEBOUND = 8 };
 
 constexpr int kAThreads = 128;   // phase A: 4 warps x 4 row-blocks x 16 variants
 constexpr int kARB = 4;
@@ -169,23 +174,28 @@ __device__ __forceinline__ double block_reduce_max(double v, double *sm) {
     return t;
 }
 
-// max|b| (NaN-propagating through the sum) and sum(b): partial[0][G] = max, partial[1][G] = sum
+// max|b| (NaN-propagating through the sum), sum(b) and sum(b^2): partial[0][G] = max, partial[1][G] = sum, partial[2][G] = sumsq.
+// efactor > 0 (fused kernel): also the a-priori bound |e_j| <= efactor * |b|_2 and the fixed-point exponent of e derived
+// from it (one bit of head room for the rounding of the bound itself).
 __global__ void __launch_bounds__(256) absmax_sum_kernel(const double *__restrict__ b, int64_t N, double *partial,
-                                                         unsigned int *counter, double *scal) {
+                                                         unsigned int *counter, double *scal, double efactor) {
     __shared__ double sm[8];
     __shared__ bool last;
-    double mx = 0, s = 0;
+    double mx = 0, s = 0, s2 = 0;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < N; i += (int64_t)gridDim.x * 256) {
         double v = b[i];
         mx = fmax(mx, fabs(v));
         s += v;
+        s2 += v * v;
     }
     mx = block_reduce_max<256>(mx, sm);
     s = block_reduce_sum<256>(s, sm);
+    s2 = block_reduce_sum<256>(s2, sm);
     const int G = gridDim.x;
     if (threadIdx.x == 0) {
         partial[blockIdx.x] = mx;
         partial[G + blockIdx.x] = s;
+        partial[2 * G + blockIdx.x] = s2;
         __threadfence();
         last = atomicInc(counter, G - 1) == (unsigned)(G - 1);
     }
@@ -193,14 +203,32 @@ __global__ void __launch_bounds__(256) absmax_sum_kernel(const double *__restric
     if (last && threadIdx.x == 0) {
         __threadfence();
         const volatile double *p = partial;
-        double m = 0, t = 0;
-        for (int i = 0; i < G; i++) { m = fmax(m, p[i]); t += p[G + i]; }
+        double m = 0, t = 0, t2 = 0;
+        for (int i = 0; i < G; i++) { m = fmax(m, p[i]); t += p[G + i]; t2 += p[2 * G + i]; }
         if (!isfinite(t)) m = t;     // NaN / Inf anywhere in b poisons the product like it does in the reference
         scal[S_MAXB] = m;
         scal[S_SUMB] = t;
         double unit;
         quant_shift(m, &unit);
         scal[S_UNITB] = unit;
+        if (efactor > 0) {
+            // |b|_2, falling back to sqrt(N) max|b| when the sum of squares over- or underflowed
+            double nrm = sqrt((double)N) * m;
+            if (isfinite(t2) && m * m > 1e-290 && t2 >= 0.999 * m * m) nrm = fmin(nrm, sqrt(t2) * (1.0 + 1e-9));
+            double eb = efactor * nrm;
+            if (!isfinite(t)) eb = t;
+            double eunit = 0, esh = 0;
+            if (eb > 0 && isfinite(eb)) {
+                const int sh = 53 - ilogb(eb);
+                esh = (double)sh;
+                eunit = scalbn(1.0, -sh);
+            } else if (eb != 0) {
+                eunit = __longlong_as_double(0x7ff8000000000000LL);
+            }
+            scal[S_FEBOUND] = eb;
+            scal[S_FESH] = esh;
+            scal[S_FUNITE] = eunit;
+        }
     }
 }
 
@@ -709,6 +737,7 @@ bool imma_available(const Context &c) { return c.imma != nullptr; }
 
 void imma_release(Context &c) {
     c.async_err = nullptr;   // points into the plan's pinned flag
+    c.async_err_dev = nullptr;
     delete c.imma;
     c.imma = nullptr;
 }
@@ -791,7 +820,7 @@ void imma_prepare(Context &c) {
         }
         for (cudaEvent_t *e : {&p->ev_in, &p->ev_u, &p->ev_hm, &p->ev_corr}) SGB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         p->scal.ensure(16);
-        p->red.ensure(4 * 1024);
+        p->red.ensure(8 * 1024);
         p->counter.ensure(8);
         SGB_CUDA(cudaMemsetAsync(p->counter.get(), 0, sizeof(unsigned int) * 8, c.stream));
         SGB_CUDA(cudaMemsetAsync(p->scal.get(), 0, sizeof(double) * 16, c.stream));
@@ -812,8 +841,8 @@ void imma_prepare(Context &c) {
                 p->f_tiles = (M + kFV - 1) / kFV;
                 if (per_sm >= 1 && p->f_grid <= per_sm * c.sm_count) {
                     p->dfrag128.ensure((size_t)p->ksteps * 2048);
-                    p->f_acc.ensure((size_t)p->f_tiles * kFV * 2);
-                    p->f_counter.ensure((size_t)p->f_tiles);
+                    p->f_acc_stride = ((p->f_tiles + 15) / 16) * 16 + 16;   // odd multiple of 128 B between limbs
+                    p->f_acc.ensure((size_t)p->f_acc_stride * kFV * 2);
                     p->f_rout.ensure(N);
                     p->f_u.ensure(M);
                     p->f_htotal.ensure(1);
@@ -821,6 +850,40 @@ void imma_prepare(Context &c) {
                     p->f_herr.ensure(1);
                     *p->f_herr.p = 0;
                     SGB_CUDA(cudaMemsetAsync(p->f_err.get(), 0, sizeof(int), c.stream));
+                    // bound on |e_j| / |b|_2 (Cauchy-Schwarz).  sum_n lut_j[c_nj]^2 = n0 l0^2 + n1 l1^2 + n2 l2^2 grows with n2
+                    // at fixed (n_valid, allele sum), so n2 = floor(sum / 2) gives a rigorous upper bound (<= 2x the HWE value).
+                    std::vector<double> hl((size_t)4 * M);
+                    c.d2h(hl.data(), c.lut.get(), sizeof(double) * 4 * M);
+                    c.sync();
+                    double ef = 0;
+                    for (int64_t j = 0; j < M; j++) {
+                        const double num = c.h_cnt_num[j], sum = c.h_cnt_sum[j];
+                        const double n2 = std::floor(sum / 2), n1 = sum - 2 * n2, n0 = std::max(0.0, num - n1 - n2);
+                        const double l0 = hl[4 * j], l1 = hl[4 * j + 1], l2 = hl[4 * j + 2];
+                        const double ss = n0 * l0 * l0 + n1 * l1 * l1 + n2 * l2 * l2;
+                        ef = std::max(ef, std::sqrt(ss) * std::fabs(l1 - l0));
+                    }
+                    p->f_efactor = ef / (double)c.M_total * (1.0 + 1e-9);
+                    if (!(p->f_efactor > 0) || !std::isfinite(p->f_efactor)) p->f_efactor = 1e-300;   // all-monomorphic shard: e == 0
+                    if (const char *e = getenv("SGB_FUSED_LAG")) p->f_lag = atoi(e);
+                    p->f_lag = std::min(kFMaxLag, std::max(1, p->f_lag));
+                    {
+                        typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+                        void *fn = nullptr;
+                        cudaDriverEntryPointQueryResult qres;
+                        SGB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+                        if (!fn || qres != cudaDriverEntryPointSuccess) throw Error(SGB_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+                        const cuuint64_t gdim[2] = {(cuuint64_t)c.pitch, (cuuint64_t)M};
+                        const cuuint64_t gstride[1] = {(cuuint64_t)c.pitch};
+                        const cuuint32_t box[2] = {128, (cuuint32_t)kFV};
+                        const cuuint32_t estr[2] = {1, 1};
+                        CUresult r = ((EncodeFn)fn)(&p->f_tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)c.packed.get(), gdim, gstride, box, estr,
+                                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        if (r != CUDA_SUCCESS) throw Error(SGB_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+                    }
                     p->fused_ok = true;
                 }
             }
@@ -848,6 +911,7 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
     const int sp_grid = c.sm_count * p->opt_grid_mult;
     if (p->fused_ok && c.kernel != SGB_KERNEL_IMMA_TWOPASS) {
         c.async_err = p->f_herr.p;
+        c.async_err_dev = p->f_err.get();
         for (int col = 0; col < k; col++) {
             const double *b = b_all + (size_t)col * N;
             double *out = out_all + (size_t)col * N;
@@ -859,21 +923,20 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
             c.prof_begin();
             sum_tiles_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c.stream>>>(p->upart.get(), p->n_stiles, M, p->f_u.get());
             SGB_CHECK_LAUNCH();
-            absmax_sum_kernel<<<G, 256, 0, c.stream>>>(b, N, p->red.get(), p->counter.get(), p->scal.get());
+            absmax_sum_kernel<<<G, 256, 0, c.stream>>>(b, N, p->red.get(), p->counter.get(), p->scal.get(), p->f_efactor);
             SGB_CHECK_LAUNCH();
             digits_b128_kernel<<<(unsigned)((p->ksteps * 256 + 255) / 256), 256, 0, c.stream>>>(b, N, p->ksteps * 256, p->scal.get(),
                                                                                               p->dfrag128.get());
             SGB_CHECK_LAUNCH();
-            SGB_CUDA(cudaMemsetAsync(p->f_acc.get(), 0, sizeof(unsigned long long) * p->f_tiles * kFV * 2, c.stream));
-            SGB_CUDA(cudaMemsetAsync(p->f_counter.get(), 0, sizeof(unsigned int) * p->f_tiles, c.stream));
+            SGB_CUDA(cudaMemsetAsync(p->f_acc.get(), 0, sizeof(unsigned long long) * p->f_acc_stride * kFV * 2, c.stream));
             c.prof_end("imma_prep_b (absmax+digits+memset)");
             FusedArgs fa;
             fa.packed = c.packed.get(); fa.pitch = c.pitch; fa.M = M; fa.N = N; fa.ksteps = p->ksteps;
             fa.ks_per_cta = p->f_ks_per_cta; fa.n_tiles = p->f_tiles; fa.dfrag128 = p->dfrag128.get();
-            fa.acc_t = p->f_acc.get(); fa.counter = p->f_counter.get(); fa.u = p->f_u.get();
+            fa.acc_t = p->f_acc.get(); fa.acc_stride = p->f_acc_stride; fa.u = p->f_u.get(); fa.lag = p->f_lag;
             fa.lut = c.lut.get(); fa.inv_mtotal = 1.0 / (double)c.M_total; fa.scal = p->scal.get(); fa.hm = p->hm.get();
             fa.h_total = p->f_htotal.get(); fa.rout = p->f_rout.get(); fa.err = p->f_err.get();
-            void *kargs[] = {&fa};
+            void *kargs[] = {&p->f_tmap, &fa};
             c.prof_begin();
             SGB_CUDA(cudaLaunchCooperativeKernel((const void *)imma_fused_kernel, dim3(p->f_grid), dim3(kFThreads), kargs,
                                                  (size_t)kFSmemBytes, c.stream));
@@ -909,7 +972,7 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
         c.prof_end("sparse_tile_sum_kernel (U_j)");
         if (fork) SGB_CUDA(cudaEventRecord(p->ev_u, side));
         c.prof_begin();
-        absmax_sum_kernel<<<G, 256, 0, c.stream>>>(b, N, p->red.get(), p->counter.get(), p->scal.get());
+        absmax_sum_kernel<<<G, 256, 0, c.stream>>>(b, N, p->red.get(), p->counter.get(), p->scal.get(), 0.0);
         SGB_CHECK_LAUNCH();
         digits_b_kernel<<<(unsigned)((p->ksteps * 256 + 255) / 256), 256, 0, c.stream>>>(b, N, p->ksteps * 256, p->scal.get(),
                                                                                        p->dfrag.get());
@@ -927,7 +990,7 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
         if (fork) SGB_CUDA(cudaStreamWaitEvent(c.stream, p->ev_u, 0));
         c.prof_begin();
         finalize_dots_kernel<<<Gm, 256, 0, c.stream>>>(p->tq.get(), p->split_a, p->upart.get(), p->n_stiles, c.lut.get(), M,
-                                                       1.0 / (double)c.M_total, p->e.get(), p->hm.get(), p->red.get() + 2048,
+                                                       1.0 / (double)c.M_total, p->e.get(), p->hm.get(), p->red.get() + 4096,
                                                        p->counter.get() + 1, p->scal.get());
         SGB_CHECK_LAUNCH();
         if (fork) {
