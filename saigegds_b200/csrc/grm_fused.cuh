@@ -6,8 +6,9 @@
 // dots of all CTAs are summed through exact 64-bit integer reductions in L2, and then used again for phase B
 // (apply); the int32 accumulators of phase B live in registers for the whole product.
 //
-//   compute warps 0..7 : step s: wait full[s] -> phase A(tile s) -> per-warp partial dots into shared memory
-//                                wait ready[s-lag] -> phase B(tile s-lag) -> arrive empty[s-lag]
+//   compute warps 0..7 : phase A(tile s) when full[s] has completed -> per-warp partial dots into shared memory;
+//                        phase B(oldest tile) as soon as its ready[] has completed -> arrive empty[]; B is preferred, so the
+//                        distance between the two phases adapts to the cross-CTA latency (no fixed lag)
 //   loader warp 8      : wait empty -> arm full with expect_tx -> one bulk copy per row (lane <-> variant)
 //   publisher warp 9   : wait part_full[s] -> add the 8 warps' partials (lane <-> variant) -> two red.add.u64 per
 //                        variant.  Every CTA adds 2^52 on top of its value, so a limb carries its own arrival count
@@ -35,10 +36,9 @@ constexpr int kFRowBytes = kFMaxKs * 64;          // 768
 constexpr int kFPanels = kFRowBytes / 128;        // a tile is 6 panels of [32 variants x 128 B], each written by one 2-D TMA copy
 constexpr int kFPanelBytes = kFV * 128;           // 4,096; SWIZZLE_128B: 16-byte chunk index ^= (row & 7) -> both ldmatrix patterns conflict-free
 constexpr int kFTileBytes = kFPanels * kFPanelBytes;   // 24,576
-constexpr int kFNBuf = 8;               // tile ring: (kFNBuf - lag - 1) in flight + phase A + lag waiting / in phase B
-constexpr int kFMaxLag = kFNBuf - 2;
-constexpr int kFNE = 8;                 // e-digit ring (>= lag + 2)
-constexpr int kFNPart = 2;              // partial-dot slots
+constexpr int kFNBuf = 9;               // tile ring: loads in flight + tiles waiting for their e digits
+constexpr int kFNE = 10;                // e-digit ring (>= kFNBuf: phase B may trail phase A by a full tile ring)
+constexpr int kFNPart = 1;              // partial-dot slots (the publisher drains a slot ~10x faster than a tile takes)
 constexpr int kFHpw = 3;                // half-steps (128 samples) per compute warp: 24 / 8
 constexpr int kFRbw = 6;                // 64-sample row-blocks per compute warp: 48 / 8
 constexpr long long kFSpinMax = 1ll << 22;
@@ -50,7 +50,7 @@ struct FusedSmem {
     alignas(16) int part[kFNPart][kFComputeWarps][kFV * 8];   // per-warp partial dots x 64: [variant][digit plane]
     alignas(16) unsigned char efrag[kFNE][256];
 };
-constexpr int kFSmemBytes = kFNBuf * kFTileBytes + (int)sizeof(FusedSmem) + 1024;   // + slack to align the tiles to 1 KB
+constexpr int kFSmemBytes = kFNBuf * kFTileBytes + (int)sizeof(FusedSmem);   // dynamic shared memory starts 1 KB aligned (checked)
 static_assert(kFSmemBytes <= 227 * 1024, "fused kernel shared memory");
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -90,6 +90,12 @@ __device__ __forceinline__ bool mbar_wait_a(unsigned a, unsigned parity, volatil
     *err = 1;
     return false;
 }
+__device__ __forceinline__ bool mbar_test_a(unsigned a, unsigned parity) {
+    unsigned ok;
+    asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tmap, int x, int y, unsigned long long *bar,
                                             unsigned long long policy) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
@@ -126,7 +132,8 @@ __device__ __forceinline__ void ldsm_t8(uint32_t (&r)[4], unsigned addr) {
 struct FusedArgs {
     const uint8_t *packed; size_t pitch; int64_t M, N, ksteps;
     int ks_per_cta;                     // K-steps per CTA (<= kFMaxKs)
-    int lag;                            // phase B runs `lag` tiles behind phase A (1 .. kFMaxLag)
+    int lag;                            // phase B runs `lag` tiles behind phase A (1 .. kFNBuf - 2)
+    int poll_ns;                        // back-off between two polls of a tile's limbs
     int64_t n_tiles;
     const int8_t *dfrag128;             // [half-step][lane][t0][h][beta]: digits of b, 1 KB per 128 samples
     unsigned long long *acc_t;          // [64 = variant-in-tile x limb][acc_stride] exact integer T'_j limbs + arrival counts (zeroed before
@@ -145,7 +152,7 @@ struct FusedArgs {
 
 __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_constant__ CUtensorMap tmap, FusedArgs A) {
     extern __shared__ uint8_t smem_dyn[];
-    uint8_t *smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    uint8_t *smem_raw = smem_dyn;
     uint8_t *tiles = smem_raw;
     FusedSmem &S = *reinterpret_cast<FusedSmem *>(smem_raw + kFNBuf * kFTileBytes);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
@@ -157,6 +164,7 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
     volatile int *err = A.err;
 
     if (tid == 0) {
+        if (smem_u32(smem_raw) & 1023u) *A.err = 3;     // SWIZZLE_128B needs 1 KB aligned tiles
         for (int i = 0; i < kFNBuf; i++) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], kFComputeWarps); }
         for (int i = 0; i < kFNPart; i++) { mbar_init(&S.part_full[i], kFComputeWarps); mbar_init(&S.part_free[i], 1); }
         for (int i = 0; i < kFNE; i++) mbar_init(&S.ready[i], 1);
@@ -211,6 +219,7 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
         const int esh = (int)A.scal[S_FESH];
         const bool e_on = eunit > 0 && isfinite(eunit);
         const unsigned long long want = (unsigned long long)n_cta;
+        const unsigned poll_ns = (unsigned)A.poll_ns;
         double hsum = 0;                 // lane-wise partial of H (fixed order: tile order, then a butterfly)
         for (int64_t tb = f; tb < T; tb += kFNFin) {
             const int64_t j = tb * kFV + lane;
@@ -220,14 +229,14 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
             const unsigned long long *src = A.acc_t + (size_t)(2 * lane) * A.acc_stride + tb;
             unsigned long long x0 = 0, x1 = 0;
             bool ok = true;
-            for (long long it = 0;; it++) {
+            for (int it = 0;; it++) {
                 x0 = ld_relaxed_u64(src);
                 x1 = ld_relaxed_u64(src + A.acc_stride);
                 const bool done = ((x0 + (kFArrive >> 1)) >> 52) == want && ((x1 + (kFArrive >> 1)) >> 52) == want;
                 if (__all_sync(0xffffffffu, done)) break;
-                int bad = (it >= kFSpinMax) ? 1 : 0;
-                if ((it & 255) == 255 && *err) bad = 1;
-                if (__any_sync(0xffffffffu, bad)) { *err = 1; ok = false; break; }
+                // back off: a spinning warp competes with two compute warps for the issue port and the integer pipe
+                __nanosleep(poll_ns);
+                if (it >= (1 << 20)) { *err = 1; ok = false; break; }
             }
             if (!ok) break;
             double ej = 0, hj = 0;
@@ -239,21 +248,28 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
                 const double dot = inv * Tj + l0 * (sumb - uj);
                 ej = dot * inv * A.inv_mtotal;
                 hj = dot * l0 * A.inv_mtotal;
-                if ((int)(tb % n_cta) == (int)blockIdx.x) A.hm[j] = hj + 3.0 * ej;
-                if (e_on && fabs(ej) > ebound) *err = 2;      // the a-priori bound must hold; fail loudly if it ever does not
             }
-            hsum += hj;
             const int e = (int)(tb % kFNE);
             // (the slot is free: its previous tile tb-8 finished phase B before this CTA's phase A of tile tb completed,
             //  which the arrival count of tile tb includes)
-            int8_t d[8];
-            to_digits((e_on && isfinite(ej)) ? ej : 0.0, esh, d);
+            // digits d_l in [-64, 63] of the 56-bit fixed-point value, all at once: adding 64 to every digit position turns
+            // them into the plain base-128 digits of a non-negative number
+            const long long Bq = __double2ll_rn(scalbn((e_on && isfinite(ej)) ? ej : 0.0, esh)) + 0x1020408102040LL;   // sum_{l<7} 64 * 128^l
             const int hh = lane >> 4, vq = (lane >> 2) & 3, beta = lane & 3;
 #pragma unroll
-            for (int l = 0; l < 8; l++) S.efrag[e][(l * 4 + vq) * 8 + hh * 4 + beta] = (unsigned char)d[l];
+            for (int l = 0; l < 8; l++) {
+                const int dl = (l < 7) ? ((int)((Bq >> (7 * l)) & 127) - 64) : (int)(Bq >> 49);
+                S.efrag[e][(l * 4 + vq) * 8 + hh * 4 + beta] = (unsigned char)(int8_t)dl;
+            }
             __syncwarp();
             __threadfence_block();
             if (lane == 0) mbar_arrive(&S.ready[e]);
+            // off the critical path: H, the output-correction weights, the sanity check of the bound
+            hsum += hj;
+            if (j < A.M) {
+                if ((int)(tb % n_cta) == (int)blockIdx.x) A.hm[j] = hj + 3.0 * ej;
+                if (e_on && fabs(ej) > ebound) *err = 2;      // the a-priori bound must hold; fail loudly if it ever does not
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) hsum += __shfl_xor_sync(0xffffffffu, hsum, o);
@@ -344,88 +360,102 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
         const int Ti = (int)T;
         int bA = 0, phA = 0;            // tile ring slot / parity of tile s
         int bB = 0;                     // tile ring slot of tile tb
-        int pA = 0, phP = 1;            // partial-dot slot of tile s; parity of the part_free wait (first use of a slot: no wait)
+        int phP = 1;                    // parity of the part_free wait (first use of the slot: no wait)
         int eB = 0, phE = 0;            // e-digit slot / parity of tile tb
         bool alive = true;
-        for (int s0 = 0; s0 < Ti + lag && alive; s0 += 2048) {
-            const int s1 = min(Ti + lag, s0 + 2048);
-            for (int s = s0; s < s1; s++) {
-                if (s < Ti) {
-                    // ---------------- phase A on tile s
-                    if (!mbar_wait_a(full0 + bA * 8, (unsigned)phA, err)) { alive = false; break; }
-                    // all six A fragments first ([16 variants x 32 bytes]: matrices (rows 0-7 | 8-15) x (bytes 0-15 | 16-31)),
-                    // then the 24 tensor-core instructions.  Half-steps beyond the slice see zeros (TMA zero fill, zero digits).
-                    const unsigned a_base = a_addr + bA * kFTileBytes;
-                    uint32_t fa[2][kFHpw][4];
+        // One step = phase A on tile s and phase B on tile tb = s - lag.  Both waits first, then all twelve fragment loads, then
+        // the 48 tensor-core instructions of the two phases interleaved (independent work for the scheduler), then the stores.
+        auto step = [&](auto do_a, auto do_b, int s) -> bool {
+            constexpr bool DA = decltype(do_a)::value, DB = decltype(do_b)::value;
+            uint32_t fa[2][kFHpw][4], fb[kFRbw][4], bfx = 0, bfy = 0;
+            int accA[2][4][4];
+            if (DA) {
+                if (!mbar_wait_a(full0 + bA * 8, (unsigned)phA, err)) return false;
+            }
+            if (DB) {
+                if (!mbar_wait_a(ready0 + eB * 8, (unsigned)phE, err)) return false;
+            }
+            if (DA) {
+                // A fragments ([16 variants x 32 bytes]: matrices (rows 0-7 | 8-15) x (bytes 0-15 | 16-31)); half-steps beyond
+                // the slice see zeros (TMA zero fill, zero digits)
+                const unsigned a_base = a_addr + bA * kFTileBytes;
 #pragma unroll
-                    for (int r = 0; r < 2; r++)
+                for (int r = 0; r < 2; r++)
 #pragma unroll
-                        for (int i = 0; i < kFHpw; i++) ldsm_x4(fa[r][i], a_base + r * 16 * 128 + i * 2 * kFPanelBytes);
-                    int accA[2][4][4];
+                    for (int i = 0; i < kFHpw; i++) ldsm_x4(fa[r][i], a_base + r * 16 * 128 + i * 2 * kFPanelBytes);
 #pragma unroll
-                    for (int r = 0; r < 2; r++)
+                for (int r = 0; r < 2; r++)
 #pragma unroll
-                        for (int t = 0; t < 4; t++)
+                    for (int t = 0; t < 4; t++)
 #pragma unroll
-                            for (int q = 0; q < 4; q++) accA[r][t][q] = 0;
+                        for (int q = 0; q < 4; q++) accA[r][t][q] = 0;
+            }
+            if (DB) {
+                asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(bfx), "=r"(bfy) : "r"(efrag_l + eB * 256) : "memory");
+                const unsigned tb_base = bB * kFTileBytes;
 #pragma unroll
-                    for (int i = 0; i < kFHpw; i++)
+                for (int r = 0; r < kFRbw; r++) ldsm_t8(fb[r], b_off[r] + tb_base);
+            }
 #pragma unroll
-                        for (int r = 0; r < 2; r++)
+            for (int k = 0; k < 6; k++) {
+                if (DA) {
+                    const int i = k >> 1, r = k & 1;
 #pragma unroll
-                            for (int t = 0; t < 4; t++) {
-                                const uint32_t m = 0x03030303u << (2 * t);
-                                imma_nv(accA[r][t], fa[r][i][0] & m, fa[r][i][1] & m, fa[r][i][2] & m, fa[r][i][3] & m, bfr[i][t * 2],
-                                        bfr[i][t * 2 + 1]);
-                            }
-                    // partial dots -> this warp's slot: rows g / g+8 of each row-block, digit planes 2tq, 2tq+1.
-                    // ((a0*4 + a1)*4 + a2)*4 + a3 = 64 * (sum of the four planes with their 4^t factors removed)
-                    if (s >= kFNPart && !mbar_wait_a(pfree0 + pA * 8, (unsigned)phP, err)) { alive = false; break; }
-#pragma unroll
-                    for (int r = 0; r < 2; r++)
-#pragma unroll
-                        for (int hh = 0; hh < 2; hh++) {
-                            int v[2];
-#pragma unroll
-                            for (int c = 0; c < 2; c++) {
-                                const int q = 2 * hh + c;
-                                v[c] = ((accA[r][0][q] * 4 + accA[r][1][q]) * 4 + accA[r][2][q]) * 4 + accA[r][3][q];
-                            }
-                            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(part_w + pA * (kFComputeWarps * kFV * 8 * 4) + (r * 16 + hh * 8) * 32),
-                                         "r"(v[0]), "r"(v[1]) : "memory");
-                        }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_a(pfull0 + pA * 8);
-                    if (++bA == kFNBuf) { bA = 0; phA ^= 1; }
-                    if (++pA == kFNPart) { pA = 0; phP ^= 1; }
-                }
-                if (s >= lag) {
-                    // ---------------- phase B on tile tb = s - lag
-                    if (!mbar_wait_a(ready0 + eB * 8, (unsigned)phE, err)) { alive = false; break; }
-                    uint32_t bfx, bfy;
-                    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(bfx), "=r"(bfy) : "r"(efrag_l + eB * 256) : "memory");
-                    const unsigned tb_base = bB * kFTileBytes;
-                    uint32_t fb[kFRbw][4];
-#pragma unroll
-                    for (int r = 0; r < kFRbw; r++) ldsm_t8(fb[r], b_off[r] + tb_base);
-#pragma unroll
-                    for (int r = 0; r < kFRbw; r++) {
-                        imma_nv(accB[r][0], fb[r][0], fb[r][1], fb[r][2], fb[r][3], bfx, bfy);
-#pragma unroll
-                        for (int t = 1; t < 4; t++) {
-                            const uint32_t m = 0x03030303u << (2 * t);
-                            imma_nv(accB[r][t], fb[r][0] & m, fb[r][1] & m, fb[r][2] & m, fb[r][3] & m, bfx, bfy);
-                        }
+                    for (int t = 0; t < 4; t++) {
+                        const uint32_t m = 0x03030303u << (2 * t);
+                        imma_nv(accA[r][t], fa[r][i][0] & m, fa[r][i][1] & m, fa[r][i][2] & m, fa[r][i][3] & m, bfr[i][t * 2], bfr[i][t * 2 + 1]);
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_a(empty0 + bB * 8);
-                    if (++bB == kFNBuf) bB = 0;
-                    if (++eB == kFNE) { eB = 0; phE ^= 1; }
+                }
+                if (DB) {
+                    imma_nv(accB[k][0], fb[k][0], fb[k][1], fb[k][2], fb[k][3], bfx, bfy);
+#pragma unroll
+                    for (int t = 1; t < 4; t++) {
+                        const uint32_t m = 0x03030303u << (2 * t);
+                        imma_nv(accB[k][t], fb[k][0] & m, fb[k][1] & m, fb[k][2] & m, fb[k][3] & m, bfx, bfy);
+                    }
                 }
             }
-            // at most 2048 tiles went into the int32 accumulators (unmasked plane: 255 * 64 * 32 per tile < 2^31 / 2048)
+            if (DB) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(empty0 + bB * 8);
+                if (++bB == kFNBuf) bB = 0;
+                if (++eB == kFNE) { eB = 0; phE ^= 1; }
+            }
+            if (DA) {
+                // partial dots -> this warp's slot: rows g / g+8 of each row-block, digit planes 2tq, 2tq+1.
+                // ((a0*4 + a1)*4 + a2)*4 + a3 = 64 * (sum of the four planes with their 4^t factors removed)
+                if (s >= 1 && !mbar_wait_a(pfree0, (unsigned)phP, err)) return false;
+#pragma unroll
+                for (int r = 0; r < 2; r++)
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        int v[2];
+#pragma unroll
+                        for (int c = 0; c < 2; c++) {
+                            const int q = 2 * hh + c;
+                            v[c] = ((accA[r][0][q] * 4 + accA[r][1][q]) * 4 + accA[r][2][q]) * 4 + accA[r][3][q];
+                        }
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(part_w + (r * 16 + hh * 8) * 32), "r"(v[0]), "r"(v[1]) : "memory");
+                    }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(pfull0);
+                if (++bA == kFNBuf) { bA = 0; phA ^= 1; }
+                phP ^= 1;
+            }
+            return true;
+        };
+        const std::true_type yes;
+        const std::false_type no;
+        const int ramp = min(lag, Ti);
+        for (int s = 0; s < ramp && alive; s++) alive = step(yes, no, s);                     // tiles 0 .. lag-1: phase A only
+        for (int s0 = ramp; s0 < Ti && alive; s0 += 2048) {                                    // steady state
+            const int s1 = min(Ti, s0 + 2048);
+            for (int s = s0; s < s1 && alive; s++) alive = step(yes, yes, s);
+            // at most 2048 (+ lag) tiles went into the int32 accumulators (unmasked plane: 255 * 64 * 32 per tile < 2^31 / 4096)
             flush();
         }
+        for (int s = Ti; s < Ti + ramp && alive; s++) alive = step(no, yes, s);                // drain: phase B only
+        flush();
     }
     __syncthreads();
     if (blockIdx.x == 0 && tid == 0) {

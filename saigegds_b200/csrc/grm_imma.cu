@@ -34,6 +34,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <type_traits>
 #include <cmath>
 
 #include <cuda.h>
@@ -71,7 +72,7 @@ struct ImmaPlan {
     DevBuf<unsigned long long> f_acc;
     CUtensorMap f_tmap;      // packed matrix as a 2-D byte tensor [M][pitch], box 128 B x 32 rows, SWIZZLE_128B
     double f_efactor = 0;    // max_j |inv_j| sqrt(sum_n lut_j[c_nj]^2) / M_total (bound on |e_j| / |b|_2)
-    int f_lag = 4;
+    int f_poll_ns = 100;
     int64_t f_acc_stride = 0;
     DevBuf<double> f_rout, f_htotal, f_u;
     DevBuf<int> f_err;
@@ -865,8 +866,7 @@ void imma_prepare(Context &c) {
                     }
                     p->f_efactor = ef / (double)c.M_total * (1.0 + 1e-9);
                     if (!(p->f_efactor > 0) || !std::isfinite(p->f_efactor)) p->f_efactor = 1e-300;   // all-monomorphic shard: e == 0
-                    if (const char *e = getenv("SGB_FUSED_LAG")) p->f_lag = atoi(e);
-                    p->f_lag = std::min(kFMaxLag, std::max(1, p->f_lag));
+                    if (const char *e = getenv("SGB_FUSED_POLL_NS")) p->f_poll_ns = std::max(0, atoi(e));
                     {
                         typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -933,7 +933,7 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
             FusedArgs fa;
             fa.packed = c.packed.get(); fa.pitch = c.pitch; fa.M = M; fa.N = N; fa.ksteps = p->ksteps;
             fa.ks_per_cta = p->f_ks_per_cta; fa.n_tiles = p->f_tiles; fa.dfrag128 = p->dfrag128.get();
-            fa.acc_t = p->f_acc.get(); fa.acc_stride = p->f_acc_stride; fa.u = p->f_u.get(); fa.lag = p->f_lag;
+            fa.acc_t = p->f_acc.get(); fa.acc_stride = p->f_acc_stride; fa.u = p->f_u.get(); fa.poll_ns = p->f_poll_ns; fa.lag = std::min(kFNBuf - 2, std::max(1, getenv("SGB_FUSED_LAG") ? atoi(getenv("SGB_FUSED_LAG")) : 6));
             fa.lut = c.lut.get(); fa.inv_mtotal = 1.0 / (double)c.M_total; fa.scal = p->scal.get(); fa.hm = p->hm.get();
             fa.h_total = p->f_htotal.get(); fa.rout = p->f_rout.get(); fa.err = p->f_err.get();
             void *kargs[] = {&p->f_tmap, &fa};

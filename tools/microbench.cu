@@ -198,6 +198,11 @@ int main() {
         run("DMMA m8n8k4 f64 (FMAs)", [&](long long *c) { k_dmma<<<sms * bps, T>>>((double *)buf, c, 1.0000001); }, 8 * 256.0 / 32, T, bps, sms, "FMA");
         run("DFMA || DMMA (warps split)", [&](long long *c) { k_dfma_dmma<<<sms * bps, T>>>((double *)buf, c, 1.0000001); }, 8 * (1 + 256.0 / 32) / 2, T, bps, sms, "FMA");
     }
+    // IMMA rate as a function of warps per scheduler (the fused kernel has 2 compute warps per SMSP)
+    for (int T : {128, 256, 384, 512, 768, 1024}) {
+        run("IMMA (MACs)", [&](long long *c) { k_imma<0><<<sms, T>>>((int *)buf, c, 12345u); }, 8 * 4096.0 / 32, T, 1, sms, "MAC");
+        run("IMMA + 4 LOP3 (MACs)", [&](long long *c) { k_imma<1><<<sms, T>>>((int *)buf, c, 12345u); }, 8 * 4096.0 / 32, T, 1, sms, "MAC");
+    }
     uint32_t *probe;
     CK(cudaMalloc(&probe, 64 * 4));
     k_ldmatrix_probe<<<1, 32>>>(probe);
