@@ -31,7 +31,8 @@ def default_params(**kw) -> OrcParams:
 
 def build(force=False):
     if force or not os.path.exists(LIB_PATH) or \
-            os.path.getmtime(LIB_PATH) < os.path.getmtime(os.path.join(HERE, "saige_oracle.cpp")):
+            os.path.getmtime(LIB_PATH) < max(os.path.getmtime(os.path.join(HERE, f))
+                                             for f in ("saige_oracle.cpp", "saige_score_oracle.cpp")):
         subprocess.check_call(["make", "-C", HERE, "-s"])
     return LIB_PATH
 
@@ -181,6 +182,50 @@ class Oracle:
     @property
     def num_products(self):
         return lib().orc_num_products(self.h)
+
+
+def init_nullmod(trait, y, mu, noK_X1, noK_XV, noK_XXVX_inv, noK_V, tau):
+    """The derived arrays of .init_nullmod (R/assoc_single.r:17-67), all samples (ii = 1..n).  Matrices are K x n in
+    R's column-major order, i.e. C-contiguous [n][K] here."""
+    y, mu = _f64(y), _f64(mu)
+    X1 = _f64(noK_X1)                                   # n x K
+    XXVX_inv = _f64(noK_XXVX_inv)                       # n x K
+    V = _f64(noK_V)
+    m = dict(trait=trait, tau=_f64(tau), y=y, mu=mu, y_mu=y - mu, mu2=mu * (1 - mu),
+             t_XXVX_inv=np.ascontiguousarray(XXVX_inv),                       # [n][K] == K x n column-major
+             XV=np.ascontiguousarray(_f64(noK_XV).T),                         # noK_XV is K x n -> [n][K]
+             t_XVX_inv_XV=np.ascontiguousarray(XXVX_inv * V[:, None]),
+             t_X=np.ascontiguousarray(X1))
+    if trait == "binary":
+        m["XVX"] = np.ascontiguousarray(X1.T @ (X1 * m["mu2"][:, None]))
+    else:
+        m["XVX"] = np.ascontiguousarray(X1.T @ X1)
+    m["S_a"] = _f64((X1 * m["y_mu"][:, None]).sum(axis=0))
+    return m
+
+
+def score_test(model, dosage, var_ratio, maf=float("nan"), mac=10.0, missing=0.1, spa_pval=0.05):
+    """seqAssocGLMM_SPA's per-variant test (src/saige_main.cpp:188-407) on dosage [n_var][n] (NaN = missing).
+    Returns dict of arrays (AF, mac, num, beta, SE, pval, p_norm, converged) and the `valid` mask."""
+    ds = np.array(dosage, dtype=np.float64, order="C", copy=True)
+    n_var, n = ds.shape
+    K = model["t_X"].shape[1]
+    out = np.empty((n_var, 8))
+    valid = np.empty(n_var, dtype=np.int32)
+    lib().orc_score_test(C.c_int(0 if model["trait"] == "binary" else 1), C.c_long(n), C.c_int(K), _p(model["tau"]),
+                         _p(model["y"]), _p(model["mu"]), _p(model["y_mu"]), _p(model["mu2"]), _p(model["t_XXVX_inv"]),
+                         _p(model["XV"]), _p(model["t_XVX_inv_XV"]), _p(model["XVX"]), _p(model["t_X"]), _p(model["S_a"]),
+                         C.c_double(var_ratio), C.c_double(maf), C.c_double(mac), C.c_double(missing), C.c_double(spa_pval),
+                         C.c_long(n_var), _p(ds), _p(out), _p(valid, C.c_int))
+    names = ["AF", "mac", "num", "beta", "SE", "pval", "p_norm", "converged"]
+    res = {k: out[:, i].copy() for i, k in enumerate(names)}
+    res["valid"] = valid.astype(bool)
+    return res
+
+
+def qnorm(p):
+    lib().orc_qnorm.restype = C.c_double
+    return lib().orc_qnorm(C.c_double(p))
 
 
 def max_threads():

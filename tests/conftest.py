@@ -74,6 +74,14 @@ def gpu():
     return sg.Context(0)
 
 
+def dosage_all(fx):
+    """Alt-allele dosages [10000][n] of every variant of the fixture (NaN = missing), as seqAssocGLMM_SPA reads them."""
+    p = fx.packed_all
+    d = np.stack([(p >> s) & 3 for s in (0, 2, 4, 6)], axis=2).reshape(p.shape[0], -1)[:, :fx.n_samp].astype(np.float64)
+    d[d == 3] = np.nan
+    return d
+
+
 def random_packed(rng, n_samp, n_var, missing=0.02, maf_lo=0.01):
     """Random 2-bit packed matrix [n_var][ceil(n/4)] with missing codes; pad bits random (raw, unsanitised)."""
     maf = rng.uniform(maf_lo, 0.5, size=n_var)

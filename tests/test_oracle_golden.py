@@ -112,3 +112,35 @@ def test_pcg_iteration_counts(oracle, fx, setup_binary):
     assert 2 <= it <= 6
     Ax = 1.0 * x / w + 0.5 * oracle.grm_mv(x)
     assert np.sum((Ax - setup_binary["X"][:, 1]) ** 2) <= 1e-5
+
+
+# ---------------------------------------------------------------- downstream p-values (seqAssocGLMM_SPA)
+@pytest.mark.parametrize("trait", ["binary", "quantitative"])
+def test_score_test_matches_golden_pvalues(fx, trait):
+    """test.saige_pval (inst/unitTests/test_SAIGE.R:79-106): the reference's golden model pushed through the restated
+    score test + SPA (src/saige_main.cpp:188-407, src/SPATest.cpp) reproduces all 10,000 golden rows -- including the
+    434 saddle-point-adjusted ones -- far inside the reference's own 1e-7."""
+    from conftest import dosage_all
+    from oracle import oracle as orc
+    md, pv = (fx.model, fx.pval) if trait == "binary" else (fx.model_quant, fx.pval_quant)
+    m = orc.init_nullmod(trait, md["noK_y"], md["fitted_values"], md["noK_X1"], md["noK_XV"], md["noK_XXVX_inv"], md["noK_V"],
+                         md["tau"])
+    r = orc.score_test(m, dosage_all(fx), float(np.mean(md["vr_ratio"])), mac=4.0)
+    ids = pv["id"] - 1
+    assert r["valid"][ids].all() and r["valid"].sum() == len(ids)
+    assert np.array_equal(r["AF"][ids], pv["AF_alt"]) and np.array_equal(r["mac"][ids], pv["mac"])
+    assert np.array_equal(r["num"][ids].astype(np.int64), pv["num"].astype(np.int64))
+    assert np.max(np.abs(r["pval"][ids] - pv["pval"]) / pv["pval"]) < 1e-12
+    assert np.max(np.abs(r["beta"][ids] - pv["beta"]) / np.abs(pv["beta"])) < 1e-10
+    assert np.max(np.abs(r["SE"][ids] - pv["SE"]) / pv["SE"]) < 1e-10
+    if trait == "binary":
+        assert np.max(np.abs(r["p_norm"][ids] - pv["p_norm"]) / pv["p_norm"]) < 1e-12
+        assert np.array_equal(r["converged"][ids].astype(int), pv["converged"])
+        assert int(np.sum(pv["pval"] != pv["p_norm"])) == 434          # SURVEY.md 8(c): the SPA-adjusted rows
+
+
+def test_qnorm_known_answers():
+    from oracle import oracle as orc
+    # R: qnorm(c(0.025, 0.5, 1e-10, 0.975))
+    for p, want in ((0.025, -1.959963984540054), (0.5, 0.0), (1e-10, -6.361340902404056), (0.975, 1.959963984540054)):
+        assert abs(orc.qnorm(p) - want) <= 1e-14 * max(1.0, abs(want))
