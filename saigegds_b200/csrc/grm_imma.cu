@@ -116,6 +116,10 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -410,29 +414,59 @@ __global__ void __launch_bounds__(kSpThreads) sparse_tile_sum_kernel(const int64
     double *sv = reinterpret_cast<double *>(smem_sp);
     uint16_t *sidx = reinterpret_cast<uint16_t *>(smem_sp + kSpTile * 8);
     int64_t *spos = reinterpret_cast<int64_t *>(smem_sp + kSpTile * 8 + kSpCap * 2);
+    __shared__ int64_t s_bounds[2][2];     // index range of this / the next work item (fetched one item ahead)
     const int64_t n_chunks = (R + kSpRows - 1) / kSpRows;
     const int64_t n_work = n_chunks * n_tiles;
-    for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+    auto item_range = [&](int64_t w, int64_t &lo, int64_t &hi) {
+        const int64_t t = w / n_chunks, chunk = w % n_chunks;
+        lo = (int64_t)t * R + chunk * kSpRows;
+        hi = (int64_t)t * R + min(R, (chunk + 1) * kSpRows);
+    };
+    if (threadIdx.x == 0 && (int64_t)blockIdx.x < n_work) {
+        int64_t lo, hi;
+        item_range(blockIdx.x, lo, hi);
+        s_bounds[0][0] = pos[lo];
+        s_bounds[0][1] = pos[hi];
+    }
+    int it = 0;
+    for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x, it++) {
         const int t = (int)(w / n_chunks);
         const int64_t chunk = w % n_chunks;
         const int64_t c0 = (int64_t)t * kSpTile;
         const int64_t r0 = chunk * kSpRows, r1 = min(R, r0 + kSpRows);
         const int nrow = (int)(r1 - r0);
         const int64_t *pp = pos + (size_t)t * R + r0;
-        __syncthreads();                                   // previous work item fully consumed
-        for (int i = threadIdx.x; i <= nrow; i += kSpThreads) spos[i] = pp[i];
-        for (int i = threadIdx.x; i < kSpTile; i += kSpThreads) sv[i] = (c0 + i < C) ? vec[c0 + i] : 0.0;
-        const int64_t e0 = pp[0], e1 = pp[nrow];
+        __syncthreads();                                   // previous work item fully consumed; s_bounds[it & 1] visible
+        const int64_t e0 = s_bounds[it & 1][0], e1 = s_bounds[it & 1][1];
         const int64_t a0 = e0 & ~(int64_t)7;               // 16-byte aligned start of the index range
+        // everything this item needs is requested at once (one memory latency per item): row offsets, vector tile, indices
+        for (int i = threadIdx.x; i <= nrow; i += kSpThreads) cp_async8(spos + i, pp + i);
+        for (int i = threadIdx.x; i < kSpTile; i += kSpThreads) {
+            if (c0 + i < C) cp_async8(sv + i, vec + c0 + i); else sv[i] = 0.0;
+        }
+        {
+            const int64_t pe = min(e1, a0 + kSpCap);
+            const int ngran = (int)((pe - a0 + 7) >> 3);
+            for (int i = threadIdx.x; i < ngran; i += kSpThreads) cp_async16(sidx + i * 8, idx16 + a0 + (int64_t)i * 8);
+        }
+        cp_async_commit();
+        if (threadIdx.x == 0 && w + gridDim.x < n_work) {   // bounds of the next item: their latency hides behind this item's loads
+            int64_t lo, hi;
+            item_range(w + gridDim.x, lo, hi);
+            s_bounds[(it + 1) & 1][0] = pos[lo];
+            s_bounds[(it + 1) & 1][1] = pos[hi];
+        }
         double acc[kSpRows / kSpThreads];
 #pragma unroll
         for (int k = 0; k < kSpRows / kSpThreads; k++) acc[k] = 0;
-        for (int64_t pc = a0; pc < e1; pc += kSpCap) {     // almost always a single piece
+        for (int64_t pc = a0; pc < e1 || pc == a0; pc += kSpCap) {     // almost always a single piece
             const int64_t pe = min(e1, pc + kSpCap);
-            const int ngran = (int)((pe - pc + 7) >> 3);
-            __syncthreads();
-            for (int i = threadIdx.x; i < ngran; i += kSpThreads) cp_async16(sidx + i * 8, idx16 + pc + (int64_t)i * 8);
-            cp_async_commit();
+            if (pc != a0) {
+                const int ngran = (int)((pe - pc + 7) >> 3);
+                __syncthreads();
+                for (int i = threadIdx.x; i < ngran; i += kSpThreads) cp_async16(sidx + i * 8, idx16 + pc + (int64_t)i * 8);
+                cp_async_commit();
+            }
             cp_async_wait<0>();
             __syncthreads();
 #pragma unroll
@@ -449,6 +483,7 @@ __global__ void __launch_bounds__(kSpThreads) sparse_tile_sum_kernel(const int64
                     if (hi > lo) acc[k] += (s0 + s1) + (s2 + s3);
                 }
             }
+            if (e1 <= a0) break;
         }
 #pragma unroll
         for (int k = 0; k < kSpRows / kSpThreads; k++) {
