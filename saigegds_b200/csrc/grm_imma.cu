@@ -205,11 +205,19 @@ __global__ void __launch_bounds__(256) absmax_sum_kernel(const double *__restric
         last = atomicInc(counter, G - 1) == (unsigned)(G - 1);
     }
     __syncthreads();
-    if (last && threadIdx.x == 0) {
-        __threadfence();
+    if (!last) return;
+    // the last block adds the partials with a fixed tree (deterministic), all threads taking part
+    __threadfence();
+    {
         const volatile double *p = partial;
-        double m = 0, t = 0, t2 = 0;
-        for (int i = 0; i < G; i++) { m = fmax(m, p[i]); t += p[G + i]; t2 += p[2 * G + i]; }
+        double m1 = 0, t1 = 0, t21 = 0;
+        for (int i = threadIdx.x; i < G; i += 256) { m1 = fmax(m1, p[i]); t1 += p[G + i]; t21 += p[2 * G + i]; }
+        mx = block_reduce_max<256>(m1, sm);
+        s = block_reduce_sum<256>(t1, sm);
+        s2 = block_reduce_sum<256>(t21, sm);
+    }
+    if (threadIdx.x == 0) {
+        double m = mx, t = s, t2 = s2;
         if (!isfinite(t)) m = t;     // NaN / Inf anywhere in b poisons the product like it does in the reference
         scal[S_MAXB] = m;
         scal[S_SUMB] = t;
