@@ -952,7 +952,11 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
     // In profiling mode everything runs serially on the main stream so that each kernel can be timed.
     cudaStream_t side = (c.profiling || !p->opt_fork) ? c.stream : p->side;
     const int sp_grid = c.sm_count * p->opt_grid_mult;
-    if (p->fused_ok && c.kernel != SGB_KERNEL_IMMA_TWOPASS) {
+    // The fused kernel pays ~1 us of cross-CTA latency per 32-variant tile whatever the slice width, so it only beats the two
+    // HBM passes when every CTA's slice is (nearly) full: SGB_KERNEL_AUTO takes it from 10 of the 12 K-steps per CTA upwards
+    // (N >= ~380K on 148 SMs) and the two-pass kernels otherwise; SGB_KERNEL_IMMA forces it whenever the shape allows.
+    const bool use_fused = p->fused_ok && (c.kernel == SGB_KERNEL_IMMA || (c.kernel == SGB_KERNEL_AUTO && p->f_ks_per_cta >= 10));
+    if (use_fused) {
         c.async_err = p->f_herr.p;
         c.async_err_dev = p->f_err.get();
         for (int col = 0; col < k; col++) {
