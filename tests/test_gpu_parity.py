@@ -158,6 +158,39 @@ def test_product_properties_at_scale(gpu, kernel):
         gpu.set_kernel("auto")
 
 
+@pytest.mark.parametrize("n,m,label", [(430000, 100000, "C3"), (430000, 300000, "C5")])
+def test_full_size_products(gpu, n, m, label):
+    """BASELINE.json's full shapes (C3: 430K x 100K, 10.75 GB packed; C5: 430K x 300K, 32 GB): far beyond the scalar oracle, so
+    the three independent kernels (fused single pass -- all 140 CTAs and every tile --, two-pass tensor core, FP64 CUDA core)
+    are checked against each other and through size-independent properties: linearity, symmetry, positive definiteness,
+    e_i'A e_i = diag(GRM)_i, bit reproducibility, multi-RHS == single RHS."""
+    try:
+        lut, diag = gpu.store_synthetic(n, m, seed=200, missing_rate=0.005, want_outputs=True)
+        rng = np.random.default_rng(5)
+        x, y = rng.standard_normal(n), rng.standard_normal(n)
+        gpu.set_kernel("imma")                                                # fused single pass (forced)
+        Ax, Ay = gpu.get_crossprod_b_grm(x), gpu.get_crossprod_b_grm(y)
+        assert np.array_equal(Ax, gpu.get_crossprod_b_grm(x))                 # bit reproducible
+        assert relinf(gpu.get_crossprod_b_grm(2.5 * x - 0.5 * y), 2.5 * Ax - 0.5 * Ay) < 1e-11
+        assert abs(y @ Ax - x @ Ay) / abs(y @ Ax) < 1e-10
+        assert x @ Ax > 0
+        e = np.zeros(n); e[123457] = 1.0
+        assert abs(gpu.get_crossprod_b_grm(e)[123457] - diag[123457]) / diag[123457] < 1e-11
+        B = np.stack([x, y, e], axis=1)
+        out = gpu.get_crossprod_b_grm(B)
+        assert np.array_equal(out[:, 0], Ax) and np.array_equal(out[:, 1], Ay)
+        gpu.set_kernel("imma2")                                               # two HBM passes
+        assert relinf(gpu.get_crossprod_b_grm(x), Ax) < PROD_TOL
+        if label == "C3":
+            gpu.set_kernel("simt")                                            # FP64 CUDA cores, no quantisation anywhere
+            assert relinf(gpu.get_crossprod_b_grm(x), Ax) < PROD_TOL
+        gpu.set_kernel("auto")                                                # nearly full slices: auto == fused here
+        assert np.array_equal(gpu.get_crossprod_b_grm(x), Ax)
+    finally:
+        gpu.set_kernel("auto")
+        gpu.store_synthetic(1024, 64)                                         # release the big shard
+
+
 def test_synthetic_generator_is_shard_invariant(gpu):
     full = gpu.synth_to_host(1003, 64, 0, seed=11)
     part = gpu.synth_to_host(1003, 20, 30, seed=11)
