@@ -196,6 +196,11 @@ int sgb_free_device(sgb_context *ctx, void *ptr_device);
 int sgb_time_products_device(sgb_context *ctx, const double *b_device, double *out_device, int k, int reps,
                              float *total_ms);
 int sgb_malloc_device(sgb_context *ctx, int64_t bytes, void **ptr_device);
+/* Page-locked host memory for the vectors handed to the host-pointer entry points (sgb_grm_mv, sgb_pcg, ...): the copies
+ * then run at PCIe speed instead of being staged by the driver.  Any host pointer is accepted by those entry points;
+ * this only makes them faster (an Rcpp shim can keep a pinned mirror of the vectors it passes per PCG iteration). */
+int sgb_malloc_host(sgb_context *ctx, int64_t bytes, void **ptr_host);
+int sgb_free_host(sgb_context *ctx, void *ptr_host);
 /* Per-kernel CUDA-event timing of the product kernels (serialises the stream; measurement aid only).
  * sgb_kernel_times writes lines "name total_ms launches\n" into buf. */
 int sgb_set_profiling(sgb_context *ctx, int on);

@@ -75,7 +75,7 @@ SYMBOLS = [
     "sgb_fit_AI_PCG_quant", "sgb_calc_var_ratio_binary", "sgb_calc_var_ratio_quant", "sgb_r_set_seed",
     "sgb_r_unif_rand", "sgb_r_sample_int", "sgb_get_stats", "sgb_reset_stats", "sgb_synth_geno_device",
     "sgb_copy_from_device", "sgb_free_device", "sgb_time_products_device", "sgb_malloc_device", "sgb_copy_to_device",
-    "sgb_set_profiling", "sgb_kernel_times",
+    "sgb_set_profiling", "sgb_kernel_times", "sgb_malloc_host", "sgb_free_host",
 ]
 
 

@@ -53,6 +53,9 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
+            for ptr in getattr(self, "_pinned", []):
+                L.lib().sgb_free_host(self._h, ptr)
+            self._pinned = []
             L.lib().sgb_ctx_destroy(self._h)
             self._h = None
 
@@ -136,14 +139,31 @@ class Context:
         return ds
 
     # ---- products and solves ----
-    def get_crossprod_b_grm(self, b: np.ndarray) -> np.ndarray:
-        """(1/M) G G' b for one vector [N] or k vectors [N, k] (host in, host out)."""
+    def get_crossprod_b_grm(self, b: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """(1/M) G G' b for one vector [N] or k vectors [N, k] (host in, host out).  `out` (same shape, float64, Fortran
+        order) is filled in place when given -- with `pinned_empty` buffers for both, the copies run at PCIe speed."""
         b = np.asarray(b, dtype=np.float64)
         one = b.ndim == 1
         bb = _f64(b.reshape(self.n_samp, -1), "F")
-        out = np.empty_like(bb, order="F")
-        L.check(L.lib().sgb_grm_mv(self._h, _p(bb), _p(out), C.c_int(bb.shape[1])))
-        return out[:, 0].copy() if one else out
+        if out is not None:
+            oo = out.reshape(self.n_samp, -1)
+            if oo.dtype != np.float64 or not oo.flags.f_contiguous or oo.shape != bb.shape:
+                raise L.InvalidArgument(L.SGB_ERR_INVALID, "out must be float64, Fortran-contiguous and shaped like b")
+            L.check(L.lib().sgb_grm_mv(self._h, _p(bb), _p(oo), C.c_int(bb.shape[1])))
+            return out
+        oo = np.empty_like(bb, order="F")
+        L.check(L.lib().sgb_grm_mv(self._h, _p(bb), _p(oo), C.c_int(bb.shape[1])))
+        return oo[:, 0].copy() if one else oo
+
+    def pinned_empty(self, shape) -> np.ndarray:
+        """A float64 Fortran-order array in page-locked host memory (sgb_malloc_host); freed with the context."""
+        n = int(np.prod(shape))
+        ptr = C.c_void_p()
+        L.check(L.lib().sgb_malloc_host(self._h, C.c_int64(8 * max(n, 1)), C.byref(ptr)))
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(ptr)
+        buf = (C.c_double * max(n, 1)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape, order="F")
 
     def get_diag_sigma(self, w, tau) -> np.ndarray:
         w, tau = _f64(w), _f64(tau)

@@ -301,6 +301,12 @@ int sgb_malloc_device(sgb_context *ctx, int64_t bytes, void **ptr_device) {
 int sgb_free_device(sgb_context *ctx, void *ptr_device) {
     return guarded(ctx, [&] { SGB_CUDA(cudaFree(ptr_device)); });
 }
+int sgb_malloc_host(sgb_context *ctx, int64_t bytes, void **ptr_host) {
+    return guarded(ctx, [&] { SGB_CUDA(cudaMallocHost(ptr_host, (size_t)bytes)); });
+}
+int sgb_free_host(sgb_context *ctx, void *ptr_host) {
+    return guarded(ctx, [&] { SGB_CUDA(cudaFreeHost(ptr_host)); });
+}
 int sgb_copy_to_device(sgb_context *ctx, void *dst_device, const void *src_host, int64_t bytes) {
     return guarded(ctx, [&] { ctx->h2d(dst_device, src_host, (size_t)bytes); ctx->sync(); });
 }

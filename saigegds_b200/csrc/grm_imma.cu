@@ -73,6 +73,7 @@ struct ImmaPlan {
     CUtensorMap f_tmap;      // packed matrix as a 2-D byte tensor [M][pitch], box 128 B x 32 rows, SWIZZLE_128B
     double f_efactor = 0;    // max_j |inv_j| sqrt(sum_n lut_j[c_nj]^2) / M_total (bound on |e_j| / |b|_2)
     int f_poll_ns = 100;
+    int f_lag = 6;           // phase B runs this many tiles behind phase A (env SGB_FUSED_LAG)
     int64_t f_acc_stride = 0;
     DevBuf<double> f_rout, f_htotal, f_u;
     DevBuf<int> f_err;
@@ -910,6 +911,8 @@ void imma_prepare(Context &c) {
                     p->f_efactor = ef / (double)c.M_total * (1.0 + 1e-9);
                     if (!(p->f_efactor > 0) || !std::isfinite(p->f_efactor)) p->f_efactor = 1e-300;   // all-monomorphic shard: e == 0
                     if (const char *e = getenv("SGB_FUSED_POLL_NS")) p->f_poll_ns = std::max(0, atoi(e));
+                    if (const char *e = getenv("SGB_FUSED_LAG")) p->f_lag = atoi(e);
+                    p->f_lag = std::min(kFNBuf - 2, std::max(1, p->f_lag));
                     {
                         typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -962,6 +965,22 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
         for (int col = 0; col < k; col++) {
             const double *b = b_all + (size_t)col * N;
             double *out = out_all + (size_t)col * N;
+            // the small preparation kernels (max|b|, |b|_2, digits of b, zeroing of the limbs) need no shared memory and run on
+            // the side stream beside the sparse U_j kernel
+            const bool fork = side != c.stream;
+            if (fork) {
+                SGB_CUDA(cudaEventRecord(p->ev_in, c.stream));
+                SGB_CUDA(cudaStreamWaitEvent(side, p->ev_in, 0));
+            }
+            c.prof_begin();
+            absmax_sum_kernel<<<G, 256, 0, side>>>(b, N, p->red.get(), p->counter.get(), p->scal.get(), p->f_efactor);
+            SGB_CHECK_LAUNCH();
+            digits_b128_kernel<<<(unsigned)((p->ksteps * 256 + 255) / 256), 256, 0, side>>>(b, N, p->ksteps * 256, p->scal.get(),
+                                                                                          p->dfrag128.get());
+            SGB_CHECK_LAUNCH();
+            SGB_CUDA(cudaMemsetAsync(p->f_acc.get(), 0, sizeof(unsigned long long) * p->f_acc_stride * kFV * 2, side));
+            c.prof_end("imma_prep_b (absmax+digits+memset)");
+            if (fork) SGB_CUDA(cudaEventRecord(p->ev_u, side));
             c.prof_begin();
             sparse_tile_sum_kernel<<<sp_grid, kSpThreads, kSpSmem, c.stream>>>(p->mv_pos.get(), p->mv_i16.get(), b, M, N,
                                                                             p->n_stiles, p->upart.get());
@@ -970,17 +989,12 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
             c.prof_begin();
             sum_tiles_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c.stream>>>(p->upart.get(), p->n_stiles, M, p->f_u.get());
             SGB_CHECK_LAUNCH();
-            absmax_sum_kernel<<<G, 256, 0, c.stream>>>(b, N, p->red.get(), p->counter.get(), p->scal.get(), p->f_efactor);
-            SGB_CHECK_LAUNCH();
-            digits_b128_kernel<<<(unsigned)((p->ksteps * 256 + 255) / 256), 256, 0, c.stream>>>(b, N, p->ksteps * 256, p->scal.get(),
-                                                                                              p->dfrag128.get());
-            SGB_CHECK_LAUNCH();
-            SGB_CUDA(cudaMemsetAsync(p->f_acc.get(), 0, sizeof(unsigned long long) * p->f_acc_stride * kFV * 2, c.stream));
-            c.prof_end("imma_prep_b (absmax+digits+memset)");
+            c.prof_end("sum_tiles_kernel");
+            if (fork) SGB_CUDA(cudaStreamWaitEvent(c.stream, p->ev_u, 0));
             FusedArgs fa;
             fa.packed = c.packed.get(); fa.pitch = c.pitch; fa.M = M; fa.N = N; fa.ksteps = p->ksteps;
             fa.ks_per_cta = p->f_ks_per_cta; fa.n_tiles = p->f_tiles; fa.dfrag128 = p->dfrag128.get();
-            fa.acc_t = p->f_acc.get(); fa.acc_stride = p->f_acc_stride; fa.u = p->f_u.get(); fa.poll_ns = p->f_poll_ns; fa.lag = std::min(kFNBuf - 2, std::max(1, getenv("SGB_FUSED_LAG") ? atoi(getenv("SGB_FUSED_LAG")) : 6));
+            fa.acc_t = p->f_acc.get(); fa.acc_stride = p->f_acc_stride; fa.u = p->f_u.get(); fa.poll_ns = p->f_poll_ns; fa.lag = p->f_lag;
             fa.lut = c.lut.get(); fa.inv_mtotal = 1.0 / (double)c.M_total; fa.scal = p->scal.get(); fa.hm = p->hm.get();
             fa.h_total = p->f_htotal.get(); fa.rout = p->f_rout.get(); fa.err = p->f_err.get();
             void *kargs[] = {&p->f_tmap, &fa};
