@@ -482,13 +482,17 @@ __global__ void __launch_bounds__(kSpThreads) sparse_tile_sum_kernel(const int64
             for (int k = 0; k < kSpRows / kSpThreads; k++) {
                 const int r = threadIdx.x + k * kSpThreads;
                 if (r < nrow) {
-                    const int64_t lo = max(spos[r], pc), hi = min(spos[r + 1], pe);
+                    // entries [lo, hi) of this row inside the staged piece, as 32-bit offsets; four indices per 64-bit shared
+                    // load once the offset is 4-aligned (the shared-memory pipe, not HBM, bounds this kernel)
+                    const int lo = (int)(max(spos[r], pc) - pc), hi = (int)(min(spos[r + 1], pe) - pc);
                     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-                    int64_t i = lo;
+                    int i = lo;
+                    for (; i < hi && (i & 3); i++) s0 += sv[sidx[i]];
                     for (; i + 4 <= hi; i += 4) {
-                        s0 += sv[sidx[i - pc]]; s1 += sv[sidx[i - pc + 1]]; s2 += sv[sidx[i - pc + 2]]; s3 += sv[sidx[i - pc + 3]];
+                        const uint2 q = *reinterpret_cast<const uint2 *>(sidx + i);
+                        s0 += sv[q.x & 0xffffu]; s1 += sv[q.x >> 16]; s2 += sv[q.y & 0xffffu]; s3 += sv[q.y >> 16];
                     }
-                    for (; i < hi; i++) s0 += sv[sidx[i - pc]];
+                    for (; i < hi; i++) s1 += sv[sidx[i]];
                     if (hi > lo) acc[k] += (s0 + s1) + (s2 + s3);
                 }
             }
