@@ -642,8 +642,16 @@ __global__ void __launch_bounds__(kBThreads, 2) imma_apply_kernel(const uint8_t 
             for (int t = 0; t < 4; t++)
 #pragma unroll
                 for (int hh = 0; hh < 2; hh++) {
-                    double v = w0 * (double)(acc[rb][t][2 * hh] >> (2 * t)) + w1 * (double)(acc[rb][t][2 * hh + 1] >> (2 * t));
-                    acc[rb][t][2 * hh] = acc[rb][t][2 * hh + 1] = 0;
+                    // t = 0 holds the UNMASKED bytes (c0 + 4 c1 + 16 c2 + 64 c3 meet the same multiplier): plane 0 by subtraction
+                    int s0, s1;
+                    if (t == 0) {
+                        s0 = acc[rb][0][2 * hh] - acc[rb][1][2 * hh] - acc[rb][2][2 * hh] - acc[rb][3][2 * hh];
+                        s1 = acc[rb][0][2 * hh + 1] - acc[rb][1][2 * hh + 1] - acc[rb][2][2 * hh + 1] - acc[rb][3][2 * hh + 1];
+                    } else {
+                        s0 = acc[rb][t][2 * hh] >> (2 * t);
+                        s1 = acc[rb][t][2 * hh + 1] >> (2 * t);
+                    }
+                    double v = w0 * (double)s0 + w1 * (double)s1;
                     v += __shfl_xor_sync(0xffffffffu, v, 1);
                     v += __shfl_xor_sync(0xffffffffu, v, 2);
                     const int64_t n = ((int64_t)byte0 + (warp * kBRB + rb) * 16 + g + hh * 8) * 4 + t;
@@ -652,6 +660,12 @@ __global__ void __launch_bounds__(kBThreads, 2) imma_apply_kernel(const uint8_t 
                         *dst = first_flush ? v : (*dst + v);
                     }
                 }
+#pragma unroll
+        for (int rb = 0; rb < kBRB; rb++)
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) acc[rb][t][q] = 0;
         first_flush = false;
     };
 
@@ -677,14 +691,15 @@ __global__ void __launch_bounds__(kBThreads, 2) imma_apply_kernel(const uint8_t 
                 uint32_t x0, x1, x2, x3;   // x0/x1: variants 0-15 at byte g / g+8; x2/x3: variants 16-31
                 asm volatile("ldmatrix.sync.aligned.m16n16.x2.trans.shared.b8 {%0,%1,%2,%3}, [%4];"
                              : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(addr));
+                imma_u8s8(acc[rb][0], x0, x1, x2, x3, bf.x, bf.y);
 #pragma unroll
-                for (int t = 0; t < 4; t++) {
+                for (int t = 1; t < 4; t++) {
                     const uint32_t m = 0x03030303u << (2 * t);
                     imma_u8s8(acc[rb][t], x0 & m, x1 & m, x2 & m, x3 & m, bf.x, bf.y);
                 }
             }
         }
-        // one accumulator sees 32 terms of at most 192*64 per K-block: flush every 2048 K-blocks (< 2^30)
+        // one accumulator sees 32 terms of at most 255*64 per K-block (the unmasked plane): flush every 2048 K-blocks (< 2^31)
         since_flush += kKbPerStage;
         if (since_flush >= 2048) { flush(); since_flush = 0; }
     }
