@@ -62,6 +62,11 @@ struct ImmaPlan {
     DevBuf<uint16_t> mv_i16; // [nnz] sample offset inside the tile
     DevBuf<int64_t> ms_pos;  // [n_vtiles * N + 1] tile-major start of (variant tile, sample)
     DevBuf<uint16_t> ms_i16; // [nnz] variant offset inside the tile
+    // lane-interleaved ("ELL") copy of the two lists, what sparse_ell_sum_kernel reads: per (tile, group of 32 rows) a block
+    // [k][lane] of 16-bit offsets padded to the longest row of the group with kSpTile (a zero slot of the vector tile)
+    DevBuf<int64_t> mv_gstart, ms_gstart;   // [n_tiles * n_groups + 1] block starts (entries, multiples of 32)
+    DevBuf<uint16_t> mv_ell, ms_ell;
+    bool use_csr = false;    // env SGB_SPARSE_CSR: the older row-per-thread kernel (comparison only)
     int n_stiles = 0, n_vtiles = 0;
     int opt_fork = 1, opt_grid_mult = 2, opt_stages = 3;   // tuning knobs (env: SGB_SPARSE_FORK, SGB_SPARSE_GRID_MULT, SGB_DOTS_STAGES)
     // fused single-pass kernel (grm_fused.cuh)
@@ -506,6 +511,167 @@ __global__ void __launch_bounds__(kSpThreads) sparse_tile_sum_kernel(const int64
     }
 }
 
+// ---- bulk-copy (TMA) helpers of the sparse kernel ---------------------------------------------------------------------
+__device__ __forceinline__ unsigned sp_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sp_mbar_init(unsigned long long *b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sp_smem(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sp_mbar_expect_tx(unsigned long long *b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sp_smem(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sp_mbar_wait(unsigned long long *b, unsigned parity) {
+    const unsigned a = sp_smem(b);
+    unsigned ok = 0;
+    while (!ok)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void sp_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sp_smem(dst)), "l"(src), "r"(bytes), "r"(sp_smem(bar)) : "memory");
+}
+
+// ---- lane-interleaved layout ------------------------------------------------------------------------------------------
+// The row-per-thread walk above spends ~24 instructions per entry (divergent trip counts, 64-bit bookkeeping) and is bound
+// by instruction issue, not by memory.  Here the entries of 32 consecutive rows are stored interleaved, [k][lane], padded to
+// the longest row of the group with the index of a zero slot: a warp walks its group with one coalesced 64-byte index
+// load, one gather and one add per 32 entries, no branches and no per-row offsets (1.5x the index bytes at 0.5 % missing).
+constexpr int kEllRows = 1024;                    // rows per work item = 32 groups
+constexpr int kEllThreads = 512;                  // 16 warps x 2 groups
+constexpr int kEllCap = 36864;                    // index entries staged per piece (72 KB); an item holds ~1024 x 30 at 0.5 % missing
+constexpr int kEllSv = kSpTile + 8;               // vector tile + the zero slot (padded to 64 bytes)
+constexpr int kEllSmem = kEllSv * 8 + kEllCap * 2 + 40 * 8;
+
+// len32[t * G + g] = 32 * (longest row of group g in tile t); pos = the tile-major CSR starts
+__global__ void ell_len_kernel(const int64_t *__restrict__ pos, int64_t R, int64_t G, int n_tiles, int64_t *__restrict__ len32) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G * n_tiles) return;
+    const int64_t t = i / G, g = i % G;
+    int64_t mx = 0;
+    for (int r = 0; r < 32; r++) {
+        const int64_t row = g * 32 + r;
+        if (row < R) mx = max(mx, pos[t * R + row + 1] - pos[t * R + row]);
+    }
+    len32[i] = mx * 32;
+}
+// one warp per (tile, group): lane <-> row
+__global__ void ell_fill_kernel(const int64_t *__restrict__ pos, const uint16_t *__restrict__ i16, int64_t R, int64_t G, int n_tiles,
+                                const int64_t *__restrict__ gstart, uint16_t *__restrict__ ell) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= G * n_tiles) return;
+    const int64_t t = i / G, g = i % G, row = g * 32 + lane;
+    const int64_t s = gstart[i], len = (gstart[i + 1] - s) >> 5;
+    int64_t p0 = 0, mylen = 0;
+    if (row < R) { p0 = pos[t * R + row]; mylen = pos[t * R + row + 1] - p0; }
+    for (int64_t k = 0; k < len; k++) ell[s + k * 32 + lane] = (k < mylen) ? i16[p0 + k] : (uint16_t)kSpTile;
+}
+
+__global__ void __launch_bounds__(kEllThreads) sparse_ell_sum_kernel(const int64_t *__restrict__ gstart, const uint16_t *__restrict__ ell,
+                                                                     const double *__restrict__ vec, int64_t R, int64_t C, int64_t G,
+                                                                     int n_tiles, double *__restrict__ part) {
+    extern __shared__ __align__(16) uint8_t smem_sp[];
+    double *sv = reinterpret_cast<double *>(smem_sp);
+    uint16_t *sidx = reinterpret_cast<uint16_t *>(smem_sp + kEllSv * 8);
+    int64_t *sgs = reinterpret_cast<int64_t *>(smem_sp + kEllSv * 8 + kEllCap * 2);     // 33 group starts of the item
+    __shared__ int64_t s_bounds[2][2];
+    __shared__ unsigned long long s_bar;
+    unsigned bar_phase = 0;
+    if (threadIdx.x == 0) {
+        sp_mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n_chunks = (G + 31) / 32;
+    const int64_t n_work = n_chunks * n_tiles;
+    auto item_range = [&](int64_t w, int64_t &lo, int64_t &hi) {
+        const int64_t t = w / n_chunks, chunk = w % n_chunks;
+        lo = t * G + chunk * 32;
+        hi = t * G + min(G, (chunk + 1) * 32);
+    };
+    if (threadIdx.x == 0 && (int64_t)blockIdx.x < n_work) {
+        int64_t lo, hi;
+        item_range(blockIdx.x, lo, hi);
+        s_bounds[0][0] = gstart[lo];
+        s_bounds[0][1] = gstart[hi];
+    }
+    if (threadIdx.x < 8) sv[kSpTile + threadIdx.x] = 0.0;                                 // the zero slot
+    int it = 0;
+    for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x, it++) {
+        const int t = (int)(w / n_chunks);
+        const int64_t chunk = w % n_chunks;
+        const int64_t c0 = (int64_t)t * kSpTile;
+        const int64_t g0 = chunk * 32;
+        const int ng = (int)(min(G, g0 + 32) - g0);
+        const int64_t *gp = gstart + (size_t)t * G + g0;
+        __syncthreads();                                   // previous item consumed; s_bounds[it & 1] visible
+        const int64_t e0 = s_bounds[it & 1][0], e1 = s_bounds[it & 1][1];
+        // everything the item needs in three requests: the 33 group starts (cp.async), the vector tile and the first piece of
+        // the index block (one bulk copy each, completion counted on an mbarrier; per-thread cp.async only where the tile is
+        // ragged or the vector is not 16-byte aligned)
+        for (int i = threadIdx.x; i <= ng; i += kEllThreads) cp_async8(sgs + i, gp + i);
+        const int ncol = (int)min((int64_t)kSpTile, C - c0);
+        const bool sv_bulk = ((ncol & 1) == 0) && ((reinterpret_cast<uintptr_t>(vec + c0) & 15) == 0);
+        if (!sv_bulk)
+            for (int i = threadIdx.x; i < ncol; i += kEllThreads) cp_async8(sv + i, vec + c0 + i);
+        for (int i = ncol + threadIdx.x; i < kSpTile; i += kEllThreads) sv[i] = 0.0;
+        {
+            const int64_t pe = min(e1, e0 + kEllCap);
+            if (threadIdx.x == 0) {
+                const unsigned nb_idx = (unsigned)((pe - e0) * 2), nb_sv = sv_bulk ? (unsigned)ncol * 8u : 0u;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic reads/writes of the buffers
+                sp_mbar_expect_tx(&s_bar, nb_idx + nb_sv);
+                if (nb_sv) sp_bulk_g2s(sv, vec + c0, nb_sv, &s_bar);
+                if (nb_idx) sp_bulk_g2s(sidx, ell + e0, nb_idx, &s_bar);
+            }
+        }
+        cp_async_commit();
+        if (threadIdx.x == 0 && w + gridDim.x < n_work) {
+            int64_t lo, hi;
+            item_range(w + gridDim.x, lo, hi);
+            s_bounds[(it + 1) & 1][0] = gstart[lo];
+            s_bounds[(it + 1) & 1][1] = gstart[hi];
+        }
+        double acc[2] = {0, 0};
+        for (int64_t pc = e0; pc < e1 || pc == e0; pc += kEllCap) {     // almost always a single piece
+            const int64_t pe = min(e1, pc + kEllCap);
+            if (pc != e0) {
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    sp_mbar_expect_tx(&s_bar, (unsigned)((pe - pc) * 2));
+                    sp_bulk_g2s(sidx, ell + pc, (unsigned)((pe - pc) * 2), &s_bar);
+                }
+            }
+            cp_async_wait<0>();
+            sp_mbar_wait(&s_bar, bar_phase);
+            bar_phase ^= 1;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int gi = warp + 16 * k;
+                if (gi < ng) {
+                    const int lo = (int)(max(sgs[gi], pc) - pc), hi = (int)(min(sgs[gi + 1], pe) - pc);
+                    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+                    int i = lo + lane;
+                    for (; i + 96 < hi; i += 128) {
+                        s0 += sv[sidx[i]]; s1 += sv[sidx[i + 32]]; s2 += sv[sidx[i + 64]]; s3 += sv[sidx[i + 96]];
+                    }
+                    for (; i < hi; i += 32) s0 += sv[sidx[i]];
+                    acc[k] += (s0 + s1) + (s2 + s3);
+                }
+            }
+            if (e1 <= e0) break;
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int gi = warp + 16 * k;
+            const int64_t r = (g0 + gi) * 32 + lane;
+            if (gi < ng && r < R) part[(size_t)t * R + r] = acc[k];
+        }
+    }
+}
+
 // cnt[t * R + r] = number of entries of row r (sorted list idx[ptr[r] .. ptr[r+1])) with column in tile t
 __global__ void sparse_tile_count_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx, int64_t R,
                                          int64_t *__restrict__ cnt) {
@@ -795,6 +961,22 @@ int pick_split(int64_t tiles, int slots, int max_split) {
     return best;
 }
 
+// missing-genotype sums: rows = variants gathering b (U_j) or rows = samples gathering hm (corr_n)
+void launch_sparse(Context &c, ImmaPlan *p, bool by_variant, const double *vec, cudaStream_t st, int grid) {
+    const int64_t R = by_variant ? c.M : c.N, C = by_variant ? c.N : c.M;
+    const int nt = by_variant ? p->n_stiles : p->n_vtiles;
+    double *part = by_variant ? p->upart.get() : p->cpart.get();
+    if (p->use_csr) {
+        sparse_tile_sum_kernel<<<grid, kSpThreads, kSpSmem, st>>>((by_variant ? p->mv_pos : p->ms_pos).get(),
+                                                                  (by_variant ? p->mv_i16 : p->ms_i16).get(), vec, R, C, nt, part);
+    } else {
+        sparse_ell_sum_kernel<<<grid, kEllThreads, kEllSmem, st>>>((by_variant ? p->mv_gstart : p->ms_gstart).get(),
+                                                                  (by_variant ? p->mv_ell : p->ms_ell).get(), vec, R, C, (R + 31) / 32, nt,
+                                                                  part);
+    }
+    SGB_CHECK_LAUNCH();
+}
+
 }  // namespace
 
 bool imma_available(const Context &c) { return c.imma != nullptr; }
@@ -873,6 +1055,29 @@ void imma_prepare(Context &c) {
         tile_major(p->mv_ptr, p->mv_idx, M, p->n_stiles, p->mv_pos, p->mv_i16);
         tile_major(p->ms_ptr, p->ms_idx, N, p->n_vtiles, p->ms_pos, p->ms_i16);
         c.sync();
+        auto to_ell = [&](const DevBuf<int64_t> &pos, const DevBuf<uint16_t> &i16, int64_t R, int nt, DevBuf<int64_t> &gstart,
+                          DevBuf<uint16_t> &ell) {
+            const int64_t G = (R + 31) / 32, cells = G * nt;
+            gstart.ensure((size_t)cells + 1);
+            SGB_CUDA(cudaMemsetAsync(gstart.get() + cells, 0, sizeof(int64_t), c.stream));
+            ell_len_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, c.stream>>>(pos.get(), R, G, nt, gstart.get());
+            SGB_CHECK_LAUNCH();
+            thrust::exclusive_scan(thrust::cuda::par.on(c.stream), gstart.get(), gstart.get() + cells + 1, gstart.get());
+            int64_t total = 0;
+            c.d2h(&total, gstart.get() + cells, sizeof(int64_t));
+            c.sync();
+            ell.ensure((size_t)total + 64);
+            ell_fill_kernel<<<(unsigned)((cells + 7) / 8), 256, 0, c.stream>>>(pos.get(), i16.get(), R, G, nt, gstart.get(), ell.get());
+            SGB_CHECK_LAUNCH();
+        };
+        to_ell(p->mv_pos, p->mv_i16, M, p->n_stiles, p->mv_gstart, p->mv_ell);
+        to_ell(p->ms_pos, p->ms_i16, N, p->n_vtiles, p->ms_gstart, p->ms_ell);
+        c.sync();
+        p->use_csr = getenv("SGB_SPARSE_CSR") != nullptr;
+        if (!p->use_csr) {                    // the row-major-in-tile lists are only kept for the comparison switch
+            p->mv_pos.release(); p->mv_i16.release(); p->ms_pos.release(); p->ms_i16.release();
+        }
+        SGB_CUDA(cudaFuncSetAttribute(sparse_ell_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEllSmem));
         // the row-major 32-bit lists are only needed to build the tile-major ones
         p->mv_idx.release(); p->ms_idx.release();
         SGB_CUDA(cudaFuncSetAttribute(sparse_tile_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmem));
@@ -1001,9 +1206,7 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
             c.prof_end("imma_prep_b (absmax+digits+memset)");
             if (fork) SGB_CUDA(cudaEventRecord(p->ev_u, side));
             c.prof_begin();
-            sparse_tile_sum_kernel<<<sp_grid, kSpThreads, kSpSmem, c.stream>>>(p->mv_pos.get(), p->mv_i16.get(), b, M, N,
-                                                                            p->n_stiles, p->upart.get());
-            SGB_CHECK_LAUNCH();
+            launch_sparse(c, p, true, b, c.stream, sp_grid);
             c.prof_end("sparse_tile_sum_kernel (U_j)");
             c.prof_begin();
             sum_tiles_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c.stream>>>(p->upart.get(), p->n_stiles, M, p->f_u.get());
@@ -1023,9 +1226,7 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
             c.prof_end("imma_fused_kernel");
             SGB_CUDA(cudaMemcpyAsync(p->f_herr.p, p->f_err.get(), sizeof(int), cudaMemcpyDeviceToHost, c.stream));
             c.prof_begin();
-            sparse_tile_sum_kernel<<<sp_grid, kSpThreads, kSpSmem, c.stream>>>(p->ms_pos.get(), p->ms_i16.get(), p->hm.get(), N, M,
-                                                                            p->n_vtiles, p->cpart.get());
-            SGB_CHECK_LAUNCH();
+            launch_sparse(c, p, false, p->hm.get(), c.stream, sp_grid);
             c.prof_end("sparse_tile_sum_kernel (corr_n)");
             c.prof_begin();
             combine_fused_kernel<<<(unsigned)((N + 255) / 256), 256, 0, c.stream>>>(p->f_rout.get(), N, p->cpart.get(), p->n_vtiles,
@@ -1046,9 +1247,7 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
             SGB_CUDA(cudaStreamWaitEvent(side, p->ev_in, 0));
         }
         c.prof_begin();
-        sparse_tile_sum_kernel<<<sp_grid, kSpThreads, kSpSmem, side>>>(p->mv_pos.get(), p->mv_i16.get(), b, M, N,
-                                                                                p->n_stiles, p->upart.get());
-        SGB_CHECK_LAUNCH();
+        launch_sparse(c, p, true, b, side, sp_grid);
         c.prof_end("sparse_tile_sum_kernel (U_j)");
         if (fork) SGB_CUDA(cudaEventRecord(p->ev_u, side));
         c.prof_begin();
@@ -1082,9 +1281,7 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
         SGB_CHECK_LAUNCH();
         c.prof_end("imma_finalize+digits_e");
         c.prof_begin();
-        sparse_tile_sum_kernel<<<sp_grid, kSpThreads, kSpSmem, side>>>(p->ms_pos.get(), p->ms_i16.get(), p->hm.get(), N,
-                                                                                M, p->n_vtiles, p->cpart.get());
-        SGB_CHECK_LAUNCH();
+        launch_sparse(c, p, false, p->hm.get(), side, sp_grid);
         c.prof_end("sparse_tile_sum_kernel (corr_n)");
         if (fork) SGB_CUDA(cudaEventRecord(p->ev_corr, side));
         c.prof_begin();
