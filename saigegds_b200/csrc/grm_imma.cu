@@ -554,7 +554,11 @@ __global__ void ell_len_kernel(const int64_t *__restrict__ pos, int64_t R, int64
     }
     len32[i] = mx * 32;
 }
-// one warp per (tile, group): lane <-> row
+// one warp per (tile, group): lane <-> row.  The order of a row's entries is free, and the gather from the shared-memory vector
+// tile is what bounds the kernel (a random 8-byte gather costs ~6 shared-memory wavefronts per warp: two half-warps x ~3
+// lanes on the fullest of the 16 eight-byte banks).  Entries are therefore placed so that at step k lane l reads bank
+// (k + l) mod 16 whenever the row has such an entry -- distinct banks within each half-warp; entries that find their
+// preferred steps taken go to the last free step, the rest of the column is padding (one address: a broadcast).
 __global__ void ell_fill_kernel(const int64_t *__restrict__ pos, const uint16_t *__restrict__ i16, int64_t R, int64_t G, int n_tiles,
                                 const int64_t *__restrict__ gstart, uint16_t *__restrict__ ell) {
     const int lane = threadIdx.x & 31;
@@ -564,12 +568,26 @@ __global__ void ell_fill_kernel(const int64_t *__restrict__ pos, const uint16_t 
     const int64_t s = gstart[i], len = (gstart[i + 1] - s) >> 5;
     int64_t p0 = 0, mylen = 0;
     if (row < R) { p0 = pos[t * R + row]; mylen = pos[t * R + row + 1] - p0; }
-    for (int64_t k = 0; k < len; k++) ell[s + k * 32 + lane] = (k < mylen) ? i16[p0 + k] : (uint16_t)kSpTile;
+    uint16_t *col = ell + s + lane;                          // this row's column: col[k * 32]
+    for (int64_t k = 0; k < len; k++) col[k * 32] = 0xFFFFu;  // free
+    int64_t last_free = len - 1;
+    for (int64_t e = 0; e < mylen; e++) {
+        const uint16_t v = i16[p0 + e];
+        int64_t k = ((int)(v & 15) - lane) & 15;
+        while (k < len && col[k * 32] != 0xFFFFu) k += 16;
+        if (k >= len) {
+            while (col[last_free * 32] != 0xFFFFu) last_free--;
+            k = last_free;
+        }
+        col[k * 32] = v;
+    }
+    for (int64_t k = 0; k < len; k++)
+        if (col[k * 32] == 0xFFFFu) col[k * 32] = (uint16_t)kSpTile;
 }
 
 __global__ void __launch_bounds__(kEllThreads) sparse_ell_sum_kernel(const int64_t *__restrict__ gstart, const uint16_t *__restrict__ ell,
                                                                      const double *__restrict__ vec, int64_t R, int64_t C, int64_t G,
-                                                                     int n_tiles, double *__restrict__ part) {
+                                                                     int n_tiles, double *__restrict__ part, int ablate) {
     extern __shared__ __align__(16) uint8_t smem_sp[];
     double *sv = reinterpret_cast<double *>(smem_sp);
     uint16_t *sidx = reinterpret_cast<uint16_t *>(smem_sp + kEllSv * 8);
@@ -589,15 +607,18 @@ __global__ void __launch_bounds__(kEllThreads) sparse_ell_sum_kernel(const int64
         lo = t * G + chunk * 32;
         hi = t * G + min(G, (chunk + 1) * 32);
     };
-    if (threadIdx.x == 0 && (int64_t)blockIdx.x < n_work) {
+    // every CTA walks a contiguous range of the tile-major work list: the vector tile is reloaded only when the tile changes
+    const int64_t w_begin = n_work * blockIdx.x / gridDim.x, w_end = n_work * (blockIdx.x + 1) / gridDim.x;
+    if (threadIdx.x == 0 && w_begin < w_end) {
         int64_t lo, hi;
-        item_range(blockIdx.x, lo, hi);
+        item_range(w_begin, lo, hi);
         s_bounds[0][0] = gstart[lo];
         s_bounds[0][1] = gstart[hi];
     }
+    int cur_tile = -1;
     if (threadIdx.x < 8) sv[kSpTile + threadIdx.x] = 0.0;                                 // the zero slot
     int it = 0;
-    for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x, it++) {
+    for (int64_t w = w_begin; w < w_end; w++, it++) {
         const int t = (int)(w / n_chunks);
         const int64_t chunk = w % n_chunks;
         const int64_t c0 = (int64_t)t * kSpTile;
@@ -610,25 +631,28 @@ __global__ void __launch_bounds__(kEllThreads) sparse_ell_sum_kernel(const int64
         // the index block (one bulk copy each, completion counted on an mbarrier; per-thread cp.async only where the tile is
         // ragged or the vector is not 16-byte aligned)
         for (int i = threadIdx.x; i <= ng; i += kEllThreads) cp_async8(sgs + i, gp + i);
+        const bool new_tile = t != cur_tile;
+        cur_tile = t;
         const int ncol = (int)min((int64_t)kSpTile, C - c0);
-        const bool sv_bulk = ((ncol & 1) == 0) && ((reinterpret_cast<uintptr_t>(vec + c0) & 15) == 0);
-        if (!sv_bulk)
+        const bool sv_bulk = new_tile && ((ncol & 1) == 0) && ((reinterpret_cast<uintptr_t>(vec + c0) & 15) == 0);
+        if (new_tile && !sv_bulk)
             for (int i = threadIdx.x; i < ncol; i += kEllThreads) cp_async8(sv + i, vec + c0 + i);
-        for (int i = ncol + threadIdx.x; i < kSpTile; i += kEllThreads) sv[i] = 0.0;
+        if (new_tile)
+            for (int i = ncol + threadIdx.x; i < kSpTile; i += kEllThreads) sv[i] = 0.0;
         {
             const int64_t pe = min(e1, e0 + kEllCap);
             if (threadIdx.x == 0) {
                 const unsigned nb_idx = (unsigned)((pe - e0) * 2), nb_sv = sv_bulk ? (unsigned)ncol * 8u : 0u;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic reads/writes of the buffers
-                sp_mbar_expect_tx(&s_bar, nb_idx + nb_sv);
+                sp_mbar_expect_tx(&s_bar, ((ablate & 2) ? 0u : nb_idx) + nb_sv);
                 if (nb_sv) sp_bulk_g2s(sv, vec + c0, nb_sv, &s_bar);
-                if (nb_idx) sp_bulk_g2s(sidx, ell + e0, nb_idx, &s_bar);
+                if (nb_idx && !(ablate & 2)) sp_bulk_g2s(sidx, ell + e0, nb_idx, &s_bar);
             }
         }
         cp_async_commit();
-        if (threadIdx.x == 0 && w + gridDim.x < n_work) {
+        if (threadIdx.x == 0 && w + 1 < w_end) {
             int64_t lo, hi;
-            item_range(w + gridDim.x, lo, hi);
+            item_range(w + 1, lo, hi);
             s_bounds[(it + 1) & 1][0] = gstart[lo];
             s_bounds[(it + 1) & 1][1] = gstart[hi];
         }
@@ -650,7 +674,7 @@ __global__ void __launch_bounds__(kEllThreads) sparse_ell_sum_kernel(const int64
 #pragma unroll
             for (int k = 0; k < 2; k++) {
                 const int gi = warp + 16 * k;
-                if (gi < ng) {
+                if (gi < ng && !(ablate & 1)) {
                     const int lo = (int)(max(sgs[gi], pc) - pc), hi = (int)(min(sgs[gi + 1], pe) - pc);
                     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
                     int i = lo + lane;
@@ -972,7 +996,7 @@ void launch_sparse(Context &c, ImmaPlan *p, bool by_variant, const double *vec, 
     } else {
         sparse_ell_sum_kernel<<<grid, kEllThreads, kEllSmem, st>>>((by_variant ? p->mv_gstart : p->ms_gstart).get(),
                                                                   (by_variant ? p->mv_ell : p->ms_ell).get(), vec, R, C, (R + 31) / 32, nt,
-                                                                  part);
+                                                                  part, getenv("SGB_SPARSE_ABLATE") ? atoi(getenv("SGB_SPARSE_ABLATE")) : 0);
     }
     SGB_CHECK_LAUNCH();
 }
