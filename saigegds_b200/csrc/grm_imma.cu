@@ -540,7 +540,7 @@ constexpr int kEllRows = 1024;                    // rows per work item = 32 gro
 constexpr int kEllThreads = 512;                  // 16 warps x 2 groups
 constexpr int kEllCap = 36864;                    // index entries staged per piece (72 KB); an item holds ~1024 x 30 at 0.5 % missing
 constexpr int kEllSv = kSpTile + 8;               // vector tile + the zero slot (padded to 64 bytes)
-constexpr int kEllSmem = kEllSv * 8 + kEllCap * 2 + 40 * 8;
+constexpr int kEllSmem = kEllSv * 8 + 2 * kEllCap * 2 + 2 * 40 * 8;   // vector tile + two index stages + two sets of group starts
 
 // len32[t * G + g] = 32 * (longest row of group g in tile t); pos = the tile-major CSR starts
 __global__ void ell_len_kernel(const int64_t *__restrict__ pos, int64_t R, int64_t G, int n_tiles, int64_t *__restrict__ len32) {
@@ -585,96 +585,103 @@ __global__ void ell_fill_kernel(const int64_t *__restrict__ pos, const uint16_t 
         if (col[k * 32] == 0xFFFFu) col[k * 32] = (uint16_t)kSpTile;
 }
 
+// Persistent, one CTA per SM, two index stages: while the warps gather item i out of one stage, the bulk copy of item i + 1
+// is already in flight into the other (an item = 32 groups = 1024 rows of one tile; a CTA walks a contiguous range of the
+// tile-major item list, so the vector tile is reloaded only when the tile changes).  G is even and every block start a multiple
+// of 32 entries, so the group starts and the index block are 16-byte aligned bulk copies counted on one mbarrier per stage.
 __global__ void __launch_bounds__(kEllThreads) sparse_ell_sum_kernel(const int64_t *__restrict__ gstart, const uint16_t *__restrict__ ell,
                                                                      const double *__restrict__ vec, int64_t R, int64_t C, int64_t G,
-                                                                     int n_tiles, double *__restrict__ part, int ablate) {
+                                                                     int n_tiles, double *__restrict__ part) {
     extern __shared__ __align__(16) uint8_t smem_sp[];
     double *sv = reinterpret_cast<double *>(smem_sp);
-    uint16_t *sidx = reinterpret_cast<uint16_t *>(smem_sp + kEllSv * 8);
-    int64_t *sgs = reinterpret_cast<int64_t *>(smem_sp + kEllSv * 8 + kEllCap * 2);     // 33 group starts of the item
-    __shared__ int64_t s_bounds[2][2];
-    __shared__ unsigned long long s_bar;
-    unsigned bar_phase = 0;
+    uint16_t *sidx0 = reinterpret_cast<uint16_t *>(smem_sp + kEllSv * 8);
+    int64_t *sgs0 = reinterpret_cast<int64_t *>(smem_sp + kEllSv * 8 + 2 * kEllCap * 2);          // 2 x 40 group starts
+    __shared__ unsigned long long s_bar[2];
+    unsigned ph[2] = {0, 0};
     if (threadIdx.x == 0) {
-        sp_mbar_init(&s_bar, 1);
+        sp_mbar_init(&s_bar[0], 1);
+        sp_mbar_init(&s_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n_chunks = (G + 31) / 32;
     const int64_t n_work = n_chunks * n_tiles;
-    auto item_range = [&](int64_t w, int64_t &lo, int64_t &hi) {
-        const int64_t t = w / n_chunks, chunk = w % n_chunks;
-        lo = t * G + chunk * 32;
-        hi = t * G + min(G, (chunk + 1) * 32);
-    };
-    // every CTA walks a contiguous range of the tile-major work list: the vector tile is reloaded only when the tile changes
     const int64_t w_begin = n_work * blockIdx.x / gridDim.x, w_end = n_work * (blockIdx.x + 1) / gridDim.x;
-    if (threadIdx.x == 0 && w_begin < w_end) {
-        int64_t lo, hi;
-        item_range(w_begin, lo, hi);
-        s_bounds[0][0] = gstart[lo];
-        s_bounds[0][1] = gstart[hi];
-    }
-    int cur_tile = -1;
     if (threadIdx.x < 8) sv[kSpTile + threadIdx.x] = 0.0;                                 // the zero slot
+    // thread 0 only: index range of an item (two global loads; fetched one item before they are needed)
+    auto bounds = [&](int64_t w, int64_t &e0, int64_t &e1) {
+        const int64_t t = w / n_chunks, chunk = w % n_chunks;
+        e0 = gstart[t * G + chunk * 32];
+        e1 = gstart[t * G + min(G, (chunk + 1) * 32)];
+    };
+    // thread 0 only: request item w into `stage` (group starts + first piece of the index block [+ the vector tile])
+    auto issue = [&](int64_t w, int stage, int64_t e0, int64_t e1, bool with_sv) {
+        const int64_t t = w / n_chunks, chunk = w % n_chunks, g0 = chunk * 32, c0 = t * kSpTile;
+        const int ng = (int)(min(G, g0 + 32) - g0);
+        const unsigned nb_gs = (unsigned)(((ng + 2) & ~1) * 8);
+        const unsigned nb_idx = (unsigned)(min(e1 - e0, (int64_t)kEllCap) * 2);
+        const int ncol = (int)min((int64_t)kSpTile, C - c0);
+        const unsigned nb_sv = with_sv ? (unsigned)ncol * 8u : 0u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // earlier generic accesses of the stage
+        sp_mbar_expect_tx(&s_bar[stage], nb_gs + nb_idx + nb_sv);
+        sp_bulk_g2s(sgs0 + stage * 40, gstart + t * G + g0, nb_gs, &s_bar[stage]);
+        if (nb_idx) sp_bulk_g2s(sidx0 + (size_t)stage * kEllCap, ell + e0, nb_idx, &s_bar[stage]);
+        if (nb_sv) sp_bulk_g2s(sv, vec + c0, nb_sv, &s_bar[stage]);
+    };
+    int64_t nx0 = 0, nx1 = 0;            // thread 0: bounds of the item that will be requested next
+    if (threadIdx.x == 0 && w_begin < w_end) bounds(w_begin, nx0, nx1);
+    int cur_tile = -1;
     int it = 0;
     for (int64_t w = w_begin; w < w_end; w++, it++) {
+        const int stage = it & 1;
         const int t = (int)(w / n_chunks);
-        const int64_t chunk = w % n_chunks;
-        const int64_t c0 = (int64_t)t * kSpTile;
-        const int64_t g0 = chunk * 32;
+        const int64_t chunk = w % n_chunks, g0 = chunk * 32, c0 = (int64_t)t * kSpTile;
         const int ng = (int)(min(G, g0 + 32) - g0);
-        const int64_t *gp = gstart + (size_t)t * G + g0;
-        __syncthreads();                                   // previous item consumed; s_bounds[it & 1] visible
-        const int64_t e0 = s_bounds[it & 1][0], e1 = s_bounds[it & 1][1];
-        // everything the item needs in three requests: the 33 group starts (cp.async), the vector tile and the first piece of
-        // the index block (one bulk copy each, completion counted on an mbarrier; per-thread cp.async only where the tile is
-        // ragged or the vector is not 16-byte aligned)
-        for (int i = threadIdx.x; i <= ng; i += kEllThreads) cp_async8(sgs + i, gp + i);
         const bool new_tile = t != cur_tile;
         cur_tile = t;
-        const int ncol = (int)min((int64_t)kSpTile, C - c0);
-        const bool sv_bulk = new_tile && ((ncol & 1) == 0) && ((reinterpret_cast<uintptr_t>(vec + c0) & 15) == 0);
-        if (new_tile && !sv_bulk)
-            for (int i = threadIdx.x; i < ncol; i += kEllThreads) cp_async8(sv + i, vec + c0 + i);
-        if (new_tile)
+        __syncthreads();                 // item w - 1 fully consumed: its stage and (on a tile change) the vector tile are free
+        if (new_tile) {
+            // not requested ahead: the vector tile has to change first
+            const int ncol = (int)min((int64_t)kSpTile, C - c0);
+            const bool sv_bulk = ((ncol & 1) == 0) && ((reinterpret_cast<uintptr_t>(vec + c0) & 15) == 0);
+            if (!sv_bulk)
+                for (int i = threadIdx.x; i < ncol; i += kEllThreads) cp_async8(sv + i, vec + c0 + i);
             for (int i = ncol + threadIdx.x; i < kSpTile; i += kEllThreads) sv[i] = 0.0;
-        {
-            const int64_t pe = min(e1, e0 + kEllCap);
+            cp_async_commit();
             if (threadIdx.x == 0) {
-                const unsigned nb_idx = (unsigned)((pe - e0) * 2), nb_sv = sv_bulk ? (unsigned)ncol * 8u : 0u;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic reads/writes of the buffers
-                sp_mbar_expect_tx(&s_bar, ((ablate & 2) ? 0u : nb_idx) + nb_sv);
-                if (nb_sv) sp_bulk_g2s(sv, vec + c0, nb_sv, &s_bar);
-                if (nb_idx && !(ablate & 2)) sp_bulk_g2s(sidx, ell + e0, nb_idx, &s_bar);
+                issue(w, stage, nx0, nx1, sv_bulk);
+                if (w + 1 < w_end) bounds(w + 1, nx0, nx1);
             }
+            cp_async_wait<0>();
         }
-        cp_async_commit();
-        if (threadIdx.x == 0 && w + 1 < w_end) {
-            int64_t lo, hi;
-            item_range(w + 1, lo, hi);
-            s_bounds[(it + 1) & 1][0] = gstart[lo];
-            s_bounds[(it + 1) & 1][1] = gstart[hi];
+        // request item w + 1 (same tile) into the other stage before touching item w
+        if (threadIdx.x == 0 && w + 1 < w_end && (int)((w + 1) / n_chunks) == t) {
+            issue(w + 1, stage ^ 1, nx0, nx1, false);
+            if (w + 2 < w_end) bounds(w + 2, nx0, nx1);
         }
+        sp_mbar_wait(&s_bar[stage], ph[stage]);
+        ph[stage] ^= 1;
+        if (new_tile) __syncthreads();   // cp.async / plain stores of the vector tile by other threads
+        const uint16_t *sidx = sidx0 + (size_t)stage * kEllCap;
+        const int64_t *sgs = sgs0 + stage * 40;
+        const int64_t e0 = sgs[0], e1 = sgs[ng];
         double acc[2] = {0, 0};
-        for (int64_t pc = e0; pc < e1 || pc == e0; pc += kEllCap) {     // almost always a single piece
+        for (int64_t pc = e0;; pc += kEllCap) {                           // almost always a single piece
             const int64_t pe = min(e1, pc + kEllCap);
             if (pc != e0) {
                 __syncthreads();
                 if (threadIdx.x == 0) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    sp_mbar_expect_tx(&s_bar, (unsigned)((pe - pc) * 2));
-                    sp_bulk_g2s(sidx, ell + pc, (unsigned)((pe - pc) * 2), &s_bar);
+                    sp_mbar_expect_tx(&s_bar[stage], (unsigned)((pe - pc) * 2));
+                    sp_bulk_g2s(sidx0 + (size_t)stage * kEllCap, ell + pc, (unsigned)((pe - pc) * 2), &s_bar[stage]);
                 }
+                sp_mbar_wait(&s_bar[stage], ph[stage]);
+                ph[stage] ^= 1;
             }
-            cp_async_wait<0>();
-            sp_mbar_wait(&s_bar, bar_phase);
-            bar_phase ^= 1;
-            __syncthreads();
 #pragma unroll
             for (int k = 0; k < 2; k++) {
                 const int gi = warp + 16 * k;
-                if (gi < ng && !(ablate & 1)) {
+                if (gi < ng) {
                     const int lo = (int)(max(sgs[gi], pc) - pc), hi = (int)(min(sgs[gi + 1], pe) - pc);
                     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
                     int i = lo + lane;
@@ -685,7 +692,7 @@ __global__ void __launch_bounds__(kEllThreads) sparse_ell_sum_kernel(const int64
                     acc[k] += (s0 + s1) + (s2 + s3);
                 }
             }
-            if (e1 <= e0) break;
+            if (pe >= e1) break;
         }
 #pragma unroll
         for (int k = 0; k < 2; k++) {
@@ -994,9 +1001,9 @@ void launch_sparse(Context &c, ImmaPlan *p, bool by_variant, const double *vec, 
         sparse_tile_sum_kernel<<<grid, kSpThreads, kSpSmem, st>>>((by_variant ? p->mv_pos : p->ms_pos).get(),
                                                                   (by_variant ? p->mv_i16 : p->ms_i16).get(), vec, R, C, nt, part);
     } else {
-        sparse_ell_sum_kernel<<<grid, kEllThreads, kEllSmem, st>>>((by_variant ? p->mv_gstart : p->ms_gstart).get(),
-                                                                  (by_variant ? p->mv_ell : p->ms_ell).get(), vec, R, C, (R + 31) / 32, nt,
-                                                                  part, getenv("SGB_SPARSE_ABLATE") ? atoi(getenv("SGB_SPARSE_ABLATE")) : 0);
+        sparse_ell_sum_kernel<<<c.sm_count, kEllThreads, kEllSmem, st>>>((by_variant ? p->mv_gstart : p->ms_gstart).get(),
+                                                                  (by_variant ? p->mv_ell : p->ms_ell).get(), vec, R, C, 2 * ((R + 63) / 64), nt,
+                                                                  part);
     }
     SGB_CHECK_LAUNCH();
 }
@@ -1081,8 +1088,8 @@ void imma_prepare(Context &c) {
         c.sync();
         auto to_ell = [&](const DevBuf<int64_t> &pos, const DevBuf<uint16_t> &i16, int64_t R, int nt, DevBuf<int64_t> &gstart,
                           DevBuf<uint16_t> &ell) {
-            const int64_t G = (R + 31) / 32, cells = G * nt;
-            gstart.ensure((size_t)cells + 1);
+            const int64_t G = 2 * ((R + 63) / 64), cells = G * nt;   // even: 16-byte aligned group-start rows
+            gstart.ensure((size_t)cells + 4);
             SGB_CUDA(cudaMemsetAsync(gstart.get() + cells, 0, sizeof(int64_t), c.stream));
             ell_len_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, c.stream>>>(pos.get(), R, G, nt, gstart.get());
             SGB_CHECK_LAUNCH();
