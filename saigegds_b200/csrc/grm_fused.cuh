@@ -28,8 +28,14 @@
 
 constexpr int kFV = 32;                 // variants per tile
 constexpr int kFComputeWarps = 8;
-constexpr int kFNFin = 2;               // finaliser warps
-constexpr int kFWarps = kFComputeWarps + 2 + kFNFin;
+#ifndef SGB_FUSED_NFIN
+#define SGB_FUSED_NFIN 2
+#endif
+constexpr int kFNFin = SGB_FUSED_NFIN;  // finaliser warps (tiles round-robin).  One tile costs a finaliser ~2 us (a poll is 64 scattered L2
+                                        // loads and returns with the slowest of them); four of them were measured much slower (5.0 ms):
+                                        // more pollers on the limb lines slow the reductions themselves
+constexpr int kFWarps = (kFNFin <= 2) ? 12 : 16;   // compute + loader + publisher + finalisers (+ idle: setmaxnreg works on groups of four)
+static_assert(kFComputeWarps + 2 + kFNFin <= kFWarps, "warp roles");
 constexpr int kFThreads = kFWarps * 32;
 constexpr int kFMaxKs = 12;             // K-steps (256 samples) per CTA slice
 constexpr int kFRowBytes = kFMaxKs * 64;          // 768
@@ -113,7 +119,8 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 // register re-allocation between the warp groups (sm_90a+): the compute warps take what the service warps give up
 template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
-constexpr int kFRegsCompute = 216, kFRegsService = 72;   // 256 x 216 + 128 x 72 = 384 x 168
+// 12 warps: 256 x 216 + 128 x 72 = 384 x 168;  16 warps: 256 x 192 + 256 x 64 = 512 x 128
+constexpr int kFRegsCompute = (kFWarps == 12) ? 216 : 192, kFRegsService = (kFWarps == 12) ? 72 : 64;
 // same instruction as imma_u8s8 but not volatile: a pure register operation the scheduler may interleave freely
 __device__ __forceinline__ void imma_nv(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -212,8 +219,8 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
             red_add_u64(dst, (unsigned long long)lo + kFArrive);
             red_add_u64(dst + A.acc_stride, (unsigned long long)hi + kFArrive);
         }
-      } else {
-        // ------------------------------------------------------------------ finalisers: tiles f, f + 2, ...
+      } else if (warp < kFComputeWarps + 2 + kFNFin) {
+        // ------------------------------------------------------------------ finalisers: tiles f, f + kFNFin, ...
         const int f = warp - (kFComputeWarps + 2);
         const double unit_b = A.scal[S_UNITB], sumb = A.scal[S_SUMB], ebound = A.scal[S_FEBOUND], eunit = A.scal[S_FUNITE];
         const int esh = (int)A.scal[S_FESH];
