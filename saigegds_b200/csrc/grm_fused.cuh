@@ -236,14 +236,26 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
             const unsigned long long *src = A.acc_t + (size_t)(2 * lane) * A.acc_stride + tb;
             unsigned long long x0 = 0, x1 = 0;
             bool ok = true;
-            for (int it = 0;; it++) {
+            // Optimistic full read (64 limbs = 64 L2 lines, one per lane and limb).  While the tile is incomplete only lane 0
+            // probes (its two limbs), backing off between probes: 280 warps re-reading 64 reduction targets each were
+            // measurably slowing the reductions themselves; the full read is repeated once the probe sees all arrivals.
+            for (int it = 0;;) {
                 x0 = ld_relaxed_u64(src);
                 x1 = ld_relaxed_u64(src + A.acc_stride);
                 const bool done = ((x0 + (kFArrive >> 1)) >> 52) == want && ((x1 + (kFArrive >> 1)) >> 52) == want;
                 if (__all_sync(0xffffffffu, done)) break;
-                // back off: a spinning warp competes with two compute warps for the issue port and the integer pipe
-                __nanosleep(poll_ns);
-                if (it >= (1 << 20)) { *err = 1; ok = false; break; }
+                bool probe = false;
+                while (!probe) {
+                    __nanosleep(poll_ns);
+                    if (lane == 0) {
+                        const unsigned long long p0 = ld_relaxed_u64(src), p1 = ld_relaxed_u64(src + A.acc_stride);
+                        probe = ((p0 + (kFArrive >> 1)) >> 52) == want && ((p1 + (kFArrive >> 1)) >> 52) == want;
+                    }
+                    if (++it >= (1 << 20) || ((it & 255) == 0 && *err)) { *err = 1; ok = false; probe = true; }
+                    probe = __shfl_sync(0xffffffffu, probe ? 1 : 0, 0) != 0;
+                    ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+                }
+                if (!ok) break;
             }
             if (!ok) break;
             double ej = 0, hj = 0;

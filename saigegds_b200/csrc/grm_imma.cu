@@ -77,7 +77,7 @@ struct ImmaPlan {
     DevBuf<unsigned long long> f_acc;
     CUtensorMap f_tmap;      // packed matrix as a 2-D byte tensor [M][pitch], box 128 B x 32 rows, SWIZZLE_128B
     double f_efactor = 0;    // max_j |inv_j| sqrt(sum_n lut_j[c_nj]^2) / M_total (bound on |e_j| / |b|_2)
-    int f_poll_ns = 100;
+    int f_poll_ns = 1000;
     int f_lag = 6;           // phase B runs this many tiles behind phase A (env SGB_FUSED_LAG)
     int64_t f_acc_stride = 0;
     DevBuf<double> f_rout, f_htotal, f_u;
