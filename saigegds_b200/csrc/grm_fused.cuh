@@ -152,7 +152,8 @@ struct FusedArgs {
     double inv_mtotal;
     const double *scal;                 // S_UNITB, S_SUMB, S_FESH, S_FUNITE, S_FEBOUND
     double *hm;                         // [M] out: h_j + 3 e_j for the sparse output correction
-    double *h_total;                    // out: H = sum_j h_j
+    double *h_part;                     // out: [#CTAs] partial sums of H = sum_j h_j over the tiles a CTA owned (added in fixed order afterwards)
+    unsigned long long *edig;           // [n_tiles][32] self-validating digit blocks of e published by the tile owners (zeroed before the launch)
     double *rout;                       // [N] out: sum_j e_j c'_nj in real units (this CTA's slice)
     int *err;
 };
@@ -228,71 +229,106 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
         const unsigned long long want = (unsigned long long)n_cta;
         const unsigned poll_ns = (unsigned)A.poll_ns;
         double hsum = 0;                 // lane-wise partial of H (fixed order: tile order, then a butterfly)
-        for (int64_t tb = f; tb < T; tb += kFNFin) {
-            const int64_t j = tb * kFV + lane;
-            const int64_t jc = min(j, A.M - 1);
-            const double uj = __ldg(A.u + jc);
-            const double l0 = __ldg(A.lut + 4 * jc), l1 = __ldg(A.lut + 4 * jc + 1);
-            const unsigned long long *src = A.acc_t + (size_t)(2 * lane) * A.acc_stride + tb;
-            unsigned long long x0 = 0, x1 = 0;
-            bool ok = true;
-            // Optimistic full read (64 limbs = 64 L2 lines, one per lane and limb).  While the tile is incomplete only lane 0
-            // probes (its two limbs), backing off between probes: 280 warps re-reading 64 reduction targets each were
-            // measurably slowing the reductions themselves; the full read is repeated once the probe sees all arrivals.
-            for (int it = 0;;) {
-                x0 = ld_relaxed_u64(src);
-                x1 = ld_relaxed_u64(src + A.acc_stride);
-                const bool done = ((x0 + (kFArrive >> 1)) >> 52) == want && ((x1 + (kFArrive >> 1)) >> 52) == want;
-                if (__all_sync(0xffffffffu, done)) break;
-                bool probe = false;
-                while (!probe) {
-                    __nanosleep(poll_ns);
-                    if (lane == 0) {
-                        const unsigned long long p0 = ld_relaxed_u64(src), p1 = ld_relaxed_u64(src + A.acc_stride);
-                        probe = ((p0 + (kFArrive >> 1)) >> 52) == want && ((p1 + (kFArrive >> 1)) >> 52) == want;
+        // Tile tb is finalised by ONE CTA, its owner (tb mod #CTAs): the owner warp (first finaliser) reads the 64 limbs once
+        // they carry all arrivals, computes dot / e / hm in FP64, cuts e into digits and publishes the 256-byte digit block; the
+        // copier warp (second finaliser) of every CTA fetches the blocks in tile order.  (With every CTA finalising every tile,
+        // 140 x 64 limb reads per tile hit the very L2 lines the reductions go to, and a finaliser spent ~2 us per tile.)
+        // A published 8-byte word validates itself: every digit fits in 7 bits, so bit 7 of a byte repeats bit 6, and bit 7 of
+        // byte 0 is set instead -- a word that is still zero has not been written (the buffer is zeroed before the launch).
+        // Everything published is integer: the result does not depend on who computes it.
+        if (f == 0) {
+            for (int64_t tb = blockIdx.x; tb < T; tb += n_cta) {
+                const int64_t j = tb * kFV + lane;
+                const int64_t jc = min(j, A.M - 1);
+                const double uj = __ldg(A.u + jc);
+                const double l0 = __ldg(A.lut + 4 * jc), l1 = __ldg(A.lut + 4 * jc + 1);
+                const unsigned long long *src = A.acc_t + (size_t)(2 * lane) * A.acc_stride + tb;
+                unsigned long long x0 = 0, x1 = 0;
+                bool ok = true;
+                // optimistic full read; while the tile is incomplete only lane 0 probes (its two limbs), backing off in between
+                for (int it = 0;;) {
+                    x0 = ld_relaxed_u64(src);
+                    x1 = ld_relaxed_u64(src + A.acc_stride);
+                    const bool done = ((x0 + (kFArrive >> 1)) >> 52) == want && ((x1 + (kFArrive >> 1)) >> 52) == want;
+                    if (__all_sync(0xffffffffu, done)) break;
+                    bool probe = false;
+                    while (!probe) {
+                        __nanosleep(poll_ns);
+                        if (lane == 0) {
+                            const unsigned long long p0 = ld_relaxed_u64(src), p1 = ld_relaxed_u64(src + A.acc_stride);
+                            probe = ((p0 + (kFArrive >> 1)) >> 52) == want && ((p1 + (kFArrive >> 1)) >> 52) == want;
+                        }
+                        if (++it >= (1 << 20) || ((it & 255) == 0 && *err)) { *err = 1; ok = false; probe = true; }
+                        probe = __shfl_sync(0xffffffffu, probe ? 1 : 0, 0) != 0;
+                        ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
                     }
-                    if (++it >= (1 << 20) || ((it & 255) == 0 && *err)) { *err = 1; ok = false; probe = true; }
-                    probe = __shfl_sync(0xffffffffu, probe ? 1 : 0, 0) != 0;
-                    ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+                    if (!ok) break;
                 }
                 if (!ok) break;
-            }
-            if (!ok) break;
-            double ej = 0, hj = 0;
-            if (j < A.M) {
-                const long long lo = (long long)(x0 - want * kFArrive), hi = (long long)(x1 - want * kFArrive);
-                const double tsum = (double)lo + 268435456.0 * (double)hi;          // 128^4 = 2^28
-                const double Tj = (unit_b == 0 ? 0.0 : unit_b * tsum) - 3.0 * uj;
-                const double inv = l1 - l0;
-                const double dot = inv * Tj + l0 * (sumb - uj);
-                ej = dot * inv * A.inv_mtotal;
-                hj = dot * l0 * A.inv_mtotal;
-            }
-            const int e = (int)(tb % kFNE);
-            // (the slot is free: its previous tile tb-8 finished phase B before this CTA's phase A of tile tb completed,
-            //  which the arrival count of tile tb includes)
-            // digits d_l in [-64, 63] of the 56-bit fixed-point value, all at once: adding 64 to every digit position turns
-            // them into the plain base-128 digits of a non-negative number
-            const long long Bq = __double2ll_rn(scalbn((e_on && isfinite(ej)) ? ej : 0.0, esh)) + 0x1020408102040LL;   // sum_{l<7} 64 * 128^l
-            const int hh = lane >> 4, vq = (lane >> 2) & 3, beta = lane & 3;
+                double ej = 0, hj = 0;
+                if (j < A.M) {
+                    const long long lo = (long long)(x0 - want * kFArrive), hi = (long long)(x1 - want * kFArrive);
+                    const double tsum = (double)lo + 268435456.0 * (double)hi;          // 128^4 = 2^28
+                    const double Tj = (unit_b == 0 ? 0.0 : unit_b * tsum) - 3.0 * uj;
+                    const double inv = l1 - l0;
+                    const double dot = inv * Tj + l0 * (sumb - uj);
+                    ej = dot * inv * A.inv_mtotal;
+                    hj = dot * l0 * A.inv_mtotal;
+                }
+                // digits d_l in [-64, 63] of the 56-bit fixed-point value, all at once: adding 64 to every digit position
+                // turns them into the plain base-128 digits of a non-negative number.  Lane <-> variant here; the 8-byte word
+                // w of the block holds digit plane w >> 2 of the variants 16 hh + 4 (w & 3) + beta (bytes hh * 4 + beta), so
+                // the block is transposed through the warp with shuffles.
+                const long long Bq = __double2ll_rn(scalbn((e_on && isfinite(ej)) ? ej : 0.0, esh)) + 0x1020408102040LL;   // sum_{l<7} 64 * 128^l
+                unsigned long long word = 0;
+                const int pl = lane >> 2, vq = lane & 3;                               // this lane assembles word `lane`
 #pragma unroll
-            for (int l = 0; l < 8; l++) {
-                const int dl = (l < 7) ? ((int)((Bq >> (7 * l)) & 127) - 64) : (int)(Bq >> 49);
-                S.efrag[e][(l * 4 + vq) * 8 + hh * 4 + beta] = (unsigned char)(int8_t)dl;
+                for (int by = 0; by < 8; by++) {
+                    const int srcl = (by >> 2) * 16 + vq * 4 + (by & 3);               // variant whose digit goes into byte `by`
+                    const long long Bs = __shfl_sync(0xffffffffu, Bq, srcl);
+                    const int dl = (pl < 7) ? ((int)((Bs >> (7 * pl)) & 127) - 64) : (int)(Bs >> 49);
+                    word |= (unsigned long long)(unsigned)(dl & 0xFF) << (8 * by);
+                }
+                word |= 0x80ull;                                                       // valid
+                asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(A.edig + (size_t)tb * 32 + lane), "l"(word) : "memory");
+                // off the critical path: H, the output-correction weights, the sanity check of the bound
+                hsum += hj;
+                if (j < A.M) {
+                    A.hm[j] = hj + 3.0 * ej;
+                    if (e_on && fabs(ej) > ebound) *err = 2;      // the a-priori bound must hold; fail loudly if it ever does not
+                }
             }
-            __syncwarp();
-            __threadfence_block();
-            if (lane == 0) mbar_arrive(&S.ready[e]);
-            // off the critical path: H, the output-correction weights, the sanity check of the bound
-            hsum += hj;
-            if (j < A.M) {
-                if ((int)(tb % n_cta) == (int)blockIdx.x) A.hm[j] = hj + 3.0 * ej;
-                if (e_on && fabs(ej) > ebound) *err = 2;      // the a-priori bound must hold; fail loudly if it ever does not
+        } else {
+            // ---- copier: digit blocks in tile order, four tiles' words in flight
+            unsigned long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+            const unsigned long long *gd = A.edig + lane;
+            if (0 < T) w0 = ld_relaxed_u64(gd);
+            if (1 < T) w1 = ld_relaxed_u64(gd + 32);
+            if (2 < T) w2 = ld_relaxed_u64(gd + 64);
+            if (3 < T) w3 = ld_relaxed_u64(gd + 96);
+            bool ok = true;
+            for (int64_t tb = 0; tb < T; tb++) {
+                for (int it = 0; !__all_sync(0xffffffffu, w0 != 0); it++) {
+                    __nanosleep(poll_ns);
+                    if (it >= (1 << 20) || ((it & 255) == 255 && *err)) { *err = 1; ok = false; break; }
+                    if (w0 == 0) w0 = ld_relaxed_u64(gd + tb * 32);
+                }
+                if (!ok) break;
+                const int e = (int)(tb % kFNE);
+                // (the e-digit slot is free: its previous tile finished phase B before this CTA's phase A of tile tb completed,
+                //  which the arrival count of tile tb includes)
+                const unsigned long long dg = (w0 & ~0x80ull) | ((w0 & 0x40ull) << 1);     // bit 7 of byte 0 back to the sign
+                *reinterpret_cast<unsigned long long *>(&S.efrag[e][lane * 8]) = dg;
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) mbar_arrive(&S.ready[e]);
+                w0 = w1; w1 = w2; w2 = w3;
+                w3 = (tb + 4 < T) ? ld_relaxed_u64(gd + (tb + 4) * 32) : 0;
             }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) hsum += __shfl_xor_sync(0xffffffffu, hsum, o);
-        if (lane == 0) S.hsum[f] = hsum;
+        if (lane == 0 && f == 0) A.h_part[blockIdx.x] = hsum;        // partial H of the tiles this CTA owned
       }
     } else {
         // ------------------------------------------------------------------ compute warps
@@ -477,11 +513,6 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
         flush();
     }
     __syncthreads();
-    if (blockIdx.x == 0 && tid == 0) {
-        double h = 0;
-        for (int f = 0; f < kFNFin; f++) h += S.hsum[f];
-        *A.h_total = h;
-    }
 }
 
 // digits of b for the fused kernel: [half-step (128 samples)][lane = l*4+tq][t0][h][beta]
@@ -508,6 +539,15 @@ __global__ void sum_tiles_kernel(const double *__restrict__ part, int n_tiles, i
     double s = 0;
     for (int t = 0; t < n_tiles; t++) s += part[(size_t)t * R + r];
     out[r] = s;
+}
+
+// H = sum of the finalisers' partials in a fixed order
+__global__ void sum_h_kernel(const double *__restrict__ part, int n, double *__restrict__ h_total) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double h = 0;
+        for (int i = 0; i < n; i++) h += part[i];
+        *h_total = h;
+    }
 }
 
 // out_n = R_n (real units) + H - corr_n

@@ -77,10 +77,11 @@ struct ImmaPlan {
     DevBuf<unsigned long long> f_acc;
     CUtensorMap f_tmap;      // packed matrix as a 2-D byte tensor [M][pitch], box 128 B x 32 rows, SWIZZLE_128B
     double f_efactor = 0;    // max_j |inv_j| sqrt(sum_n lut_j[c_nj]^2) / M_total (bound on |e_j| / |b|_2)
-    int f_poll_ns = 1000;
+    int f_poll_ns = 30;
     int f_lag = 6;           // phase B runs this many tiles behind phase A (env SGB_FUSED_LAG)
     int64_t f_acc_stride = 0;
-    DevBuf<double> f_rout, f_htotal, f_u;
+    DevBuf<double> f_rout, f_htotal, f_u, f_hpart;
+    DevBuf<unsigned long long> f_edig;   // [f_tiles][32] digit blocks of e published by the tile owners
     DevBuf<int> f_err;
     PinBuf<int> f_herr;
     DevBuf<double> upart;    // [n_stiles][M] U_j per sample tile
@@ -1146,6 +1147,8 @@ void imma_prepare(Context &c) {
                     p->f_rout.ensure(N);
                     p->f_u.ensure(M);
                     p->f_htotal.ensure(1);
+                    p->f_hpart.ensure((size_t)p->f_grid);
+                    p->f_edig.ensure((size_t)p->f_tiles * 32 + 128);
                     p->f_err.ensure(1);
                     p->f_herr.ensure(1);
                     *p->f_herr.p = 0;
@@ -1234,6 +1237,7 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
                                                                                           p->dfrag128.get());
             SGB_CHECK_LAUNCH();
             SGB_CUDA(cudaMemsetAsync(p->f_acc.get(), 0, sizeof(unsigned long long) * p->f_acc_stride * kFV * 2, side));
+            SGB_CUDA(cudaMemsetAsync(p->f_edig.get(), 0, sizeof(unsigned long long) * (p->f_tiles * 32 + 128), side));
             c.prof_end("imma_prep_b (absmax+digits+memset)");
             if (fork) SGB_CUDA(cudaEventRecord(p->ev_u, side));
             c.prof_begin();
@@ -1249,11 +1253,13 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
             fa.ks_per_cta = p->f_ks_per_cta; fa.n_tiles = p->f_tiles; fa.dfrag128 = p->dfrag128.get();
             fa.acc_t = p->f_acc.get(); fa.acc_stride = p->f_acc_stride; fa.u = p->f_u.get(); fa.poll_ns = p->f_poll_ns; fa.lag = p->f_lag;
             fa.lut = c.lut.get(); fa.inv_mtotal = 1.0 / (double)c.M_total; fa.scal = p->scal.get(); fa.hm = p->hm.get();
-            fa.h_total = p->f_htotal.get(); fa.rout = p->f_rout.get(); fa.err = p->f_err.get();
+            fa.h_part = p->f_hpart.get(); fa.edig = p->f_edig.get(); fa.rout = p->f_rout.get(); fa.err = p->f_err.get();
             void *kargs[] = {&p->f_tmap, &fa};
             c.prof_begin();
             SGB_CUDA(cudaLaunchCooperativeKernel((const void *)imma_fused_kernel, dim3(p->f_grid), dim3(kFThreads), kargs,
                                                  (size_t)kFSmemBytes, c.stream));
+            sum_h_kernel<<<1, 32, 0, c.stream>>>(p->f_hpart.get(), p->f_grid, p->f_htotal.get());
+            SGB_CHECK_LAUNCH();
             c.prof_end("imma_fused_kernel");
             SGB_CUDA(cudaMemcpyAsync(p->f_herr.p, p->f_err.get(), sizeof(int), cudaMemcpyDeviceToHost, c.stream));
             c.prof_begin();
@@ -1264,7 +1270,7 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
                                                                                   p->f_htotal.get(), out);
             SGB_CHECK_LAUNCH();
             c.prof_end("combine_kernel");
-            c.stats.n_kernel_launches += 7;
+            c.stats.n_kernel_launches += 8;
             c.stats.n_product_launches += 1;
         }
         return;
