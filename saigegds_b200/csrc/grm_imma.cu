@@ -68,7 +68,7 @@ struct ImmaPlan {
     DevBuf<uint16_t> mv_ell, ms_ell;
     bool use_csr = false;    // env SGB_SPARSE_CSR: the older row-per-thread kernel (comparison only)
     int n_stiles = 0, n_vtiles = 0;
-    int opt_fork = 1, opt_grid_mult = 2, opt_stages = 3;   // tuning knobs (env: SGB_SPARSE_FORK, SGB_SPARSE_GRID_MULT, SGB_DOTS_STAGES)
+    int opt_fork = 1, opt_fork_fused = 0, opt_grid_mult = 2, opt_stages = 3;   // tuning knobs (env: SGB_SPARSE_FORK, SGB_SPARSE_GRID_MULT, SGB_DOTS_STAGES)
     // fused single-pass kernel (grm_fused.cuh)
     bool fused_ok = false;
     int f_ks_per_cta = 0, f_grid = 0;
@@ -994,11 +994,13 @@ int pick_split(int64_t tiles, int slots, int max_split) {
 }
 
 // missing-genotype sums: rows = variants gathering b (U_j) or rows = samples gathering hm (corr_n)
-void launch_sparse(Context &c, ImmaPlan *p, bool by_variant, const double *vec, cudaStream_t st, int grid) {
+void launch_sparse(Context &c, ImmaPlan *p, bool by_variant, const double *vec, cudaStream_t st, int grid, bool beside_imma) {
     const int64_t R = by_variant ? c.M : c.N, C = by_variant ? c.N : c.M;
     const int nt = by_variant ? p->n_stiles : p->n_vtiles;
     double *part = by_variant ? p->upart.get() : p->cpart.get();
-    if (p->use_csr) {
+    // beside the two-pass tensor-core kernels the row-per-thread kernel is used: its CTAs (88 KB) fit next to two IMMA CTAs on an
+    // SM, the lane-interleaved kernel (one 180 KB CTA per SM) would serialise with them; on its own the latter is 1.6x faster
+    if (p->use_csr || beside_imma) {
         sparse_tile_sum_kernel<<<grid, kSpThreads, kSpSmem, st>>>((by_variant ? p->mv_pos : p->ms_pos).get(),
                                                                   (by_variant ? p->mv_i16 : p->ms_i16).get(), vec, R, C, nt, part);
     } else {
@@ -1105,10 +1107,7 @@ void imma_prepare(Context &c) {
         to_ell(p->mv_pos, p->mv_i16, M, p->n_stiles, p->mv_gstart, p->mv_ell);
         to_ell(p->ms_pos, p->ms_i16, N, p->n_vtiles, p->ms_gstart, p->ms_ell);
         c.sync();
-        p->use_csr = getenv("SGB_SPARSE_CSR") != nullptr;
-        if (!p->use_csr) {                    // the row-major-in-tile lists are only kept for the comparison switch
-            p->mv_pos.release(); p->mv_i16.release(); p->ms_pos.release(); p->ms_i16.release();
-        }
+        p->use_csr = getenv("SGB_SPARSE_CSR") != nullptr;   // comparison switch: the row-per-thread kernel everywhere
         SGB_CUDA(cudaFuncSetAttribute(sparse_ell_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEllSmem));
         // the row-major 32-bit lists are only needed to build the tile-major ones
         p->mv_idx.release(); p->ms_idx.release();
@@ -1193,6 +1192,7 @@ void imma_prepare(Context &c) {
             }
         }
         if (const char *e = getenv("SGB_SPARSE_FORK")) p->opt_fork = atoi(e);
+        if (const char *e = getenv("SGB_FUSED_FORK")) p->opt_fork_fused = atoi(e);
         if (const char *e = getenv("SGB_SPARSE_GRID_MULT")) p->opt_grid_mult = std::max(1, atoi(e));
         if (const char *e = getenv("SGB_DOTS_STAGES")) p->opt_stages = (atoi(e) == 4) ? 4 : 3;
         SGB_CUDA(cudaFuncSetAttribute(imma_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBStages * kBStageBytes));
@@ -1225,23 +1225,25 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
             double *out = out_all + (size_t)col * N;
             // the small preparation kernels (max|b|, |b|_2, digits of b, zeroing of the limbs) need no shared memory and run on
             // the side stream beside the sparse U_j kernel
-            const bool fork = side != c.stream;
+            // (measured inside whole fits: forking costs more in cross-stream dependencies than the ~0.05 ms it hides)
+            const bool fork = side != c.stream && p->opt_fork_fused;
             if (fork) {
                 SGB_CUDA(cudaEventRecord(p->ev_in, c.stream));
                 SGB_CUDA(cudaStreamWaitEvent(side, p->ev_in, 0));
             }
             c.prof_begin();
-            absmax_sum_kernel<<<G, 256, 0, side>>>(b, N, p->red.get(), p->counter.get(), p->scal.get(), p->f_efactor);
+            cudaStream_t pst = fork ? side : c.stream;
+            absmax_sum_kernel<<<G, 256, 0, pst>>>(b, N, p->red.get(), p->counter.get(), p->scal.get(), p->f_efactor);
             SGB_CHECK_LAUNCH();
-            digits_b128_kernel<<<(unsigned)((p->ksteps * 256 + 255) / 256), 256, 0, side>>>(b, N, p->ksteps * 256, p->scal.get(),
+            digits_b128_kernel<<<(unsigned)((p->ksteps * 256 + 255) / 256), 256, 0, pst>>>(b, N, p->ksteps * 256, p->scal.get(),
                                                                                           p->dfrag128.get());
             SGB_CHECK_LAUNCH();
-            SGB_CUDA(cudaMemsetAsync(p->f_acc.get(), 0, sizeof(unsigned long long) * p->f_acc_stride * kFV * 2, side));
-            SGB_CUDA(cudaMemsetAsync(p->f_edig.get(), 0, sizeof(unsigned long long) * (p->f_tiles * 32 + 128), side));
+            SGB_CUDA(cudaMemsetAsync(p->f_acc.get(), 0, sizeof(unsigned long long) * p->f_acc_stride * kFV * 2, pst));
+            SGB_CUDA(cudaMemsetAsync(p->f_edig.get(), 0, sizeof(unsigned long long) * (p->f_tiles * 32 + 128), pst));
             c.prof_end("imma_prep_b (absmax+digits+memset)");
             if (fork) SGB_CUDA(cudaEventRecord(p->ev_u, side));
             c.prof_begin();
-            launch_sparse(c, p, true, b, c.stream, sp_grid);
+            launch_sparse(c, p, true, b, c.stream, sp_grid, false);
             c.prof_end("sparse_tile_sum_kernel (U_j)");
             c.prof_begin();
             sum_tiles_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c.stream>>>(p->upart.get(), p->n_stiles, M, p->f_u.get());
@@ -1263,7 +1265,7 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
             c.prof_end("imma_fused_kernel");
             SGB_CUDA(cudaMemcpyAsync(p->f_herr.p, p->f_err.get(), sizeof(int), cudaMemcpyDeviceToHost, c.stream));
             c.prof_begin();
-            launch_sparse(c, p, false, p->hm.get(), c.stream, sp_grid);
+            launch_sparse(c, p, false, p->hm.get(), c.stream, sp_grid, false);
             c.prof_end("sparse_tile_sum_kernel (corr_n)");
             c.prof_begin();
             combine_fused_kernel<<<(unsigned)((N + 255) / 256), 256, 0, c.stream>>>(p->f_rout.get(), N, p->cpart.get(), p->n_vtiles,
@@ -1284,7 +1286,7 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
             SGB_CUDA(cudaStreamWaitEvent(side, p->ev_in, 0));
         }
         c.prof_begin();
-        launch_sparse(c, p, true, b, side, sp_grid);
+        launch_sparse(c, p, true, b, side, sp_grid, fork);
         c.prof_end("sparse_tile_sum_kernel (U_j)");
         if (fork) SGB_CUDA(cudaEventRecord(p->ev_u, side));
         c.prof_begin();
@@ -1318,7 +1320,7 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
         SGB_CHECK_LAUNCH();
         c.prof_end("imma_finalize+digits_e");
         c.prof_begin();
-        launch_sparse(c, p, false, p->hm.get(), side, sp_grid);
+        launch_sparse(c, p, false, p->hm.get(), side, sp_grid, fork);
         c.prof_end("sparse_tile_sum_kernel (corr_n)");
         if (fork) SGB_CUDA(cudaEventRecord(p->ev_corr, side));
         c.prof_begin();
