@@ -541,21 +541,19 @@ __global__ void sum_tiles_kernel(const double *__restrict__ part, int n_tiles, i
     out[r] = s;
 }
 
-// H = sum of the finalisers' partials in a fixed order
-__global__ void sum_h_kernel(const double *__restrict__ part, int n, double *__restrict__ h_total) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double h = 0;
-        for (int i = 0; i < n; i++) h += part[i];
-        *h_total = h;
-    }
-}
-
 // out_n = R_n (real units) + H - corr_n
 __global__ void combine_fused_kernel(const double *__restrict__ rout, int64_t N, const double *__restrict__ cpart, int n_ctiles,
-                                     const double *__restrict__ h_total, double *__restrict__ out) {
+                                     const double *__restrict__ h_part, int n_hpart, double *__restrict__ out) {
+    __shared__ double sh_h;
+    if (threadIdx.x == 0) {              // H = the owners' partial sums in a fixed order
+        double h = 0;
+        for (int i = 0; i < n_hpart; i++) h += h_part[i];
+        sh_h = h;
+    }
+    __syncthreads();
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     double corr = 0;
     for (int t = 0; t < n_ctiles; t++) corr += cpart[(size_t)t * N + n];
-    out[n] = rout[n] + *h_total - corr;
+    out[n] = rout[n] + sh_h - corr;
 }

@@ -68,7 +68,7 @@ struct ImmaPlan {
     DevBuf<uint16_t> mv_ell, ms_ell;
     bool use_csr = false;    // env SGB_SPARSE_CSR: the older row-per-thread kernel (comparison only)
     int n_stiles = 0, n_vtiles = 0;
-    int opt_fork = 1, opt_fork_fused = 0, opt_grid_mult = 2, opt_stages = 3;   // tuning knobs (env: SGB_SPARSE_FORK, SGB_SPARSE_GRID_MULT, SGB_DOTS_STAGES)
+    int opt_fork = 1, opt_fork_fused = -1, opt_grid_mult = 2, opt_stages = 3;   // tuning knobs (env: SGB_SPARSE_FORK, SGB_SPARSE_GRID_MULT, SGB_DOTS_STAGES)
     // fused single-pass kernel (grm_fused.cuh)
     bool fused_ok = false;
     int f_ks_per_cta = 0, f_grid = 0;
@@ -1225,8 +1225,9 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
             double *out = out_all + (size_t)col * N;
             // the small preparation kernels (max|b|, |b|_2, digits of b, zeroing of the limbs) need no shared memory and run on
             // the side stream beside the sparse U_j kernel
-            // (measured inside whole fits: forking costs more in cross-stream dependencies than the ~0.05 ms it hides)
-            const bool fork = side != c.stream && p->opt_fork_fused;
+            // (single right-hand side only: with many columns per call -- the fits -- the cross-stream dependencies were measured
+            //  to cost more than the ~0.03 ms they hide; env SGB_FUSED_FORK = 0 / 1 forces it off / on)
+            const bool fork = side != c.stream && (p->opt_fork_fused == 1 || (p->opt_fork_fused < 0 && k == 1));
             if (fork) {
                 SGB_CUDA(cudaEventRecord(p->ev_in, c.stream));
                 SGB_CUDA(cudaStreamWaitEvent(side, p->ev_in, 0));
@@ -1260,8 +1261,6 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
             c.prof_begin();
             SGB_CUDA(cudaLaunchCooperativeKernel((const void *)imma_fused_kernel, dim3(p->f_grid), dim3(kFThreads), kargs,
                                                  (size_t)kFSmemBytes, c.stream));
-            sum_h_kernel<<<1, 32, 0, c.stream>>>(p->f_hpart.get(), p->f_grid, p->f_htotal.get());
-            SGB_CHECK_LAUNCH();
             c.prof_end("imma_fused_kernel");
             SGB_CUDA(cudaMemcpyAsync(p->f_herr.p, p->f_err.get(), sizeof(int), cudaMemcpyDeviceToHost, c.stream));
             c.prof_begin();
@@ -1269,10 +1268,10 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
             c.prof_end("sparse_tile_sum_kernel (corr_n)");
             c.prof_begin();
             combine_fused_kernel<<<(unsigned)((N + 255) / 256), 256, 0, c.stream>>>(p->f_rout.get(), N, p->cpart.get(), p->n_vtiles,
-                                                                                  p->f_htotal.get(), out);
+                                                                                  p->f_hpart.get(), p->f_grid, out);
             SGB_CHECK_LAUNCH();
             c.prof_end("combine_kernel");
-            c.stats.n_kernel_launches += 8;
+            c.stats.n_kernel_launches += 7;
             c.stats.n_product_launches += 1;
         }
         return;
