@@ -6,15 +6,15 @@
 // dots of all CTAs are summed through exact 64-bit integer reductions in L2, and then used again for phase B
 // (apply); the int32 accumulators of phase B live in registers for the whole product.
 //
-//   compute warps 0..7 : phase A(tile s) when full[s] has completed -> per-warp partial dots into shared memory;
-//                        phase B(oldest tile) as soon as its ready[] has completed -> arrive empty[]; B is preferred, so the
-//                        distance between the two phases adapts to the cross-CTA latency (no fixed lag)
-//   loader warp 8      : wait empty -> arm full with expect_tx -> one bulk copy per row (lane <-> variant)
-//   publisher warp 9   : wait part_full[s] -> add the 8 warps' partials (lane <-> variant) -> two red.add.u64 per
+//   compute warps 0..7 : step s: wait full[s] and ready[s-lag]; phase A(tile s) and phase B(tile s-lag) issued interleaved;
+//                        arrive empty[s-lag]; per-warp partial dots of tile s into shared memory -> part_full
+//   loader warp 8      : wait empty -> arm full with expect_tx -> six 2-D TMA copies [32 variants x 128 B], SWIZZLE_128B
+//   publisher warp 9   : wait part_full -> add the 8 warps' partials (lane <-> variant) -> two red.add.u64 per
 //                        variant.  Every CTA adds 2^52 on top of its value, so a limb carries its own arrival count
 //                        in bits 52.. and needs no fence, flag or second round trip.
-//   finaliser warps 10, 11 (alternate tiles): poll the tile's limbs until all CTAs have arrived -> dot, e, hm
-//                        (lane <-> variant) -> base-128 digits of e in MMA fragment order -> ready[tile]
+//   owner warp 10      : for the tiles this CTA owns (tile mod #CTAs): read the limbs once all CTAs have arrived -> dot, e, hm
+//                        in FP64 -> base-128 digits of e in MMA fragment order -> publish the self-validating 256-byte block
+//   copier warp 11     : fetch the digit blocks of ALL tiles in order (four in flight) into the e-digit ring -> ready[tile]
 //
 // All cross-warp synchronisation is mbarrier based; there is no CTA-wide barrier in the main loop.  The fixed-point
 // exponent of e is chosen BEFORE the launch from a rigorous bound: |e_j| <= |inv_j| sqrt(sum_n lut_j[c_nj]^2) |b|_2 / M
@@ -31,9 +31,8 @@ constexpr int kFComputeWarps = 8;
 #ifndef SGB_FUSED_NFIN
 #define SGB_FUSED_NFIN 2
 #endif
-constexpr int kFNFin = SGB_FUSED_NFIN;  // finaliser warps (tiles round-robin).  One tile costs a finaliser ~2 us (a poll is 64 scattered L2
-                                        // loads and returns with the slowest of them); four of them were measured much slower (5.0 ms):
-                                        // more pollers on the limb lines slow the reductions themselves
+constexpr int kFNFin = SGB_FUSED_NFIN;  // finaliser warps: the owner warp and the copier warp
+static_assert(kFNFin == 2, "one owner warp and one copier warp");
 constexpr int kFWarps = (kFNFin <= 2) ? 12 : 16;   // compute + loader + publisher + finalisers (+ idle: setmaxnreg works on groups of four)
 static_assert(kFComputeWarps + 2 + kFNFin <= kFWarps, "warp roles");
 constexpr int kFThreads = kFWarps * 32;
@@ -52,7 +51,6 @@ constexpr unsigned long long kFArrive = 1ull << 52;   // arrival count lives abo
 
 struct FusedSmem {
     unsigned long long full[kFNBuf], empty[kFNBuf], part_full[kFNPart], part_free[kFNPart], ready[kFNE];
-    double hsum[kFNFin];
     alignas(16) int part[kFNPart][kFComputeWarps][kFV * 8];   // per-warp partial dots x 64: [variant][digit plane]
     alignas(16) unsigned char efrag[kFNE][256];
 };
