@@ -135,6 +135,29 @@ int sgb_store_2b_geno(sgb_context *ctx, const uint8_t *packed, int64_t n_samp, i
 int sgb_store_2b_geno_device(sgb_context *ctx, uint8_t *packed_device, int take_ownership, int64_t n_samp,
                              int64_t n_bytes_per_variant, int64_t n_variant_local, int64_t n_variant_total,
                              int64_t variant_offset, double *buf_std_geno, double *buf_diag_grm);
+
+/* ---- sparse genotypes: the reference's default geno.sparse=TRUE ----------------------------- */
+#define SGB_GENO_RAW 0  /* RAWSXP: one byte per sample, 0/1/2, anything else = missing */
+#define SGB_GENO_INT 1  /* INTSXP: 0/1/2, anything else (NA_integer_) = missing        */
+#define SGB_GENO_REAL 2 /* REALSXP: dosage rounded to 0/1/2, non-finite = missing     */
+/* saige_get_sparse (saige_fitnull.cpp:252-320): one variant's genotypes -> the integer vector
+ * (n1, n2, n3, indices of 1s, indices of 2s, indices of missing), 0-based, counted on the minor allele
+ * (codes are flipped 0<->2 when the coded allele is the major one, :295-303).  `out` needs n_samp + 3
+ * ints -- the buffer saige_init_sparse (:244-249) registers; *out_len receives the used length.
+ * Host only: no context, no device.  Unlike the reference it does not overwrite `geno`. */
+int sgb_get_sparse(const void *geno, int geno_type, int64_t n_samp, int32_t *out, int64_t *out_len);
+/* saige_store_sp_geno (saige_fitnull.cpp:324-388).  The R list of integer vectors arrives flattened:
+ * variant j's vector is sp_data[sp_offsets[j] .. sp_offsets[j+1]).  The lists are packed to the 2-bit layout on
+ * the host (slab-wise, pinned staging) and stored like sgb_store_2b_geno, so every later call (products, fits,
+ * variance ratio, sgb_get_geno_ds) is the same device path.  buf_std_geno receives the reference's SPARSE table
+ * (entries 1..3 relative to entry 0, :358), bit-identical; buf_diag_grm as :363-385.  Malformed vectors
+ * (counts not matching the length, index outside [0, n_samp)) -> SGB_ERR_INVALID (the reference reads out of bounds). */
+int sgb_store_sp_geno(sgb_context *ctx, const int32_t *sp_data, const int64_t *sp_offsets, int64_t n_samp,
+                      int64_t n_variant_local, int64_t n_variant_total, int64_t variant_offset,
+                      double *buf_std_geno, double *buf_diag_grm);
+/* The host packing step of sgb_store_sp_geno on its own: packed [n_variant][ceil(n_samp/4)], pad samples = 3. */
+int sgb_sparse_to_packed(const int32_t *sp_data, const int64_t *sp_offsets, int64_t n_samp, int64_t n_variant,
+                         uint8_t *packed);
 /* Integer results of the LUT pass (n_valid, sum at saige_fitnull.cpp:187-192), bit-exact. */
 int sgb_allele_counts(sgb_context *ctx, int32_t *n_valid, int32_t *sum);
 /* get_geno_ds (saige_fitnull.cpp:394-427): dosage of local variant snp_idx, missing -> NaN. */

@@ -86,6 +86,19 @@ class Oracle:
                                 C.c_int(num_thread), _p(lut), _p(diag))
         return lut.reshape(m, 4), diag
 
+    def store_sp_geno(self, sp_geno_list, n_samp: int, num_thread: int = 1):
+        """saige_store_sp_geno: sp_geno_list = list of int32 vectors (n1, n2, n3, indices) as made by get_sparse."""
+        m = len(sp_geno_list)
+        self.n, self.m = int(n_samp), int(m)
+        offsets = np.zeros(m + 1, dtype=np.int64)
+        offsets[1:] = np.cumsum([len(v) for v in sp_geno_list])
+        data = np.ascontiguousarray(np.concatenate(sp_geno_list), dtype=np.int32)
+        lut = np.empty(4 * m)
+        diag = np.empty(self.n)
+        lib().orc_store_sp_geno(self.h, _p(data, C.c_int), _p(offsets, C.c_long), C.c_long(self.n), C.c_long(m),
+                                C.c_int(num_thread), _p(lut), _p(diag))
+        return lut.reshape(m, 4), diag
+
     def allele_counts(self):
         nv = np.empty(self.m, dtype=np.int32)
         sm = np.empty(self.m, dtype=np.int32)
@@ -221,6 +234,26 @@ def score_test(model, dosage, var_ratio, maf=float("nan"), mac=10.0, missing=0.1
     res = {k: out[:, i].copy() for i, k in enumerate(names)}
     res["valid"] = valid.astype(bool)
     return res
+
+
+def get_sparse(geno, n_samp=None):
+    """saige_get_sparse (src/saige_fitnull.cpp:252-320) on one variant: uint8 codes, int32 genotypes or float64 dosages."""
+    geno = np.ascontiguousarray(geno)
+    n = len(geno) if n_samp is None else int(n_samp)
+    if n > len(geno):
+        raise ValueError("No enough genotypes.")
+    if geno.dtype == np.uint8:
+        t = 0
+    elif geno.dtype == np.int32:
+        t = 1
+    elif geno.dtype == np.float64:
+        t = 2
+    else:
+        raise ValueError("Invalid data type.")
+    out = np.empty(n + 4, dtype=np.int32)
+    lib().orc_get_sparse.restype = C.c_long
+    k = lib().orc_get_sparse(geno.ctypes.data_as(C.c_void_p), C.c_int(t), C.c_long(n), _p(out, C.c_int))
+    return out[:k].copy()
 
 
 def qnorm(p):

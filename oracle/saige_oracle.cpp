@@ -139,6 +139,9 @@ struct Oracle {
     bool verbose = false;
     std::string last_error;
     BYTE num_valid[256], num_sum[256];
+    // sparse store (saige_fitnull.cpp:236-242): per variant n1, n2, n3, then the three index runs
+    std::vector<std::vector<int>> Geno_Sparse;
+    bool sparse = false;
 
     Oracle() { init_lookup_table(); }
 
@@ -155,6 +158,7 @@ struct Oracle {
     void store_2b_geno(const BYTE *packed, size_t n_samp, size_t n_packed, size_t n_var, int nthread) {
         owned.assign(packed, packed + n_packed * n_var);
         Geno_PackedRaw = owned.data();
+        sparse = false; Geno_Sparse.clear();
         Geno_NumSamp = n_samp; Geno_PackedNumSamp = n_packed; Geno_NumVariant = n_var;
         NumThreads = nthread;
         if (NumThreads > (int)Geno_NumSamp) NumThreads = (int)Geno_NumSamp;
@@ -194,9 +198,96 @@ struct Oracle {
         for (size_t i = 0; i < n_samp; i++) buf_diag_grm[i] *= 1.0 / Geno_NumVariant;
     }
 
-    // get_geno_ds, saige_fitnull.cpp:394-427 (dense branch): missing -> NaN
+    // saige_store_sp_geno, saige_fitnull.cpp:324-388.  data/offsets: variant i's integer vector is
+    // data[offsets[i] .. offsets[i+1]) = n1, n2, n3, indices of 1s, of 2s, of missing (0-based).
+    void store_sp_geno(const int *data, const long *offsets, size_t n_samp, size_t n_var, int nthread) {
+        Geno_PackedRaw = nullptr; owned.clear(); sparse = true;
+        Geno_Sparse.resize(n_var);
+        for (size_t i = 0; i < n_var; i++) Geno_Sparse[i].assign(data + offsets[i], data + offsets[i + 1]);
+        Geno_NumSamp = n_samp; Geno_PackedNumSamp = 0; Geno_NumVariant = n_var;
+        NumThreads = nthread;
+        if (NumThreads > (int)Geno_NumSamp) NumThreads = (int)Geno_NumSamp;
+        if (NumThreads > (int)Geno_NumVariant) NumThreads = (int)Geno_NumVariant;
+        if (NumThreads < 1) NumThreads = 1;
+        buf_crossprod.assign(n_samp * (size_t)NumThreads, 0.0);
+        buf_std_geno.assign(4 * n_var, 0.0);
+        n_valid_v.assign(n_var, 0); sum_v.assign(n_var, 0);
+        // :343-361 look-up table, entries 1..3 stored relative to entry 0
+        for (size_t i = 0; i < n_var; i++) {
+            const int *pg = Geno_Sparse[i].data();
+            int n_valid = (int)Geno_NumSamp - pg[2];
+            int sum = pg[0] + 2 * pg[1];
+            n_valid_v[i] = n_valid; sum_v[i] = sum;
+            double af = double(sum) / (2 * n_valid);
+            double inv = 1 / sqrt(2 * af * (1 - af));
+            if (!std::isfinite(af) || !std::isfinite(inv)) af = inv = 0;
+            double *p = &buf_std_geno[4 * i];
+            p[0] = (0 - 2 * af) * inv; p[1] = (1 - 2 * af) * inv; p[2] = (2 - 2 * af) * inv; p[3] = 0;
+            p[1] -= p[0]; p[2] -= p[0]; p[3] -= p[0];
+        }
+        // :363-385 diag(GRM)
+        buf_diag_grm.assign(n_samp, 0.0);
+        double adj_g0 = 0, v;
+        for (size_t i = 0; i < n_var; i++) {
+            const double *p = &buf_std_geno[4 * i];
+            const int *pg = Geno_Sparse[i].data(), *ii = pg + 3;
+            double g0_2 = p[0] * p[0]; adj_g0 += g0_2;
+            v = (p[1] + p[0]) * (p[1] + p[0]) - g0_2;
+            for (int k = 0; k < pg[0]; k++) buf_diag_grm[*ii++] += v;
+            v = (p[2] + p[0]) * (p[2] + p[0]) - g0_2;
+            for (int k = 0; k < pg[1]; k++) buf_diag_grm[*ii++] += v;
+            v = (p[3] + p[0]) * (p[3] + p[0]) - g0_2;
+            for (int k = 0; k < pg[2]; k++) buf_diag_grm[*ii++] += v;
+        }
+        for (size_t i = 0; i < n_samp; i++) buf_diag_grm[i] += adj_g0;
+        for (size_t i = 0; i < n_samp; i++) buf_diag_grm[i] *= 1.0 / Geno_NumVariant;
+    }
+
+    // get_crossprod_b_grm, sparse branch, saige_fitnull.cpp:445-476 and :520-535
+    void crossprod_b_grm_sparse(const double *b, double *out_b) {
+        const size_t N = Geno_NumSamp, M = Geno_NumVariant;
+        std::fill(buf_crossprod.begin(), buf_crossprod.end(), 0.0);
+        double sum_b = 0; for (size_t n = 0; n < N; n++) sum_b += b[n];
+        dvec sum_cp_g0(NumThreads, 0.0);
+#pragma omp parallel for schedule(dynamic, 16) num_threads(NumThreads)
+        for (long i = 0; i < (long)M; i++) {
+#ifdef _OPENMP
+            const int th_idx = omp_get_thread_num();
+#else
+            const int th_idx = 0;
+#endif
+            const double *p = &buf_std_geno[4 * i];
+            const int *pg = Geno_Sparse[i].data(), *ii = pg + 3;
+            double dot = sum_b * p[0];
+            for (int k = 0; k < pg[0]; k++) dot += p[1] * b[*ii++];
+            for (int k = 0; k < pg[1]; k++) dot += p[2] * b[*ii++];
+            for (int k = 0; k < pg[2]; k++) dot += p[3] * b[*ii++];
+            double v, *pbb = &buf_crossprod[N * (size_t)th_idx];
+            ii = pg + 3;
+            sum_cp_g0[th_idx] += dot * p[0];
+            v = dot * p[1]; for (int k = 0; k < pg[0]; k++) pbb[*ii++] += v;
+            v = dot * p[2]; for (int k = 0; k < pg[1]; k++) pbb[*ii++] += v;
+            v = dot * p[3]; for (int k = 0; k < pg[2]; k++) pbb[*ii++] += v;
+        }
+        double sum_g0 = 0; for (int t = 0; t < NumThreads; t++) sum_g0 += sum_cp_g0[t];
+        for (size_t n = 0; n < N; n++) {
+            double s = 0;
+            for (int t = 0; t < NumThreads; t++) s += buf_crossprod[N * (size_t)t + n];
+            out_b[n] = (s + sum_g0) * (1.0 / M);
+        }
+    }
+
+    // get_geno_ds, saige_fitnull.cpp:394-427: missing -> NaN
     void get_geno_ds(size_t snp_idx, dvec &ds) const {
         ds.resize(Geno_NumSamp);
+        if (sparse) {  // :399-408
+            const int *pg = Geno_Sparse[snp_idx].data(), *i = pg + 3;
+            std::fill(ds.begin(), ds.end(), 0.0);
+            for (int k = 0; k < pg[0]; k++) ds[*i++] = 1;
+            for (int k = 0; k < pg[1]; k++) ds[*i++] = 2;
+            for (int k = 0; k < pg[2]; k++) ds[*i++] = NAN;
+            return;
+        }
         const BYTE *g = Geno_PackedRaw + Geno_PackedNumSamp * snp_idx;
         for (size_t n = 0; n < Geno_NumSamp; n++) {
             BYTE c = (g[n >> 2] >> (2 * (n & 3))) & 3;
@@ -207,6 +298,7 @@ struct Oracle {
     // get_crossprod_b_grm, saige_fitnull.cpp:435-536 (dense branch :477-518)
     void crossprod_b_grm(const double *b, double *out_b) {
         n_products++;
+        if (sparse) { crossprod_b_grm_sparse(b, out_b); return; }
         const size_t N = Geno_NumSamp, M = Geno_NumVariant;
         std::fill(buf_crossprod.begin(), buf_crossprod.end(), 0.0);
 #pragma omp parallel for schedule(dynamic, 16) num_threads(NumThreads)
@@ -557,6 +649,40 @@ int orc_store_2b_geno(void *h, const unsigned char *packed, long n_samp, long n_
                       double *buf_std_geno, double *buf_diag) {
     Oracle &o = *(Oracle *)h;
     o.store_2b_geno(packed, n_samp, n_packed, n_var, num_thread);
+    if (buf_std_geno) memcpy(buf_std_geno, o.buf_std_geno.data(), sizeof(double) * 4 * n_var);
+    if (buf_diag) memcpy(buf_diag, o.buf_diag_grm.data(), sizeof(double) * n_samp);
+    return 0;
+}
+// saige_get_sparse, saige_fitnull.cpp:252-320.  type: 0 = raw bytes, 1 = int32, 2 = double (the three SEXP types at
+// :260-291).  out must hold n_samp + 3 ints (the buffer of saige_init_sparse, :244-249); returns the used length.
+long orc_get_sparse(const void *geno, int type, long n_samp, int *out) {
+    const size_t num = n_samp;
+    std::vector<BYTE> gs(num);
+    if (type == 0) {
+        memcpy(gs.data(), geno, num);
+    } else if (type == 1) {
+        const int *s = (const int *)geno;
+        for (size_t i = 0; i < num; i++) gs[i] = (0 <= s[i] && s[i] <= 2) ? (BYTE)s[i] : 3;
+    } else {
+        const double *s = (const double *)geno;
+        for (size_t i = 0; i < num; i++) {
+            if (std::isfinite(s[i])) { int g = (int)round(s[i]); gs[i] = (0 <= g && g <= 2) ? (BYTE)g : 3; } else gs[i] = 3;
+        }
+    }
+    int n = 0, sum = 0;
+    for (size_t i = 0; i < num; i++) if (gs[i] < 3) { sum += gs[i]; n++; }
+    if (sum > n) for (size_t i = 0; i < num; i++) if (gs[i] < 3) gs[i] = 2 - gs[i];
+    int *p = out + 3; int n1 = 0, n2 = 0, n3 = 0;
+    for (size_t i = 0; i < num; i++) if (gs[i] == 1) { *p++ = (int)i; n1++; }
+    for (size_t i = 0; i < num; i++) if (gs[i] == 2) { *p++ = (int)i; n2++; }
+    for (size_t i = 0; i < num; i++) if (gs[i] == 3) { *p++ = (int)i; n3++; }
+    out[0] = n1; out[1] = n2; out[2] = n3;
+    return (long)(p - out);
+}
+int orc_store_sp_geno(void *h, const int *data, const long *offsets, long n_samp, long n_var, int num_thread,
+                      double *buf_std_geno, double *buf_diag) {
+    Oracle &o = *(Oracle *)h;
+    o.store_sp_geno(data, offsets, n_samp, n_var, num_thread);
     if (buf_std_geno) memcpy(buf_std_geno, o.buf_std_geno.data(), sizeof(double) * 4 * n_var);
     if (buf_diag) memcpy(buf_diag, o.buf_diag_grm.data(), sizeof(double) * n_samp);
     return 0;

@@ -4,8 +4,9 @@ Only the hot path of seqFitNullGLMM_SPA is here: packed-ge
 PCG, trace / AI-REML / variance-ratio drivers.  All numerics run in libsaigegds_b200.so (CUDA, sm_100a).
 """
 from ._lib import InvalidArgument, OverflowErrorSGB, SgbError, build  # noqa: F401
-from .api import Context, DeviceArray, NullModel, default_context, make_param, seqFitNullGLMM_SPA  # noqa: F401
+from .api import (Context, DeviceArray, NullModel, default_context, make_param, saige_get_sparse,  # noqa: F401
+                  seqFitNullGLMM_SPA, sparse_to_packed)
 from .dist import init_comm_from_torch, shard_range  # noqa: F401
 
-__all__ = ["Context", "DeviceArray", "NullModel", "default_context", "make_param", "seqFitNullGLMM_SPA",
+__all__ = ["Context", "DeviceArray", "NullModel", "default_context", "make_param", "seqFitNullGLMM_SPA", "saige_get_sparse", "sparse_to_packed",
            "init_comm_from_torch", "shard_range", "build", "SgbError", "InvalidArgument", "OverflowErrorSGB"]

@@ -76,6 +76,7 @@ SYMBOLS = [
     "sgb_r_unif_rand", "sgb_r_sample_int", "sgb_get_stats", "sgb_reset_stats", "sgb_synth_geno_device",
     "sgb_copy_from_device", "sgb_free_device", "sgb_time_products_device", "sgb_malloc_device", "sgb_copy_to_device",
     "sgb_set_profiling", "sgb_kernel_times", "sgb_malloc_host", "sgb_free_host",
+    "sgb_get_sparse", "sgb_store_sp_geno", "sgb_sparse_to_packed",
 ]
 
 

@@ -5,6 +5,8 @@ Names, argument meaning and error behaviour follow the reference:
   native entry points (src/saige_fitnull.cpp)         here
   -------------------------------------------         ---------------------------------
   saige_store_2b_geno        (:159)                   Context.saige_store_2b_geno
+  saige_init_sparse / saige_get_sparse (:244, :252)   saige_get_sparse
+  saige_store_sp_geno        (:324)                   Context.saige_store_sp_geno
   get_crossprod_b_grm        (:436)                   Context.get_crossprod_b_grm
   get_diag_sigma / PCG_diag_sigma (:543, :582)        Context.get_diag_sigma / PCG_diag_sigma
   saige_fit_AI_PCG_binary / _quant (:949, :1103)      Context.saige_fit_AI_PCG_binary / _quant
@@ -38,6 +40,45 @@ def make_param(tol=0.02, tolPCG=1e-5, seed=200, maxiter=20, maxiterPCG=500, no_i
     """The `param` list of R/saige_main.r:442-453 (num.thread has no meaning on the GPU and is ignored)."""
     return L.Param(tol, tolPCG, int(seed), int(maxiter), int(maxiterPCG), int(bool(no_iteration)), int(nrun),
                    int(num_marker), traceCVcutoff, ratioCVcutoff, int(bool(verbose)), indent.encode())
+
+
+_GENO_TYPE = {np.dtype(np.uint8): 0, np.dtype(np.int32): 1, np.dtype(np.float64): 2}
+
+
+def saige_get_sparse(geno: np.ndarray, num_samp: int | None = None) -> np.ndarray:
+    """saige_get_sparse (src/saige_fitnull.cpp:252-320; saige_init_sparse's buffer is allocated here): one variant's
+    genotypes -- uint8 codes, int32 genotypes or float64 dosages, anything outside 0/1/2 = missing -- as the int32 vector
+    (n1, n2, n3, indices of 1s, of 2s, of missing), counted on the minor allele.  Host-only library call."""
+    g = np.ascontiguousarray(geno)
+    if g.dtype not in _GENO_TYPE:
+        raise L.InvalidArgument(L.SGB_ERR_INVALID, "Invalid data type.")
+    n = len(g) if num_samp is None else int(num_samp)
+    if n > len(g):
+        raise L.InvalidArgument(L.SGB_ERR_INVALID, "No enough genotypes.")
+    out = np.empty(n + 3, dtype=np.int32)
+    k = C.c_int64(0)
+    L.check(L.lib().sgb_get_sparse(g.ctypes.data_as(C.c_void_p), C.c_int(_GENO_TYPE[g.dtype]), C.c_int64(n),
+                                   _p(out, C.c_int32), C.byref(k)))
+    return out[:k.value].copy()
+
+
+def _flatten_sparse(sp_geno_list):
+    offsets = np.zeros(len(sp_geno_list) + 1, dtype=np.int64)
+    if len(sp_geno_list):
+        offsets[1:] = np.cumsum([len(v) for v in sp_geno_list])
+        data = np.ascontiguousarray(np.concatenate(sp_geno_list), dtype=np.int32)
+    else:
+        data = np.zeros(1, dtype=np.int32)
+    return data, offsets
+
+
+def sparse_to_packed(sp_geno_list, num_samp: int) -> np.ndarray:
+    """The host packing step of saige_store_sp_geno on its own: list of sparse vectors -> uint8 [M][ceil(N/4)]."""
+    data, offsets = _flatten_sparse(sp_geno_list)
+    out = np.empty((len(sp_geno_list), (int(num_samp) + 3) // 4), dtype=np.uint8)
+    L.check(L.lib().sgb_sparse_to_packed(_p(data, C.c_int32), _p(offsets, C.c_int64), C.c_int64(num_samp),
+                                         C.c_int64(len(sp_geno_list)), _p(out, C.c_ubyte)))
+    return out
 
 
 class Context:
@@ -94,6 +135,20 @@ class Context:
         diag = np.empty(int(num_samp))
         L.check(L.lib().sgb_store_2b_geno(self._h, _p(g, C.c_ubyte), C.c_int64(num_samp), C.c_int64(nb), C.c_int64(m),
                                           C.c_int64(total), C.c_int64(variant_offset), _p(lut), _p(diag)))
+        self.n_samp, self.n_var, self.n_var_total, self.var_offset = int(num_samp), m, total, variant_offset
+        return lut, diag
+
+    def saige_store_sp_geno(self, sp_geno_list, num_samp: int, n_variant_total: int | None = None,
+                            variant_offset: int = 0):
+        """saige_store_sp_geno (:324-388): sp_geno_list = this rank's list of `saige_get_sparse` vectors.  Returns
+        (buf_std_geno [M][4] in the reference's sparse layout, buf_diag_grm [N])."""
+        m = len(sp_geno_list)
+        data, offsets = _flatten_sparse(sp_geno_list)
+        total = m if n_variant_total is None else int(n_variant_total)
+        lut = np.empty((m, 4))
+        diag = np.empty(int(num_samp))
+        L.check(L.lib().sgb_store_sp_geno(self._h, _p(data, C.c_int32), _p(offsets, C.c_int64), C.c_int64(num_samp),
+                                          C.c_int64(m), C.c_int64(total), C.c_int64(variant_offset), _p(lut), _p(diag)))
         self.n_samp, self.n_var, self.n_var_total, self.var_offset = int(num_samp), m, total, variant_offset
         return lut, diag
 
@@ -344,10 +399,10 @@ def seqFitNullGLMM_SPA(formula: str, data: dict, packed_geno: np.ndarray, trait_
                        seed=200, verbose=False, ctx: Context | None = None) -> NullModel:
     """Mirror of seqFitNullGLMM_SPA (R/saige_main.r:223-654) for data already in memory.
 
-    `packed_geno` replaces the GDS file + SeqArray:::.seqGet2bGeno (R/saige_main.r:420): a uint8 array
-    [n_variant][ceil(n_samp/4)] in the 2-bit format.  Sample/variant filtering, which the reference does
-    through SeqArray (:305-333), is the caller's job.  `geno.sparse` does not exist here: the dense 2-bit
-    path is the only one (same GRM).
+    `packed_geno` replaces the GDS file + the genotype loading at R/saige_main.r:388-421: either a uint8 array
+    [n_variant][ceil(n_samp/4)] in the 2-bit format (geno.sparse=FALSE, SeqArray:::.seqGet2bGeno) or a list of
+    `saige_get_sparse` vectors (geno.sparse=TRUE, the reference's default).  Sample/variant filtering, which the
+    reference does through SeqArray (:305-333), is the caller's job.
     """
     if trait_type not in ("binary", "quantitative"):
         raise ValueError("Invalid 'trait.type'.")
@@ -361,7 +416,10 @@ def seqFitNullGLMM_SPA(formula: str, data: dict, packed_geno: np.ndarray, trait_
     X_qrr = None
     if X_transform:
         X, X_qrr = rsetup.qr_transform(X)                                   # :378-380
-    ctx.saige_store_2b_geno(packed_geno, n)                                 # :437
+    if isinstance(packed_geno, np.ndarray) and packed_geno.ndim == 2:
+        ctx.saige_store_2b_geno(packed_geno, n)                             # :437
+    else:
+        ctx.saige_store_sp_geno(packed_geno, n)                             # :434
     n_var = ctx.n_var_total
     param = make_param(tol=tol, tolPCG=tolPCG, seed=seed, maxiter=maxiter, maxiterPCG=maxiterPCG, nrun=nrun,
                        num_marker=num_marker, traceCVcutoff=traceCVcutoff, ratioCVcutoff=ratioCVcutoff, verbose=verbose)

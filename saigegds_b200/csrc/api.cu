@@ -1,6 +1,7 @@
 // extern "C" entry points of include/saigegds_b200.h: argument checks, exception -> status code.
 #include <cstring>
 
+#include "sparse_host.h"
 #include "vecops.cuh"
 
 namespace sgb {
@@ -141,6 +142,76 @@ int sgb_store_2b_geno_device(sgb_context *ctx, uint8_t *packed_device, int take_
         sgb::store_device_layout(*ctx, packed_device, (size_t)n_bytes_per_variant);
         if (take_ownership) SGB_CUDA(cudaFree(packed_device));
         store_outputs(*ctx, buf_std_geno, buf_diag_grm);
+    });
+}
+
+int sgb_get_sparse(const void *geno, int geno_type, int64_t n_samp, int32_t *out, int64_t *out_len) {
+    return guarded(nullptr, [&] {
+        if (geno_type < SGB_GENO_RAW || geno_type > SGB_GENO_REAL) throw sgb::Error(SGB_ERR_INVALID, "Invalid data type.");
+        if (!geno || !out || !out_len || n_samp < 0) throw sgb::Error(SGB_ERR_INVALID, "invalid arguments");
+        *out_len = sgb::get_sparse_host(geno, geno_type, n_samp, out);
+    }, false);
+}
+
+int sgb_sparse_to_packed(const int32_t *sp_data, const int64_t *sp_offsets, int64_t n_samp, int64_t n_variant,
+                         uint8_t *packed) {
+    return guarded(nullptr, [&] {
+        if (!sp_data || !sp_offsets || !packed || n_samp < 1 || n_variant < 0) throw sgb::Error(SGB_ERR_INVALID, "invalid arguments");
+        try {
+            sgb::sparse_to_packed_host(sp_data, sp_offsets, 0, n_variant, n_samp, packed);
+        } catch (const std::string &e) {
+            throw sgb::Error(SGB_ERR_INVALID, e);
+        }
+    }, false);
+}
+
+int sgb_store_sp_geno(sgb_context *ctx, const int32_t *sp_data, const int64_t *sp_offsets, int64_t n_samp,
+                      int64_t n_variant_local, int64_t n_variant_total, int64_t variant_offset, double *buf_std_geno,
+                      double *buf_diag_grm) {
+    return guarded(ctx, [&] {
+        if (!sp_data || !sp_offsets) throw sgb::Error(SGB_ERR_INVALID, "sparse genotype list is NULL");
+        const int64_t nb = (n_samp + 3) / 4;
+        store_common(*ctx, n_samp, nb, n_variant_local, n_variant_total, variant_offset);
+        // pack on the host in slabs of ~64 MB (two pinned stages: one is packed while the other is copied)
+        sgb::DevBuf<uint8_t> raw;
+        raw.ensure((size_t)nb * n_variant_local);
+        const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(n_variant_local, ((int64_t)64 << 20) / nb));
+        sgb::PinBuf<uint8_t> stage[2];
+        cudaEvent_t done[2] = {nullptr, nullptr};
+        SGB_CUDA(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+        SGB_CUDA(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+        try {
+            stage[0].ensure((size_t)slab * nb);
+            if (slab < n_variant_local) stage[1].ensure((size_t)slab * nb);
+            int s = 0;
+            for (int64_t j0 = 0; j0 < n_variant_local; j0 += slab, s ^= 1) {
+                const int64_t j1 = std::min(n_variant_local, j0 + slab);
+                SGB_CUDA(cudaEventSynchronize(done[s]));   // the copy that last used this stage has finished
+                try {
+                    sgb::sparse_to_packed_host(sp_data, sp_offsets, j0, j1, n_samp, stage[s].p);
+                } catch (const std::string &e) {
+                    throw sgb::Error(SGB_ERR_INVALID, e);
+                }
+                ctx->h2d(raw.get() + (size_t)j0 * nb, stage[s].p, (size_t)(j1 - j0) * nb);
+                SGB_CUDA(cudaEventRecord(done[s], ctx->stream));
+            }
+            ctx->sync();
+        } catch (...) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaEventDestroy(done[0]);
+            cudaEventDestroy(done[1]);
+            throw;
+        }
+        cudaEventDestroy(done[0]);
+        cudaEventDestroy(done[1]);
+        sgb::store_device_layout(*ctx, raw.get(), (size_t)nb);
+        store_outputs(*ctx, buf_std_geno, buf_diag_grm);
+        // r_buf_geno in the reference's sparse layout: entries 1..3 relative to entry 0 (saige_fitnull.cpp:358)
+        if (buf_std_geno)
+            for (int64_t j = 0; j < n_variant_local; j++) {
+                double *p = buf_std_geno + 4 * j;
+                p[1] -= p[0]; p[2] -= p[0]; p[3] -= p[0];
+            }
     });
 }
 
