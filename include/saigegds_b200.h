@@ -100,6 +100,22 @@ typedef struct {
     double *maf, *mac, *var1, *var2, *ratio;
 } sgb_var_ratio;
 
+/* The model list of saige_score_test_init (src/saige_main.cpp:101-155), i.e. the arrays .init_nullmod builds
+ * (R/assoc_single.r:17-67).  "K x n" matrices are in R's column-major order, so sample i's K values are contiguous. */
+typedef struct {
+    int trait;                  /* 0 = binary (saige_score_test_bin), 1 = quantitative (saige_score_test_quant) */
+    int64_t n;                  /* samples */
+    int K;                      /* fixed-effect columns, <= 32 */
+    const double *tau;          /* [2] */
+    const double *y, *mu, *y_mu, *mu2;                 /* [n] */
+    const double *t_XXVX_inv, *XV;                     /* K x n; accepted for interface parity, not read: the dense
+                                                          branch they serve (:252-262) is folded into the other one */
+    const double *t_XVX_inv_XV, *t_X;                  /* K x n */
+    const double *XVX;                                 /* K x K */
+    const double *S_a;                                 /* [K] */
+    double var_ratio;
+} sgb_score_model;
+
 /* ---- life cycle ------------------------------------------------------------------------- */
 int sgb_ctx_create(sgb_context **out, int device_ordinal);
 int sgb_ctx_destroy(sgb_context *ctx);
@@ -189,6 +205,25 @@ int sgb_calc_var_ratio_binary(sgb_context *ctx, const sgb_fit0 *fit0, const doub
 int sgb_calc_var_ratio_quant(sgb_context *ctx, const sgb_fit0 *fit0, const double tau[2], const sgb_noK *noK,
                              const sgb_param *param, const int32_t *marker_list, int64_t n_marker,
                              sgb_var_ratio *out);
+
+/* ---- single-variant score test with saddle-point approximation (seqAssocGLMM_SPA's inner loop) ---------------- */
+/* saige_score_test_init (saige_main.cpp:101-155): copies the model to the device.  maf / mac / missing / spa_pval are
+ * M$maf, M$mac, M$missing, M$spa.pval; a non-finite value disables that filter (spa_pval: 0.05), as at :106-113. */
+int sgb_score_test_init(sgb_context *ctx, const sgb_score_model *model, double maf, double mac, double missing,
+                        double spa_pval);
+/* saige_score_test_bin / saige_score_test_quant (:288-407 / :188-285) over a batch of variants -- the reference is called
+ * once per variant by seqApply.  out[n_variant][8] = AF, mac, num, beta, SE, pval, p.norm, converged (the vector returned at
+ * :398-406; for quantitative traits p.norm == pval and converged == 1); valid[v] == 0 where the reference returns NULL
+ * (filtered variant; its out row is NaN).  Three genotype sources:
+ *   _packed  2-bit codes [n_variant][ceil(n/4)] on the host (integer genotypes: 16x less PCIe traffic than doubles),
+ *   _dosage  doubles [n_variant][n] on the host, non-finite = missing (REALSXP dosages, get_ds at :166-186),
+ *   _stored  variants [first, first + n_variant) of the matrix already stored by sgb_store_2b_geno / _sp_geno; no copy,
+ *            *kernel_ms (may be NULL) receives the CUDA-event time of the kernel. */
+int sgb_score_test_packed(sgb_context *ctx, const uint8_t *packed, int64_t n_bytes_per_variant, int64_t n_variant,
+                          double *out, int32_t *valid);
+int sgb_score_test_dosage(sgb_context *ctx, const double *dosage, int64_t n_variant, double *out, int32_t *valid);
+int sgb_score_test_stored(sgb_context *ctx, int64_t first, int64_t n_variant, double *out, int32_t *valid,
+                          float *kernel_ms);
 
 /* ---- R RNG restatement, exposed so the host can draw sample.int(n_var, n_var) (R/saige_main.r:509-511) */
 int sgb_r_set_seed(sgb_context *ctx, uint32_t seed);

@@ -6,7 +6,8 @@ PCG, trace / AI-REML / variance-ratio drivers.  All numerics run in libsaigegds_
 from ._lib import InvalidArgument, OverflowErrorSGB, SgbError, build  # noqa: F401
 from .api import (Context, DeviceArray, NullModel, default_context, make_param, saige_get_sparse,  # noqa: F401
                   seqFitNullGLMM_SPA, sparse_to_packed)
+from .assoc import ScoreTest, init_nullmod, seqAssocGLMM_SPA  # noqa: F401
 from .dist import init_comm_from_torch, shard_range  # noqa: F401
 
-__all__ = ["Context", "DeviceArray", "NullModel", "default_context", "make_param", "seqFitNullGLMM_SPA", "saige_get_sparse", "sparse_to_packed",
+__all__ = ["Context", "DeviceArray", "NullModel", "default_context", "make_param", "seqFitNullGLMM_SPA", "saige_get_sparse", "sparse_to_packed", "ScoreTest", "init_nullmod", "seqAssocGLMM_SPA",
            "init_comm_from_torch", "shard_range", "build", "SgbError", "InvalidArgument", "OverflowErrorSGB"]

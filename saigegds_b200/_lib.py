@@ -62,6 +62,14 @@ class VarRatio(C.Structure):
                 ("ratio", C.POINTER(C.c_double))]
 
 
+class ScoreModel(C.Structure):
+    _fields_ = [("trait", C.c_int), ("n", C.c_int64), ("K", C.c_int), ("tau", C.POINTER(C.c_double)),
+                ("y", C.POINTER(C.c_double)), ("mu", C.POINTER(C.c_double)), ("y_mu", C.POINTER(C.c_double)),
+                ("mu2", C.POINTER(C.c_double)), ("t_XXVX_inv", C.POINTER(C.c_double)), ("XV", C.POINTER(C.c_double)),
+                ("t_XVX_inv_XV", C.POINTER(C.c_double)), ("t_X", C.POINTER(C.c_double)), ("XVX", C.POINTER(C.c_double)),
+                ("S_a", C.POINTER(C.c_double)), ("var_ratio", C.c_double)]
+
+
 class Stats(C.Structure):
     _fields_ = [("n_products", C.c_int64), ("n_product_launches", C.c_int64), ("n_kernel_launches", C.c_int64),
                 ("n_pcg_solves", C.c_int64), ("n_pcg_iterations", C.c_int64), ("last_product_ms", C.c_double)]
@@ -77,6 +85,7 @@ SYMBOLS = [
     "sgb_copy_from_device", "sgb_free_device", "sgb_time_products_device", "sgb_malloc_device", "sgb_copy_to_device",
     "sgb_set_profiling", "sgb_kernel_times", "sgb_malloc_host", "sgb_free_host",
     "sgb_get_sparse", "sgb_store_sp_geno", "sgb_sparse_to_packed",
+    "sgb_score_test_init", "sgb_score_test_packed", "sgb_score_test_dosage", "sgb_score_test_stored",
 ]
 
 

@@ -88,6 +88,7 @@ int sgb_ctx_destroy(sgb_context *ctx) {
     return guarded(ctx, [&] {
         cudaStreamSynchronize(ctx->stream);
         sgb::imma_release(*ctx);
+        sgb::score_release(*ctx);
         sgb::comm_destroy(*ctx);
         cudaEventDestroy(ctx->ev0);
         cudaEventDestroy(ctx->ev1);
@@ -314,6 +315,21 @@ int sgb_calc_var_ratio_binary(sgb_context *ctx, const sgb_fit0 *fit0, const doub
 int sgb_calc_var_ratio_quant(sgb_context *ctx, const sgb_fit0 *fit0, const double tau[2], const sgb_noK *noK,
                              const sgb_param *param, const int32_t *marker_list, int64_t n_marker, sgb_var_ratio *out) {
     return guarded(ctx, [&] { sgb::calc_var_ratio(*ctx, true, fit0, tau, noK, param, marker_list, n_marker, out); });
+}
+
+int sgb_score_test_init(sgb_context *ctx, const sgb_score_model *model, double maf, double mac, double missing,
+                        double spa_pval) {
+    return guarded(ctx, [&] { sgb::score_init(*ctx, model, maf, mac, missing, spa_pval); });
+}
+int sgb_score_test_packed(sgb_context *ctx, const uint8_t *packed, int64_t n_bytes_per_variant, int64_t n_variant, double *out,
+                          int32_t *valid) {
+    return guarded(ctx, [&] { sgb::score_test_packed(*ctx, packed, n_bytes_per_variant, n_variant, out, valid); });
+}
+int sgb_score_test_dosage(sgb_context *ctx, const double *dosage, int64_t n_variant, double *out, int32_t *valid) {
+    return guarded(ctx, [&] { sgb::score_test_dosage(*ctx, dosage, n_variant, out, valid); });
+}
+int sgb_score_test_stored(sgb_context *ctx, int64_t first, int64_t n_variant, double *out, int32_t *valid, float *kernel_ms) {
+    return guarded(ctx, [&] { sgb::score_test_stored(*ctx, first, n_variant, out, valid, kernel_ms); });
 }
 
 int sgb_r_set_seed(sgb_context *ctx, uint32_t seed) {

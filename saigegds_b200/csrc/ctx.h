@@ -72,6 +72,8 @@ struct Comm;  // comm.cu (NCCL through dlopen)
 
 // Tiled int8-tensor-core layout of the genotype shard (grm_imma.cu)
 struct ImmaPlan;
+// Model and workspaces of the single-variant score test (score.cu)
+struct ScoreState;
 
 struct Context {
     int dev = 0;
@@ -100,6 +102,7 @@ struct Context {
     DevBuf<double> ws_tab;      // [M][4] per-variant apply table
     DevBuf<double> ws_vec;      // scratch N x k
     ImmaPlan *imma = nullptr;
+    ScoreState *score = nullptr;
 
     // ---- generic reduction workspace ----
     DevBuf<double> red_partial;
@@ -184,6 +187,12 @@ bool imma_available(const Context &c);
 void imma_grm_mv(Context &c, const double *b_device, double *out_device, int k);
 // ---- product dispatch (solver.cu) ----
 void grm_mv_device(Context &c, const double *b_device, double *out_device, int k);
+// ---- score.cu: single-variant score test + SPA (saige_main.cpp:101-407, SPATest.cpp) ----
+void score_init(Context &c, const sgb_score_model *m, double maf, double mac, double missing, double spa_pval);
+void score_release(Context &c);
+void score_test_packed(Context &c, const uint8_t *packed_host, int64_t nb, int64_t n_var, double *out, int32_t *valid);
+void score_test_dosage(Context &c, const double *dosage_host, int64_t n_var, double *out, int32_t *valid);
+void score_test_stored(Context &c, int64_t first, int64_t n_var, double *out, int32_t *valid, float *kernel_ms);
 // ---- comm.cu ----
 void comm_unique_id(unsigned char id[128]);
 void comm_init(Context &c, const unsigned char id[128], int rank, int world);

@@ -1,0 +1,387 @@
+// Single-variant score test with saddle-point approximation: the per-variant body, written once for the device.
+// Replaces single_test_quant / single_test_bin (src/saige_main.cpp:188-407), the SPA routines Korg, K1_adj, K2,
+// getroot_K1_fast, get_saddle_prob_fast, Saddle_Prob_Fast (src/SPATest.cpp:39-374) and f64_af_ac_impute
+// (src/vectorization.cpp:186-205).
+//
+// One thread block works on one variant; `Env` supplies the block (thread index, sums over the block, an exclusive scan)
+// so that the same source also compiles for one host thread in tests/native/score_body_check.cpp, where it is compared
+// with the oracle before it ever sees a GPU.  Everything a thread decides on comes out of a block-wide sum that all
+// threads receive bit-identically, so the control flow is uniform.
+//
+// The reference has two algebraically equal branches (dense for MAF >= 0.05, index lists below).  Here there is one: with
+// coef = (X'VX)^-1 X'V G and B = X coef, only samples with G != 0 are visited,
+//   var2 = coef' (X'VX) coef + sum_{G!=0} w ((G-B)^2 - B^2),   S = sum_{G!=0} (y-mu)(G-B) + (X'(y-mu)|_{G!=0} - S_a)' coef,
+// which is saige_main.cpp:218-246 / :322-350 for every MAF.  The SPA step needs the adjusted genotype of all samples only for
+// the two one-sided sums g_pos / g_neg (SPATest.cpp:320-325); q, m1 and var2 follow from the sums above.
+#pragma once
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define SGB_HD __host__ __device__ __forceinline__
+#else
+#define SGB_HD inline
+#endif
+
+namespace sgb {
+namespace score {
+
+constexpr int kOutCols = 8;   // AF, mac, num, beta, SE, pval, pval_noadj, converged  (the vector built at saige_main.cpp:277-284 / :398-406)
+
+// The arrays of .init_nullmod (R/assoc_single.r:17-67) the test reads; K x n matrices in R's column-major order = [n][K].
+struct Model {
+    int trait;                  // 0 binary, 1 quantitative
+    int64_t n;
+    int K;
+    double tau0;
+    const double *y_mu, *mu, *mu2;          // [n]
+    const double *t_XVX_inv_XV, *t_X;       // [n][K]
+    const double *XVX;                      // [K][K]
+    const double *S_a;                      // [K] = colSums(X * (y - mu))
+    const double *X_mu;                     // [K] = colSums(X * mu)   (derived at init)
+    double varRatio, thr_maf, thr_mac, thr_missing, thr_pval_spa;
+};
+
+SGB_HD double sq(double v) { return v * v; }
+SGB_HD int sign(double v) { return (v > 0) ? 1 : ((v < 0) ? -1 : 0); }
+SGB_HD double nan_value() { return NAN; }
+
+// R's distribution functions for one degree of freedom, closed forms
+SGB_HD double pchisq1_upper(double x) { return isnan(x) ? x : (x <= 0 ? 1.0 : erfc(sqrt(x * 0.5))); }
+SGB_HD double pnorm_lower(double z) { return 0.5 * erfc(-z * 0.70710678118654752440); }
+SGB_HD double pnorm_upper(double z) { return 0.5 * erfc(z * 0.70710678118654752440); }
+
+// qnorm(p): Wichura's algorithm AS 241 (PPND16), the one R's qnorm5 uses
+SGB_HD double qnorm_as241(double p) {
+    if (isnan(p) || p < 0 || p > 1) return nan_value();
+    if (p == 0) return -INFINITY;
+    if (p == 1) return INFINITY;
+    const double q = p - 0.5;
+    double r, val;
+    if (fabs(q) <= 0.425) {
+        r = .180625 - q * q;
+        return q * (((((((r * 2509.0809287301226727 + 33430.575583588128105) * r + 67265.770927008700853) * r +
+                        45921.953931549871457) * r + 13731.693765509461125) * r + 1971.5909503065514427) * r +
+                      133.14166789178437745) * r + 3.387132872796366608) /
+               (((((((r * 5226.495278852545925 + 28729.085735721942674) * r + 39307.89580009271061) * r +
+                    21213.794301586595867) * r + 5394.1960214247511077) * r + 687.1870074920579083) * r +
+                 42.313330701600911252) * r + 1.);
+    }
+    r = (q < 0) ? p : 1 - p;
+    r = sqrt(-log(r));
+    if (r <= 5.) {
+        r += -1.6;
+        val = (((((((r * 7.7454501427834140764e-4 + .0227238449892691845833) * r + .24178072517745061177) * r +
+                   1.27045825245236838258) * r + 3.64784832476320460504) * r + 5.7694972214606914055) * r +
+                4.6303378461565452959) * r + 1.42343711074968357734) /
+              (((((((r * 1.05075007164441684324e-9 + 5.475938084995344946e-4) * r + .0151986665636164571966) * r +
+                   .14810397642748007459) * r + .68976733498510000455) * r + 1.6763848301838038494) * r +
+                2.05319162663775882187) * r + 1.);
+    } else {
+        r += -5.;
+        val = (((((((r * 2.01033439929228813265e-7 + 2.71155556874348757815e-5) * r + .0012426609473880784386) * r +
+                   .026532189526576123093) * r + .29656057182850489123) * r + 1.7848265399172913358) * r +
+                5.4637849111641143699) * r + 6.6579046435011037772) /
+              (((((((r * 2.04426310338993978564e-15 + 1.4215117583164458887e-7) * r + 1.8463183175100546818e-5) * r +
+                   7.868691311456132591e-4) * r + .0148753612908506148525) * r + .13692988092273580531) * r +
+                .59983224954277312477) * r + 1.);
+    }
+    return (q < 0.0) ? -val : val;
+}
+
+// ---- genotype sources: value of sample i, NaN = missing -----------------------------------------------------------
+struct PackedRow {   // 2-bit codes, sample 4j+k in bits 2k..2k+1 of byte j, 3 = missing (the store's own format)
+    const uint8_t *row;
+    SGB_HD double operator()(int64_t i) const {
+        const unsigned c = (row[i >> 2] >> (2 * (int)(i & 3))) & 3u;
+        return c < 3 ? (double)c : nan_value();
+    }
+};
+struct DosageRow {   // REALSXP dosages as get_ds hands them on (saige_main.cpp:166-186)
+    const double *row;
+    SGB_HD double operator()(int64_t i) const {
+        const double v = row[i];
+        return isfinite(v) ? v : nan_value();
+    }
+};
+
+// Genotype after mean imputation and the flip to the minor allele (vectorization.cpp:198-203, saige_main.cpp:208-213)
+template <class Geno>
+struct Coded {
+    Geno g;
+    double imputed;
+    bool minus;
+    SGB_HD double operator()(int64_t i) const {
+        double v = g(i);
+        if (isnan(v)) v = imputed;
+        return minus ? 2 - v : v;
+    }
+};
+
+// Samples are dealt to threads in groups of four (one packed byte, one 32-byte sector of every model vector); the
+// assignment is the same in every pass, which is what makes the compaction offsets of pass 1 valid in the SPA pass.
+#define SGB_SCORE_FOR_SAMPLES(env, n, i)                                                         \
+    for (int64_t _g = (env).tid(), _ng = ((n) + 3) >> 2; _g < _ng; _g += (env).nthr())           \
+        for (int64_t i = _g << 2, _e = (i + 4 < (n)) ? i + 4 : (n); i < _e; i++)
+
+// ---- SPATest.cpp:39-80 on the compacted (g, mu) pairs of the samples with G != 0 --------------------------------------
+template <class Env>
+SGB_HD double Korg(Env &env, double t, int64_t nnz, const double *g, const double *mu) {
+    double s = 0;
+    for (int64_t k = env.tid(); k < nnz; k += env.nthr()) s += log(1 - mu[k] + mu[k] * exp(g[k] * t));
+    return env.sum(s);
+}
+template <class Env>
+SGB_HD double K1_adj(Env &env, double t, int64_t nnz, const double *g, const double *mu, double q) {
+    double s = 0;
+    for (int64_t k = env.tid(); k < nnz; k += env.nthr()) s += mu[k] * g[k] / ((1 - mu[k]) * exp(-g[k] * t) + mu[k]);
+    return env.sum(s) - q;
+}
+template <class Env>
+SGB_HD double K2(Env &env, double t, int64_t nnz, const double *g, const double *mu) {
+    double s = 0;
+    for (int64_t k = env.tid(); k < nnz; k += env.nthr()) {
+        const double m = mu[k], om = 1 - m, gi = g[k], e = exp(-gi * t);
+        const double v = (om * m * gi * gi * e) / sq(om * e + m);
+        if (isfinite(v)) s += v;
+    }
+    return env.sum(s);
+}
+
+// SPATest.cpp:134-181
+template <class Env>
+SGB_HD void getroot_K1_fast(Env &env, double g_pos, double g_neg, double &root, bool &converged, int64_t nnz, const double *g,
+                            const double *mu, double q, double NAmu, double NAsigma) {
+    const double root_tol = 1.220703125e-4;   // DBL_EPSILON ^ 0.25, SPATest.cpp:26
+    if (q >= g_pos || q <= g_neg) {
+        root = INFINITY;
+        converged = true;
+        return;
+    }
+    double t = root = 0;
+    double K1_eval = K1_adj(env, t, nnz, g, mu, q) + NAmu + NAsigma * t;
+    double prevJump = INFINITY;
+    converged = false;
+    for (int it = 1; it <= 1000; it++) {
+        const double K2_eval = K2(env, t, nnz, g, mu) + NAsigma;
+        double tnew = t - K1_eval / K2_eval;
+        if (!isfinite(tnew)) break;
+        if (fabs(tnew - t) < root_tol) {
+            converged = true;
+            break;
+        }
+        double newK1 = K1_adj(env, tnew, nnz, g, mu, q) + NAmu + NAsigma * tnew;
+        if (sign(K1_eval) != sign(newK1)) {
+            if (fabs(tnew - t) > prevJump - root_tol) {
+                tnew = t + sign(newK1 - K1_eval) * prevJump * 0.5;
+                newK1 = K1_adj(env, tnew, nnz, g, mu, q) + NAmu + NAsigma * tnew;
+                prevJump *= 0.5;
+            } else {
+                prevJump = fabs(tnew - t);
+            }
+        }
+        root = t = tnew;
+        K1_eval = newK1;
+    }
+}
+
+// SPATest.cpp:210-230
+template <class Env>
+SGB_HD double get_saddle_prob_fast(Env &env, double t, int64_t nnz, const double *g, const double *mu, double q, double NAmu,
+                                   double NAsigma) {
+    if (!isfinite(t)) return 0;
+    const double K = Korg(env, t, nnz, g, mu) + NAmu * t + 0.5 * NAsigma * t * t;
+    const double k2 = K2(env, t, nnz, g, mu) + NAsigma;
+    double pval = 0;
+    if (isfinite(K) && isfinite(k2)) {
+        const double w = sign(t) * sqrt(2 * (t * q - K));
+        const double v = t * sqrt(k2);
+        const double z = w + log(v / w) / w;
+        pval = (z > 0) ? pnorm_upper(z) : -pnorm_lower(z);
+    }
+    return pval;
+}
+
+// One variant.  KMAX >= M.K bounds the per-thread coefficient registers.  spa_g / spa_mu: scratch of n doubles each, owned
+// by this block.  out: kOutCols doubles; returns (to every thread) whether the variant passed the filters.
+template <int KMAX, class Env, class Geno>
+SGB_HD bool test_variant(Env &env, const Model &M, const Geno &geno, double *spa_g, double *spa_mu, double *out) {
+    const int64_t n = M.n;
+    const int K = M.K;
+    const bool bin = (M.trait == 0);
+
+    // ---- f64_af_ac_impute: allele frequency, allele count, number of calls
+    double s = 0;
+    int cnt = 0;
+    SGB_SCORE_FOR_SAMPLES(env, n, i) {
+        const double v = geno(i);
+        if (!isnan(v)) { s += v; cnt++; }
+    }
+    const double AC = env.sum(s);
+    const int Num = (int)env.sum((double)cnt);
+    const double AF = (Num > 0) ? (AC / (2 * Num)) : nan_value();
+    const double maf = fmin(AF, 1 - AF);
+    const double mac = fmin(AC, 2 * Num - AC);
+    const double missing = double(n - Num) / n;
+    if (!((Num > 0) && (maf > 0) && (maf >= M.thr_maf) && (mac >= M.thr_mac) && (missing <= M.thr_missing))) {
+        if (env.tid() == 0)
+            for (int k = 0; k < kOutCols; k++) out[k] = nan_value();
+        return false;
+    }
+    const bool minus = (AF > 0.5);
+    const Coded<Geno> G{geno, AF * 2, minus};
+
+    // ---- pass 1 over the samples with G != 0: coef = (X'VX)^-1 X'V G, X'(y-mu) restricted to them, G'mu
+    double coef[KMAX], xy[KMAX];
+#pragma unroll
+    for (int c = 0; c < KMAX; c++) coef[c] = xy[c] = 0;
+    double gmu = 0;
+    int my_nnz = 0;
+    SGB_SCORE_FOR_SAMPLES(env, n, i) {
+        const double v = G(i);
+        if (v != 0) {
+            my_nnz++;
+            const double ym = M.y_mu[i];
+            const double *a = M.t_XVX_inv_XV + (size_t)i * K, *x = M.t_X + (size_t)i * K;
+#pragma unroll
+            for (int c = 0; c < KMAX; c++)
+                if (c < K) { coef[c] += v * a[c]; xy[c] += ym * x[c]; }
+            gmu += v * M.mu[i];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < KMAX; c++)
+        if (c < K) { coef[c] = env.sum(coef[c]); xy[c] = env.sum(xy[c]); }
+    gmu = env.sum(gmu);
+
+    // ---- pass 2: S1 = sum (y-mu)(G-B), v2 = sum w ((G-B)^2 - B^2)
+    double S1 = 0, v2 = 0;
+    SGB_SCORE_FOR_SAMPLES(env, n, i) {
+        const double v = G(i);
+        if (v != 0) {
+            const double *x = M.t_X + (size_t)i * K;
+            double B = 0;
+#pragma unroll
+            for (int c = 0; c < KMAX; c++)
+                if (c < K) B += coef[c] * x[c];
+            const double gt = v - B, d = gt * gt - B * B;
+            S1 += M.y_mu[i] * gt;
+            v2 += bin ? d * M.mu2[i] : d;
+        }
+    }
+    S1 = env.sum(S1);
+    v2 = env.sum(v2);
+    double var2 = v2, S2 = 0, coef_xmu = 0;
+#pragma unroll
+    for (int a = 0; a < KMAX; a++)
+        if (a < K) {
+            double r = 0;
+#pragma unroll
+            for (int b = 0; b < KMAX; b++)
+                if (b < K) r += coef[b] * M.XVX[a * K + b];
+            var2 += coef[a] * r;
+            S2 += (xy[a] - M.S_a[a]) * coef[a];
+            coef_xmu += coef[a] * M.X_mu[a];
+        }
+    const double S = S1 + S2;
+    const double inv_sqrt_mac = 1.0 / sqrt(mac), inv_mac = 1.0 / mac;
+    double pval_noadj, beta;
+    if (bin) {
+        const double var1 = var2 * M.varRatio;
+        pval_noadj = pchisq1_upper(S * S / var1);
+        beta = S / var1;
+    } else {
+        const double var1 = var2 * inv_mac * M.varRatio;
+        const double Tstat = S * inv_sqrt_mac / M.tau0;
+        pval_noadj = pchisq1_upper(Tstat * Tstat / var1);
+        beta = Tstat / var1 * inv_sqrt_mac;
+    }
+
+    // ---- saddle-point approximation, saige_main.cpp:353-394 + Saddle_Prob_Fast
+    double pval = pval_noadj;
+    bool converged = isfinite(pval_noadj);
+    if (bin && converged && (pval_noadj <= M.thr_pval_spa)) {
+        const double AC2 = minus ? (2 * Num - AC) : AC;
+        const double sc = 1 / sqrt(AC2);
+        // adjusted genotype g = (G - B) / sqrt(AC2):  q - m1 = sum (y-mu) g,  m1 = sum mu g,  var2 = sum mu(1-mu) g^2
+        const double m1 = (gmu - coef_xmu) * sc;
+        const double svar2 = var2 * sc * sc, svar1 = svar2 * M.varRatio;
+        const double Tstat = S * sc;
+        const double q = Tstat / sqrt(svar1) * sqrt(svar2) + m1;      // "qtilde"
+        // one pass over all samples: one-sided sums, and the (g, mu) pairs of the samples with G != 0, compacted in
+        // thread order (offset = exclusive scan of the per-thread counts of pass 1)
+        int64_t nnz = 0;
+        int64_t at = env.excl_scan(my_nnz, nnz);
+        double g_pos = 0, g_neg = 0, sub_mu = 0, sub_sigma = 0;
+        SGB_SCORE_FOR_SAMPLES(env, n, i) {
+            const double v = G(i);
+            const double *x = M.t_X + (size_t)i * K;
+            double B = 0;
+#pragma unroll
+            for (int c = 0; c < KMAX; c++)
+                if (c < K) B += coef[c] * x[c];
+            const double g = (v - B) * sc;
+            if (g > 0) g_pos += g; else g_neg += g;
+            if (v != 0) {
+                const double m = M.mu[i];
+                spa_g[at] = g;
+                spa_mu[at] = m;
+                at++;
+                sub_mu += g * m;
+                sub_sigma += g * g * m * (1 - m);
+            }
+        }
+        g_pos = env.sum(g_pos);
+        g_neg = env.sum(g_neg);
+        const double NAmu = m1 - env.sum(sub_mu);
+        const double NAsigma = svar2 - env.sum(sub_sigma);
+        env.sync();   // the compacted pairs are read by other threads from here on
+
+        // Saddle_Prob_Fast, SPATest.cpp:298-374, with (q, m1, var1) = (qtilde, m1, svar2) and cutoff 2
+        const double sdiff = q - m1, qinv = -sdiff + m1;
+        const double p_na = pchisq1_upper(sdiff * sdiff / svar2);
+        double cutoff = 2;
+        while (true) {
+            converged = true;
+            if (cutoff < 0.1) cutoff = 0.1;
+            if (fabs(q - m1) / sqrt(svar2) < cutoff) {
+                pval = p_na;
+            } else {
+                double root1, root2;
+                bool conv1, conv2;
+                getroot_K1_fast(env, g_pos, g_neg, root1, conv1, nnz, spa_g, spa_mu, q, NAmu, NAsigma);
+                getroot_K1_fast(env, g_pos, g_neg, root2, conv2, nnz, spa_g, spa_mu, qinv, NAmu, NAsigma);
+                if (conv1 && conv2) {
+                    const double p1 = get_saddle_prob_fast(env, root1, nnz, spa_g, spa_mu, q, NAmu, NAsigma);
+                    const double p2 = get_saddle_prob_fast(env, root2, nnz, spa_g, spa_mu, qinv, NAmu, NAsigma);
+                    pval = fabs(p1) + fabs(p2);
+                } else {
+                    pval = p_na;
+                    converged = false;
+                    break;
+                }
+            }
+            if (pval != 0 && p_na / pval > 1000)
+                cutoff *= 2;
+            else
+                break;
+        }
+        if (pval == 0 && pval_noadj > 0) {
+            pval = pval_noadj;
+            converged = false;
+        }
+        beta = (Tstat / svar1) / sqrt(AC2);
+        env.sync();   // scratch is reused by the block's next variant
+    }
+    if (minus) beta = -beta;
+    if (env.tid() == 0) {
+        out[0] = AF; out[1] = mac; out[2] = (double)Num; out[3] = beta;
+        out[4] = fabs(beta / qnorm_as241(pval / 2));
+        out[5] = pval; out[6] = pval_noadj; out[7] = converged ? 1.0 : 0.0;
+    }
+    return true;
+}
+
+}  // namespace score
+}  // namespace sgb
