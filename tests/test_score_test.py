@@ -174,8 +174,8 @@ def test_gpu_score_test_reproduces_golden_pvalues(gpu, fx, trait):
         assert "p.norm" not in ans
     # real-valued dosage input, in two batches: same numbers
     ans2 = sg.seqAssocGLMM_SPA(dosage_all(fx), golden_modobj(fx, trait), mac=4, ctx=gpu, batch_bytes=40 << 20)
-    assert np.array_equal(ans2["id"], ans["id"]) and np.array_equal(ans2["pval"], ans["pval"])
-    assert np.array_equal(ans2["beta"], ans["beta"])
+    assert np.array_equal(ans2["id"], ans["id"]) and relmax(ans2["pval"], ans["pval"]) < 1e-12
+    assert relmax(ans2["beta"], ans["beta"]) < 1e-12
 
 
 @pytest.mark.gpu
