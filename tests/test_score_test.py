@@ -220,7 +220,7 @@ def test_gpu_fit_then_gpu_scan_matches_golden_pvalues(gpu, fx):
     from oracle import oracle as orc
     sp = [orc.get_sparse(c) for c in
           np.stack([(fx.packed >> s) & 3 for s in (0, 2, 4, 6)], axis=2).reshape(len(fx.packed), -1)[:, :fx.n_samp].astype(np.uint8)]
-    mod = sg.seqFitNullGLMM_SPA("y ~ x1 + x2", fx.pheno, sp, trait_type="binary", variant_id=fx.variant_id[fx.keep], ctx=gpu)
+    mod = sg.seqFitNullGLMM_SPA("y ~ x1 + x2", fx.pheno, sp, trait_type="binary", variant_id=fx.variant_id, ctx=gpu)
     ans = sg.seqAssocGLMM_SPA(fx.packed_all, mod, mac=4, ctx=gpu)
     pv = fx.pval
     assert np.array_equal(ans["id"], pv["id"])
