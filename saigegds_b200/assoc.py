@@ -70,6 +70,11 @@ class ScoreTest:
         L.check(L.lib().sgb_score_test_init(self.ctx._h, C.byref(sm), C.c_double(mobj["maf"]), C.c_double(mobj["mac"]),
                                             C.c_double(mobj["missing"]), C.c_double(mobj["spa_pval"])))
 
+    def set_path(self, name: str):
+        """'tiled' (default: shared-memory-tiled kernel for every variant + per-variant kernel for the saddle-point
+        candidates) or 'per_variant' (every variant through the per-variant kernel)."""
+        L.check(L.lib().sgb_score_test_set_path(self.ctx._h, C.c_int({"tiled": 0, "per_variant": 1}[name])))
+
     @staticmethod
     def _result(out, valid):
         r = {k: out[:, i].copy() for i, k in enumerate(COLUMNS)}
@@ -110,7 +115,7 @@ class ScoreTest:
 
 def seqAssocGLMM_SPA(geno: np.ndarray, modobj: NullModel, maf=float("nan"), mac=10.0, missing=0.1, spa_pval=0.05,
                      var_ratio=float("nan"), variant_id=None, sample_index=None, batch_bytes=1 << 30,
-                     ctx: Context | None = None) -> dict:
+                     kernel_path: str | None = None, ctx: Context | None = None) -> dict:
     """Mirror of seqAssocGLMM_SPA (R/assoc_single.r:92-334) for genotypes already in memory: `geno` replaces the GDS
     node (2-bit packed uint8 [n_var][ceil(n/4)] or float64 dosages [n_var][n]).  Returns the data.frame columns id, AF.alt,
     mac, num, beta, SE, pval (+ p.norm, converged for binary traits) of the variants that pass the filters."""
@@ -118,6 +123,8 @@ def seqAssocGLMM_SPA(geno: np.ndarray, modobj: NullModel, maf=float("nan"), mac=
         raise ValueError("No variant in the genotypic data set!")
     mobj = init_nullmod(modobj, sample_index, maf, mac, missing, spa_pval, var_ratio)
     st = ScoreTest(mobj, ctx)
+    if kernel_path is not None:
+        st.set_path(kernel_path)
     step = max(1, int(batch_bytes // max(1, geno.shape[1] * geno.itemsize)))
     parts = [st.test(geno[a:a + step]) for a in range(0, geno.shape[0], step)]
     res = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}

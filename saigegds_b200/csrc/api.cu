@@ -321,6 +321,9 @@ int sgb_score_test_init(sgb_context *ctx, const sgb_score_model *model, double m
                         double spa_pval) {
     return guarded(ctx, [&] { sgb::score_init(*ctx, model, maf, mac, missing, spa_pval); });
 }
+int sgb_score_test_set_path(sgb_context *ctx, int path) {
+    return guarded(ctx, [&] { sgb::score_set_path(*ctx, path); });
+}
 int sgb_score_test_packed(sgb_context *ctx, const uint8_t *packed, int64_t n_bytes_per_variant, int64_t n_variant, double *out,
                           int32_t *valid) {
     return guarded(ctx, [&] { sgb::score_test_packed(*ctx, packed, n_bytes_per_variant, n_variant, out, valid); });

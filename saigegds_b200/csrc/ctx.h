@@ -190,6 +190,7 @@ void grm_mv_device(Context &c, const double *b_device, double *out_device, int k
 // ---- score.cu: single-variant score test + SPA (saige_main.cpp:101-407, SPATest.cpp) ----
 void score_init(Context &c, const sgb_score_model *m, double maf, double mac, double missing, double spa_pval);
 void score_release(Context &c);
+void score_set_path(Context &c, int path);
 void score_test_packed(Context &c, const uint8_t *packed_host, int64_t nb, int64_t n_var, double *out, int32_t *valid);
 void score_test_dosage(Context &c, const double *dosage_host, int64_t n_var, double *out, int32_t *valid);
 void score_test_stored(Context &c, int64_t first, int64_t n_var, double *out, int32_t *valid, float *kernel_ms);

@@ -9,10 +9,11 @@
 // threads receive bit-identically, so the control flow is uniform.
 //
 // The reference has two algebraically equal branches (dense for MAF >= 0.05, index lists below).  Here there is one: with
-// coef = (X'VX)^-1 X'V G and B = X coef, only samples with G != 0 are visited,
-//   var2 = coef' (X'VX) coef + sum_{G!=0} w ((G-B)^2 - B^2),   S = sum_{G!=0} (y-mu)(G-B) + (X'(y-mu)|_{G!=0} - S_a)' coef,
-// which is saige_main.cpp:218-246 / :322-350 for every MAF.  The SPA step needs the adjusted genotype of all samples only for
-// the two one-sided sums g_pos / g_neg (SPATest.cpp:320-325); q, m1 and var2 follow from the sums above.
+// coef = (X'VX)^-1 X'V G and B = X coef, a single pass over the samples with G != 0 gives
+//   S = sum (y-mu)(G-B) = G'(y-mu) - S_a' coef,      var2 = sum w (G-B)^2 = G'WG - 2 coef'(X'WG) + coef' (X'WX) coef,
+// (2K + 3 model values per visited sample, no second pass), which are the numbers of saige_main.cpp:218-262 / :322-350.  The SPA step needs
+// the adjusted genotype of all samples only for the two one-sided sums g_pos / g_neg (SPATest.cpp:320-325) and for the
+// samples with G != 0; q, m1 and var2 follow from the sums above.
 #pragma once
 #include <float.h>
 #include <math.h>
@@ -203,6 +204,54 @@ SGB_HD double get_saddle_prob_fast(Env &env, double t, int64_t nnz, const double
     return pval;
 }
 
+// Filters of saige_main.cpp:197-205 / :297-305 from the allele count AC over Num called samples.
+SGB_HD bool variant_passes(const Model &M, double AC, int Num, double &AF, double &mac) {
+    AF = (Num > 0) ? (AC / (2 * Num)) : nan_value();
+    const double maf = fmin(AF, 1 - AF);
+    mac = fmin(AC, 2 * Num - AC);
+    const double missing = double(M.n - Num) / M.n;
+    return (Num > 0) && (maf > 0) && (maf >= M.thr_maf) && (mac >= M.thr_mac) && (missing <= M.thr_missing);
+}
+
+// Score statistic and its normal-approximation p-value from the per-variant sums over the samples with G != 0:
+// coef = sum G a_i (a = row of t_XVX_inv_XV), xwg = sum G w_i x_i, SyG = sum G (y-mu)_i, SwGG = sum G^2 w_i.
+// With B = X coef:  sum_i (y-mu)_i (G-B)_i = G'(y-mu) - S_a'coef  and
+// sum_i w_i (G-B)_i^2 = G'WG - 2 coef'(X'WG) + coef'(X'WX)coef.  (W = mu(1-mu) of the mixed model, while coef is weighted
+// with the V of the fixed-effects-only fit, so the cross term does not collapse.)  The reference reaches the same two
+// numbers through per-sample residuals, saige_main.cpp:218-262 / :322-350.
+template <int KMAX>
+SGB_HD void score_stats(const Model &M, const double (&coef)[KMAX], const double (&xwg)[KMAX], double SyG, double SwGG, double mac,
+                        double &S, double &var2, double &coef_xmu, double &pval_noadj, double &beta) {
+    const int K = M.K;
+    double quad = 0, cross = 0, sa_coef = 0;
+    coef_xmu = 0;
+#pragma unroll
+    for (int a = 0; a < KMAX; a++)
+        if (a < K) {
+            double r = 0;
+#pragma unroll
+            for (int b = 0; b < KMAX; b++)
+                if (b < K) r += coef[b] * M.XVX[a * K + b];
+            quad += coef[a] * r;
+            cross += coef[a] * xwg[a];
+            sa_coef += M.S_a[a] * coef[a];
+            coef_xmu += coef[a] * M.X_mu[a];
+        }
+    var2 = SwGG - 2 * cross + quad;
+    S = SyG - sa_coef;
+    const double inv_sqrt_mac = 1.0 / sqrt(mac), inv_mac = 1.0 / mac;
+    if (M.trait == 0) {
+        const double var1 = var2 * M.varRatio;
+        pval_noadj = pchisq1_upper(S * S / var1);
+        beta = S / var1;
+    } else {
+        const double var1 = var2 * inv_mac * M.varRatio;
+        const double Tstat = S * inv_sqrt_mac / M.tau0;
+        pval_noadj = pchisq1_upper(Tstat * Tstat / var1);
+        beta = Tstat / var1 * inv_sqrt_mac;
+    }
+}
+
 // One variant.  KMAX >= M.K bounds the per-thread coefficient registers.  spa_g / spa_mu: scratch of n doubles each, owned
 // by this block.  out: kOutCols doubles; returns (to every thread) whether the variant passed the filters.
 template <int KMAX, class Env, class Geno>
@@ -220,11 +269,8 @@ SGB_HD bool test_variant(Env &env, const Model &M, const Geno &geno, double *spa
     }
     const double AC = env.sum(s);
     const int Num = (int)env.sum((double)cnt);
-    const double AF = (Num > 0) ? (AC / (2 * Num)) : nan_value();
-    const double maf = fmin(AF, 1 - AF);
-    const double mac = fmin(AC, 2 * Num - AC);
-    const double missing = double(n - Num) / n;
-    if (!((Num > 0) && (maf > 0) && (maf >= M.thr_maf) && (mac >= M.thr_mac) && (missing <= M.thr_missing))) {
+    double AF, mac;
+    if (!variant_passes(M, AC, Num, AF, mac)) {
         if (env.tid() == 0)
             for (int k = 0; k < kOutCols; k++) out[k] = nan_value();
         return false;
@@ -232,71 +278,34 @@ SGB_HD bool test_variant(Env &env, const Model &M, const Geno &geno, double *spa
     const bool minus = (AF > 0.5);
     const Coded<Geno> G{geno, AF * 2, minus};
 
-    // ---- pass 1 over the samples with G != 0: coef = (X'VX)^-1 X'V G, X'(y-mu) restricted to them, G'mu
-    double coef[KMAX], xy[KMAX];
+    // ---- one pass over the samples with G != 0: coef = (X'VX)^-1 X'V G, G'(y-mu), G'WG, G'mu
+    double coef[KMAX], xwg[KMAX];
 #pragma unroll
-    for (int c = 0; c < KMAX; c++) coef[c] = xy[c] = 0;
-    double gmu = 0;
+    for (int c = 0; c < KMAX; c++) coef[c] = xwg[c] = 0;
+    double SyG = 0, SwGG = 0, gmu = 0;
     int my_nnz = 0;
     SGB_SCORE_FOR_SAMPLES(env, n, i) {
         const double v = G(i);
         if (v != 0) {
             my_nnz++;
-            const double ym = M.y_mu[i];
             const double *a = M.t_XVX_inv_XV + (size_t)i * K, *x = M.t_X + (size_t)i * K;
+            const double vw = bin ? v * M.mu2[i] : v;
 #pragma unroll
             for (int c = 0; c < KMAX; c++)
-                if (c < K) { coef[c] += v * a[c]; xy[c] += ym * x[c]; }
+                if (c < K) { coef[c] += v * a[c]; xwg[c] += vw * x[c]; }
+            SyG += v * M.y_mu[i];
+            SwGG += v * vw;
             gmu += v * M.mu[i];
         }
     }
 #pragma unroll
     for (int c = 0; c < KMAX; c++)
-        if (c < K) { coef[c] = env.sum(coef[c]); xy[c] = env.sum(xy[c]); }
+        if (c < K) { coef[c] = env.sum(coef[c]); xwg[c] = env.sum(xwg[c]); }
+    SyG = env.sum(SyG);
+    SwGG = env.sum(SwGG);
     gmu = env.sum(gmu);
-
-    // ---- pass 2: S1 = sum (y-mu)(G-B), v2 = sum w ((G-B)^2 - B^2)
-    double S1 = 0, v2 = 0;
-    SGB_SCORE_FOR_SAMPLES(env, n, i) {
-        const double v = G(i);
-        if (v != 0) {
-            const double *x = M.t_X + (size_t)i * K;
-            double B = 0;
-#pragma unroll
-            for (int c = 0; c < KMAX; c++)
-                if (c < K) B += coef[c] * x[c];
-            const double gt = v - B, d = gt * gt - B * B;
-            S1 += M.y_mu[i] * gt;
-            v2 += bin ? d * M.mu2[i] : d;
-        }
-    }
-    S1 = env.sum(S1);
-    v2 = env.sum(v2);
-    double var2 = v2, S2 = 0, coef_xmu = 0;
-#pragma unroll
-    for (int a = 0; a < KMAX; a++)
-        if (a < K) {
-            double r = 0;
-#pragma unroll
-            for (int b = 0; b < KMAX; b++)
-                if (b < K) r += coef[b] * M.XVX[a * K + b];
-            var2 += coef[a] * r;
-            S2 += (xy[a] - M.S_a[a]) * coef[a];
-            coef_xmu += coef[a] * M.X_mu[a];
-        }
-    const double S = S1 + S2;
-    const double inv_sqrt_mac = 1.0 / sqrt(mac), inv_mac = 1.0 / mac;
-    double pval_noadj, beta;
-    if (bin) {
-        const double var1 = var2 * M.varRatio;
-        pval_noadj = pchisq1_upper(S * S / var1);
-        beta = S / var1;
-    } else {
-        const double var1 = var2 * inv_mac * M.varRatio;
-        const double Tstat = S * inv_sqrt_mac / M.tau0;
-        pval_noadj = pchisq1_upper(Tstat * Tstat / var1);
-        beta = Tstat / var1 * inv_sqrt_mac;
-    }
+    double S, var2, coef_xmu, pval_noadj, beta;
+    score_stats<KMAX>(M, coef, xwg, SyG, SwGG, mac, S, var2, coef_xmu, pval_noadj, beta);
 
     // ---- saddle-point approximation, saige_main.cpp:353-394 + Saddle_Prob_Fast
     double pval = pval_noadj;

@@ -157,9 +157,10 @@ def test_init_nullmod_matches_the_reference_arrays(fx):
 # ------------------------------------------------------------------ GPU: the CUDA kernel through the C-ABI
 @pytest.mark.gpu
 @pytest.mark.parametrize("trait", ["binary", "quantitative"])
-def test_gpu_score_test_reproduces_golden_pvalues(gpu, fx, trait):
+@pytest.mark.parametrize("path", ["tiled", "per_variant"])
+def test_gpu_score_test_reproduces_golden_pvalues(gpu, fx, trait, path):
     pv = fx.pval if trait == "binary" else fx.pval_quant
-    ans = sg.seqAssocGLMM_SPA(fx.packed_all, golden_modobj(fx, trait), mac=4, ctx=gpu)
+    ans = sg.seqAssocGLMM_SPA(fx.packed_all, golden_modobj(fx, trait), mac=4, ctx=gpu, kernel_path=path)
     assert np.array_equal(ans["id"], pv["id"])
     assert np.array_equal(ans["AF.alt"], pv["AF_alt"]) and np.array_equal(ans["mac"], pv["mac"])
     assert np.array_equal(ans["num"], pv["num"].astype(np.int64))
@@ -173,7 +174,8 @@ def test_gpu_score_test_reproduces_golden_pvalues(gpu, fx, trait):
     else:
         assert "p.norm" not in ans
     # real-valued dosage input, in two batches: same numbers
-    ans2 = sg.seqAssocGLMM_SPA(dosage_all(fx), golden_modobj(fx, trait), mac=4, ctx=gpu, batch_bytes=40 << 20)
+    ans2 = sg.seqAssocGLMM_SPA(dosage_all(fx), golden_modobj(fx, trait), mac=4, ctx=gpu, batch_bytes=40 << 20,
+                               kernel_path=path)
     assert np.array_equal(ans2["id"], ans["id"]) and relmax(ans2["pval"], ans["pval"]) < 1e-12
     assert relmax(ans2["beta"], ans["beta"]) < 1e-12
 
@@ -185,12 +187,14 @@ def test_gpu_score_test_matches_oracle_with_missing_and_filters(gpu, fx, trait):
     m, vr = oracle_model(fx, trait)
     st = sg.ScoreTest(sg.init_nullmod(golden_modobj(fx, trait), maf=0.001, mac=3.0, missing=0.25, spa_pval=0.2), gpu)
     kw = dict(maf=0.001, mac=3.0, missing=0.25, spa_pval=0.2)
-    for integer in (True, False):
-        d = random_dosages(np.random.default_rng(31 + integer), fx.n_samp, 600, integer)
-        ref = orc.score_test(m, d, vr, **kw)
-        compare(st.test(d), ref, 1e-8, exact_counts=integer)
-        if integer:
-            compare(st.test(pack(d)), ref, 1e-8)
+    for path in ("tiled", "per_variant"):
+        st.set_path(path)
+        for integer in (True, False):
+            d = random_dosages(np.random.default_rng(31 + integer), fx.n_samp, 600, integer)
+            ref = orc.score_test(m, d, vr, **kw)
+            compare(st.test(d), ref, 1e-8, exact_counts=integer)
+            if integer:
+                compare(st.test(pack(d)), ref, 1e-8)
     # bit-reproducible: fixed reduction order, no atomics on the data path
     a, b = st.test(d), st.test(d)
     assert all(np.array_equal(a[k], b[k], equal_nan=True) for k in NAMES)

@@ -28,16 +28,26 @@ mod = sg.NullModel(coefficients=beta, tau=np.array([1.0, 0.3]), linear_predictor
 ctx = sg.Context(0)
 ctx.store_synthetic(n, m)
 st = sg.ScoreTest(sg.init_nullmod(mod), ctx)
+st.set_path("per_variant")
 st.test_stored(0, min(m, 256))                      # warm-up
+ref, ms_pv = st.test_stored(0, m)
+st.set_path("tiled")
+st.test_stored(0, min(m, 256))
 res, ms = st.test_stored(0, m)
 res2, ms2 = st.test_stored(0, m)
+dev = {k: float(np.nanmax(np.abs(res[k] - ref[k]) / np.maximum(np.abs(ref[k]), 1e-300))) for k in ("pval", "beta", "p.norm")}
 host = ctx.synth_to_host(n, m)
 t0 = time.perf_counter()
 res3 = st.test(host)
 e2e = time.perf_counter() - t0
 assert all(np.array_equal(res[k], res3[k], equal_nan=True) for k in res)
 pv = res["pval"][res["valid"]]
-line = {"n_samp": n, "n_variant": m, "K": K, "kernel_ms": [ms, ms2], "variants_per_s_resident": m / (min(ms, ms2) * 1e-3),
+ctx.set_profiling(True)
+st.test_stored(0, m)
+kt = ctx.kernel_times()
+ctx.set_profiling(False)
+line = {"n_samp": n, "n_variant": m, "K": K, "kernel_ms": [ms, ms2], "per_variant_path_ms": ms_pv, "kernels": kt,
+        "tiled_vs_per_variant_rel": dev, "variants_per_s_resident": m / (min(ms, ms2) * 1e-3),
         "variants_per_s_host_packed": m / e2e, "packed_GBps_resident": (n / 4) * m / (min(ms, ms2) * 1e-3) / 1e9,
         "valid": int(res["valid"].sum()), "spa_adjusted": int(np.sum(res["pval"] != res["p.norm"]) - np.sum(~res["valid"])),
         "p_below_0.05": float(np.mean(pv < 0.05)), "converged": float(np.mean(res["converged"][res["valid"]]))}
