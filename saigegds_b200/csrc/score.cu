@@ -132,12 +132,18 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // A lane's genotypes of one tile: SPL consecutive samples starting at tile * 32 SPL + lane * SPL.
+// tab[c] = value of code c after mean imputation and the flip to the minor allele (tab[3]: missing); all zero for a
+// filtered variant, which then adds nothing.
 template <int SPL>
 struct PackedFrag {
     uint32_t bits;
     __device__ __forceinline__ double value(int k) const {
         const unsigned c = (bits >> (2 * k)) & 3u;
         return c < 3 ? (double)c : score::nan_value();
+    }
+    __device__ __forceinline__ double coded(int k, const double (&tab)[4], bool, bool) const {
+        const unsigned c = (bits >> (2 * k)) & 3u;
+        return c == 0 ? tab[0] : (c == 1 ? tab[1] : (c == 2 ? tab[2] : tab[3]));
     }
 };
 struct PackedTiles {
@@ -159,6 +165,11 @@ template <int SPL>
 struct DosageFrag {
     double d[SPL];
     __device__ __forceinline__ double value(int k) const { return isfinite(d[k]) ? d[k] : score::nan_value(); }
+    __device__ __forceinline__ double coded(int k, const double (&tab)[4], bool ok, bool minus) const {
+        if (!ok) return 0.0;
+        if (!isfinite(d[k])) return tab[3];
+        return minus ? 2 - d[k] : d[k];
+    }
 };
 struct DosageTiles {
     const double *base;
@@ -226,35 +237,41 @@ score_tiled_kernel(score::Model M, Src src, int64_t n_var, const double *__restr
         const double *srcp = mt + (size_t)t * tile_doubles;
         for (int i = threadIdx.x; i < tile_doubles / 2; i += kTileWarps * 32) cp_async16(dst + 2 * i, srcp + 2 * i);
     };
+    double tab[R][4];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const double miss = ok[r] ? imputed[r] : 0.0, one = ok[r] ? 1.0 : 0.0;
+        tab[r][0] = minus[r] ? 2 * one : 0.0;
+        tab[r][1] = one;
+        tab[r][2] = minus[r] ? 0.0 : 2 * one;
+        tab[r][3] = minus[r] ? 2 * one - miss : miss;
+    }
+    using Frag = decltype(src.template fetch<SPL>(0, 0, 0));
+    Frag cur[R], nxt[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) cur[r] = nxt[r] = src.template fetch<SPL>(ok[r] ? v0 + r : 0, 0, lane);
     stage(0);
     cp_async_commit();
     for (int64_t t = 0; t < tiles; t++) {
-        if (t + 1 < tiles) stage(t + 1);
-        cp_async_commit();
-        double g[R][SPL];
+        if (t + 1 < tiles) {
+            stage(t + 1);
+            // the genotypes of the next tile travel while this one is being used
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            if (ok[r]) {
-                const auto f = src.template fetch<SPL>(v0 + r, t, lane);
-#pragma unroll
-                for (int k = 0; k < SPL; k++) {
-                    double x = f.value(k);
-                    if (isnan(x)) x = imputed[r];
-                    g[r][k] = minus[r] ? 2 - x : x;
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < SPL; k++) g[r][k] = 0;
-            }
+            for (int r = 0; r < R; r++) nxt[r] = src.template fetch<SPL>(ok[r] ? v0 + r : 0, t + 1, lane);
         }
+        cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
         const double *m = tile_smem + (size_t)(t & 1) * tile_doubles + lane;
 #pragma unroll
         for (int k = 0; k < SPL; k++) {
+            double g[R];
             bool any = false;
 #pragma unroll
-            for (int r = 0; r < R; r++) any |= (g[r][k] != 0);
+            for (int r = 0; r < R; r++) {
+                g[r] = cur[r].coded(k, tab[r], ok[r], minus[r]);
+                any |= (g[r] != 0);
+            }
             if (any) {   // samples past n hold zeros in every model row
                 const double *mk = m + k * 32;
 #pragma unroll
@@ -262,13 +279,15 @@ score_tiled_kernel(score::Model M, Src src, int64_t n_var, const double *__restr
                     if (c < K) {
                         const double a = mk[c * T], xw = mk[(K + c) * T];
 #pragma unroll
-                        for (int r = 0; r < R; r++) { coef[r][c] += g[r][k] * a; xwg[r][c] += g[r][k] * xw; }
+                        for (int r = 0; r < R; r++) { coef[r][c] += g[r] * a; xwg[r][c] += g[r] * xw; }
                     }
                 const double ym = mk[2 * K * T], w = mk[(2 * K + 1) * T];
 #pragma unroll
-                for (int r = 0; r < R; r++) { SyG[r] += g[r][k] * ym; SwGG[r] += g[r][k] * g[r][k] * w; }
+                for (int r = 0; r < R; r++) { SyG[r] += g[r] * ym; SwGG[r] += g[r] * g[r] * w; }
             }
         }
+#pragma unroll
+        for (int r = 0; r < R; r++) cur[r] = nxt[r];
         __syncthreads();   // this buffer is refilled by the copy issued in the next iteration
     }
     cp_async_wait<0>();

@@ -150,6 +150,22 @@ SGB_HD double K2(Env &env, double t, int64_t nnz, const double *g, const double 
     return env.sum(s);
 }
 
+// K1_adj and K2 at the same t from one exponential per sample (Newton's step needs both; SPATest.cpp:143-150 evaluates
+// them in two passes).  K1 term = mu g / d, K2 term = (1-mu) mu g^2 e / d^2 with e = exp(-g t), d = (1-mu) e + mu.
+template <class Env>
+SGB_HD void K1_K2(Env &env, double t, int64_t nnz, const double *g, const double *mu, double q, double &k1, double &k2) {
+    double s1 = 0, s2 = 0;
+    for (int64_t k = env.tid(); k < nnz; k += env.nthr()) {
+        const double m = mu[k], om = 1 - m, gi = g[k], e = exp(-gi * t);
+        const double inv = 1 / (om * e + m), mg = m * gi * inv;
+        s1 += mg;
+        const double v = om * e * gi * inv * mg;
+        if (isfinite(v)) s2 += v;
+    }
+    k1 = env.sum(s1) - q;
+    k2 = env.sum(s2);
+}
+
 // SPATest.cpp:134-181
 template <class Env>
 SGB_HD void getroot_K1_fast(Env &env, double g_pos, double g_neg, double &root, bool &converged, int64_t nnz, const double *g,
@@ -161,22 +177,26 @@ SGB_HD void getroot_K1_fast(Env &env, double g_pos, double g_neg, double &root, 
         return;
     }
     double t = root = 0;
-    double K1_eval = K1_adj(env, t, nnz, g, mu, q) + NAmu + NAsigma * t;
+    double k1, k2;
+    K1_K2(env, t, nnz, g, mu, q, k1, k2);
+    double K1_eval = k1 + NAmu + NAsigma * t;
     double prevJump = INFINITY;
     converged = false;
     for (int it = 1; it <= 1000; it++) {
-        const double K2_eval = K2(env, t, nnz, g, mu) + NAsigma;
+        const double K2_eval = k2 + NAsigma;          // K2 at the current t, from the pass that produced K1_eval
         double tnew = t - K1_eval / K2_eval;
         if (!isfinite(tnew)) break;
         if (fabs(tnew - t) < root_tol) {
             converged = true;
             break;
         }
-        double newK1 = K1_adj(env, tnew, nnz, g, mu, q) + NAmu + NAsigma * tnew;
+        K1_K2(env, tnew, nnz, g, mu, q, k1, k2);
+        double newK1 = k1 + NAmu + NAsigma * tnew;
         if (sign(K1_eval) != sign(newK1)) {
             if (fabs(tnew - t) > prevJump - root_tol) {
                 tnew = t + sign(newK1 - K1_eval) * prevJump * 0.5;
-                newK1 = K1_adj(env, tnew, nnz, g, mu, q) + NAmu + NAsigma * tnew;
+                K1_K2(env, tnew, nnz, g, mu, q, k1, k2);
+                newK1 = k1 + NAmu + NAsigma * tnew;
                 prevJump *= 0.5;
             } else {
                 prevJump = fabs(tnew - t);
