@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kThreads) score_test_kernel(score::Model M, Sr
 }
 
 // ---- tiled kernel ----------------------------------------------------------------------------------------------------
-constexpr int kTileWarps = 8;
+constexpr int kTileWarps = 16;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -185,14 +185,15 @@ struct DosageTiles {
     }
 };
 
-template <int KMAX, int R, int SPL, class Src>
+// EXACT: the model has exactly KMAX columns (loops and row offsets fold at compile time); otherwise KMAX bounds M.K.
+template <int KMAX, bool EXACT, int R, int SPL, class Src>
 __global__ void __launch_bounds__(kTileWarps * 32)
 score_tiled_kernel(score::Model M, Src src, int64_t n_var, const double *__restrict__ mt, int rows, double *__restrict__ out,
                    int32_t *__restrict__ valid, int32_t *__restrict__ spa_list, unsigned int *__restrict__ spa_count) {
     constexpr int T = 32 * SPL;
     extern __shared__ __align__(16) double tile_smem[];   // [2][rows][T]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int K = M.K;
+    const int K = EXACT ? KMAX : M.K;
     const int64_t n = M.n, tiles = (n + T - 1) / T;
     const int64_t v0 = ((int64_t)blockIdx.x * kTileWarps + warp) * R;
     const int tile_doubles = rows * T;
@@ -343,9 +344,9 @@ void launch_per_variant(Context &c, ScoreState &s, const Src &src, int64_t n_ite
     c.stats.n_kernel_launches++;
 }
 
-template <int KMAX, int R, int SPL, class Tiles>
+template <int KMAX, bool EXACT, int R, int SPL, class Tiles>
 void launch_tiled_kernel(Context &c, ScoreState &s, const Tiles &tiles, int64_t n_var) {
-    auto kern = score_tiled_kernel<KMAX, R, SPL, Tiles>;
+    auto kern = score_tiled_kernel<KMAX, EXACT, R, SPL, Tiles>;
     const size_t smem = (size_t)2 * s.rows * 32 * SPL * sizeof(double);
     SGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t per_block = (int64_t)kTileWarps * R;
@@ -365,11 +366,15 @@ void launch(Context &c, ScoreState &s, const Tiles &tiles, const Src &src, int64
     s.spa_list.ensure((size_t)n_var);
     SGB_CUDA(cudaMemsetAsync(s.spa_count.get(), 0, sizeof(unsigned int), c.stream));
     c.prof_begin();
-    const int K = s.M.K;
-    if (K <= 4) launch_tiled_kernel<4, 2, 8>(c, s, tiles, n_var);
-    else if (K <= 8) launch_tiled_kernel<8, 2, 8>(c, s, tiles, n_var);
-    else if (K <= 16) launch_tiled_kernel<16, 2, 8>(c, s, tiles, n_var);
-    else launch_tiled_kernel<32, 1, 4>(c, s, tiles, n_var);
+    switch (s.M.K) {   // one variant per warp, 16 warps: the 2K + 2 running sums must leave room for 512 threads per SM
+#define SGB_TILED_EXACT(KX) case KX: launch_tiled_kernel<KX, true, 1, 8>(c, s, tiles, n_var); break
+        SGB_TILED_EXACT(1); SGB_TILED_EXACT(2); SGB_TILED_EXACT(3); SGB_TILED_EXACT(4);
+        SGB_TILED_EXACT(5); SGB_TILED_EXACT(6); SGB_TILED_EXACT(7); SGB_TILED_EXACT(8);
+        SGB_TILED_EXACT(9); SGB_TILED_EXACT(10); SGB_TILED_EXACT(11); SGB_TILED_EXACT(12);
+        SGB_TILED_EXACT(13); SGB_TILED_EXACT(14); SGB_TILED_EXACT(15); SGB_TILED_EXACT(16);
+#undef SGB_TILED_EXACT
+        default: launch_tiled_kernel<32, false, 1, 4>(c, s, tiles, n_var); break;
+    }
     c.prof_end("score_tiled_kernel");
     c.stats.n_kernel_launches++;
     c.d2h(s.h_count.p, s.spa_count.get(), sizeof(unsigned int));
