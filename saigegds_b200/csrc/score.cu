@@ -94,7 +94,7 @@ struct DosageSrc {
 };
 
 template <int KMAX, class Src>
-__global__ void __launch_bounds__(kThreads) score_test_kernel(score::Model M, Src src, int64_t n_var,
+__global__ void __launch_bounds__(kThreads, 2) score_test_kernel(score::Model M, Src src, int64_t n_var,
                                                               const int32_t *__restrict__ list, double *spa,
                                                               unsigned long long *__restrict__ counter,
                                                               double *__restrict__ out, int32_t *__restrict__ valid) {
