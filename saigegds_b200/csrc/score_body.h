@@ -130,6 +130,7 @@ struct Coded {
 template <class Env>
 SGB_HD double Korg(Env &env, double t, int64_t nnz, const double *g, const double *mu) {
     double s = 0;
+#pragma unroll 4
     for (int64_t k = env.tid(); k < nnz; k += env.nthr()) s += log(1 - mu[k] + mu[k] * exp(g[k] * t));
     return env.sum(s);
 }
@@ -142,6 +143,7 @@ SGB_HD double K1_adj(Env &env, double t, int64_t nnz, const double *g, const dou
 template <class Env>
 SGB_HD double K2(Env &env, double t, int64_t nnz, const double *g, const double *mu) {
     double s = 0;
+#pragma unroll 4
     for (int64_t k = env.tid(); k < nnz; k += env.nthr()) {
         const double m = mu[k], om = 1 - m, gi = g[k], e = exp(-gi * t);
         const double v = (om * m * gi * gi * e) / sq(om * e + m);
@@ -155,6 +157,7 @@ SGB_HD double K2(Env &env, double t, int64_t nnz, const double *g, const double 
 template <class Env>
 SGB_HD void K1_K2(Env &env, double t, int64_t nnz, const double *g, const double *mu, double q, double &k1, double &k2) {
     double s1 = 0, s2 = 0;
+#pragma unroll 4   // several (g, mu) pairs in flight: the loop is bound by the latency of these loads otherwise
     for (int64_t k = env.tid(); k < nnz; k += env.nthr()) {
         const double m = mu[k], om = 1 - m, gi = g[k], e = exp(-gi * t);
         const double inv = 1 / (om * e + m), mg = m * gi * inv;
