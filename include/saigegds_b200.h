@@ -206,6 +206,17 @@ int sgb_calc_var_ratio_quant(sgb_context *ctx, const sgb_fit0 *fit0, const doubl
                              const sgb_param *param, const int32_t *marker_list, int64_t n_marker,
                              sgb_var_ratio *out);
 
+/* ---- saige_GxG_snp_bin (saige_fitnull.cpp:1480-1558): the interaction-term test of seqGLMM_GxG_spa -------------- */
+typedef struct {   /* the one-row data.frame returned at :1550-1555 */
+    double beta, SE, pval, p_norm, tau_G;
+    int64_t n_nonzero;
+    int converged;
+} sgb_gxg;
+/* fit0: the glm object (y, linear.predictors, fitted.values, family); tau: glmm$tau; inter_term[n]: the interaction
+ * term; noK: obj.noK (X1, XV, XXVX_inv); param: tolPCG / maxiterPCG are read.  Runs on the stored genotypes. */
+int sgb_GxG_snp_bin(sgb_context *ctx, const sgb_fit0 *fit0, const double tau[2], const double *inter_term,
+                    const sgb_noK *noK, const sgb_param *param, int verbose, sgb_gxg *out);
+
 /* ---- single-variant score test with saddle-point approximation (seqAssocGLMM_SPA's inner loop) ---------------- */
 /* saige_score_test_init (saige_main.cpp:101-155): copies the model to the device.  maf / mac / missing / spa_pval are
  * M$maf, M$mac, M$missing, M$spa.pval; a non-finite value disables that filter (spa_pval: 0.05), as at :106-113. */

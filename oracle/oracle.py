@@ -192,6 +192,23 @@ class Oracle:
         return dict(id=oid[:k].copy(), maf=cols[0][:k].copy(), mac=cols[1][:k].copy(), var1=cols[2][:k].copy(),
                     var2=cols[3][:k].copy(), ratio=cols[4][:k].copy())
 
+    def GxG_snp_bin(self, fit0, tau, inter_term, noK, params=None):
+        """saige_GxG_snp_bin (src/saige_fitnull.cpp:1480-1558) on the stored genotypes."""
+        params = params or default_params()
+        n = len(fit0.y)
+        X1 = np.asfortranarray(noK.X1, dtype=np.float64)
+        XV = np.asfortranarray(noK.XV, dtype=np.float64)
+        XXVX_inv = np.asfortranarray(noK.XXVX_inv, dtype=np.float64)
+        p = X1.shape[1]
+        y, eta, mu, tau, g = _f64(fit0.y), _f64(fit0.linear_predictors), _f64(fit0.fitted_values), _f64(tau), _f64(inter_term)
+        out = np.empty(7)
+        rc = lib().orc_GxG_snp_bin(self.h, C.c_int(FAMILY[fit0.family]), C.c_long(n), C.c_int(p), _p(y), _p(eta), _p(mu), _p(tau),
+                                   _p(g), _p(X1), _p(XV), _p(XXVX_inv), C.byref(params), _p(out))
+        if rc != 0:
+            raise RuntimeError(lib().orc_last_error(self.h).decode())
+        return dict(beta=out[0], SE=out[1], n_nonzero=int(out[2]), pval=out[3], p_norm=out[4], converged=bool(out[5]),
+                    tau_G=out[6])
+
     @property
     def num_products(self):
         return lib().orc_num_products(self.h)

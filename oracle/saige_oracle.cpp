@@ -856,4 +856,47 @@ int orc_calc_var_ratio(void *h, int quant, int family, long n, int p, const doub
     } catch (std::exception &e) { o.last_error = e.what(); return 1; }
 }
 
+
+double orc_qnorm(double p);
+double orc_saddle_prob(double q, double m1, double var1, long n, const double *mu, const double *g, double cutoff,
+                       int *converged, double *p_noadj);
+
+// saige_GxG_snp_bin, saige_fitnull.cpp:1480-1558.  out: beta, SE, n_nonzero, pval, p.norm, converged, tau_G.
+// No golden fixture of the reference covers this routine (parity unpinned for it); its pieces -- W, get_sigma_X, the
+// covariate adjustment, PCG, the adj term, var1/var2 -- are the ones of saige_calc_var_ratio_binary, which is pinned.
+int orc_GxG_snp_bin(void *h, int family, long n, int p, const double *y_, const double *lin_pred, const double *fitted,
+                    const double *tau_, const double *inter_term, const double *X1_, const double *XV_, const double *XXVX_inv_,
+                    const orc_params *pp, double *out) {
+    Oracle &o = *(Oracle *)h;
+    try {
+        const size_t N = n; const double tolPCG = pp->tolPCG; const int maxiterPCG = pp->maxiterPCG;
+        dvec eta(lin_pred, lin_pred + N), mu(fitted, fitted + N), y(y_, y_ + N), W(N);
+        for (size_t i = 0; i < N; i++) { double me = mu_eta1(family, eta[i]); W[i] = me * me / variance1(family, mu[i]); }
+        double tau[2] = {tau_[0], tau_[1]};
+        dmat X1(N, p); memcpy(X1.a.data(), X1_, sizeof(double) * N * p);
+        dmat XV(p, N); memcpy(XV.a.data(), XV_, sizeof(double) * N * p);
+        dmat XXVX_inv(N, p); memcpy(XXVX_inv.a.data(), XXVX_inv_, sizeof(double) * N * p);
+        dmat Sigma_iX = get_sigma_X(o, W, tau, X1, maxiterPCG, tolPCG);
+        dvec G0(inter_term, inter_term + N);
+        int n_nonzero = 0; for (size_t i = 0; i < N; i++) if (G0[i] != 0) n_nonzero++;
+        dvec G = times(XXVX_inv, times(XV, G0));
+        for (size_t i = 0; i < N; i++) G[i] = G0[i] - G[i];
+        dvec Sigma_iG = o.PCG_diag_sigma(W, tau, G, maxiterPCG, tolPCG);
+        dmat Minv = mat_inv(t_times(X1, Sigma_iX));
+        dvec adj = times(Sigma_iX, times(Minv, t_times(X1, Sigma_iG)));
+        double S = 0, s1 = 0, s2 = 0, var2 = 0, q = 0, m1 = 0;
+        for (size_t i = 0; i < N; i++) {
+            S += (y[i] - mu[i]) * G[i]; s1 += G[i] * Sigma_iG[i]; s2 += G[i] * adj[i];
+            var2 += mu[i] * (1 - mu[i]) * G[i] * G[i]; q += y[i] * G[i]; m1 += mu[i] * G[i];
+        }
+        const double var1 = s1 - s2, beta = S / var1, Tstat = q - m1;
+        const double qtilde = Tstat / sqrt(var1) * sqrt(var2) + m1;
+        int converged = 0; double pnorm = 0;
+        const double pval = orc_saddle_prob(qtilde, m1, var2, (long)N, mu.data(), G.data(), 2, &converged, &pnorm);
+        const double SE = fabs(beta / orc_qnorm(pval / 2));
+        out[0] = beta; out[1] = SE; out[2] = n_nonzero; out[3] = pval; out[4] = pnorm; out[5] = converged; out[6] = tau[1];
+        return 0;
+    } catch (std::exception &e) { o.last_error = e.what(); return 1; }
+}
+
 }  // extern "C"

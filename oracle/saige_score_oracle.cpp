@@ -198,6 +198,101 @@ double Saddle_Prob_Fast(double q, double m1, double var1, size_t n_g, const doub
     return pval;
 }
 
+// SPATest.cpp:90-131, the full saddle-point root finder (all samples, no normal part)
+void getroot_K1(double g_pos, double g_neg, double &root, bool &converged, double init, size_t n_g, const double *mu,
+                const double *g, double q) {
+    if (q >= g_pos || q <= g_neg) {
+        root = kInf;
+        converged = true;
+        return;
+    }
+    double t = root = init;
+    double K1_eval = K1_adj(t, n_g, mu, g, q);
+    double prevJump = kInf;
+    converged = false;
+    for (int it = 1; it <= MaxNumIter; it++) {
+        const double K2_eval = K2(t, n_g, mu, g);
+        double tnew = t - K1_eval / K2_eval;
+        if (!std::isfinite(tnew)) break;
+        if (fabs(tnew - t) < root_tol) {
+            converged = true;
+            break;
+        }
+        double newK1 = K1_adj(tnew, n_g, mu, g, q);
+        if (sign(K1_eval) != sign(newK1)) {
+            if (fabs(tnew - t) > prevJump - root_tol) {
+                tnew = t + sign(newK1 - K1_eval) * prevJump * 0.5;
+                newK1 = K1_adj(tnew, n_g, mu, g, q);
+                prevJump *= 0.5;
+            } else {
+                prevJump = fabs(tnew - t);
+            }
+        }
+        root = t = tnew;
+        K1_eval = newK1;
+    }
+}
+
+// SPATest.cpp:185-207
+double get_saddle_prob(double t, size_t n_g, const double *mu, const double *g, double q) {
+    if (!std::isfinite(t)) return 0;
+    const double K = Korg(t, n_g, mu, g);
+    const double k2 = K2(t, n_g, mu, g);
+    double pval = 0;
+    if (std::isfinite(K) && std::isfinite(k2)) {
+        const double w = sign(t) * sqrt(2 * (t * q - K));
+        const double v = t * sqrt(k2);
+        const double z = w + log(v / w) / w;
+        pval = (z > 0) ? pnorm_upper(z) : -pnorm_lower(z);
+    }
+    return pval;
+}
+
+// SPATest.cpp:232-296
+double Saddle_Prob(double q, double m1, double var1, size_t n_g, const double *mu, const double *g, double cutoff,
+                   bool &converged, double *p_noadj) {
+    const double s = q - m1;
+    const double qinv = -s + m1;
+    const double pval_noadj = pchisq1_upper(s * s / var1);
+    double pval;
+    double g_pos = 0, g_neg = 0;
+    bool init = false;
+    if (p_noadj) *p_noadj = pval_noadj;
+    while (true) {
+        converged = true;
+        if (cutoff < 0.1) cutoff = 0.1;
+        if (fabs(q - m1) / sqrt(var1) < cutoff) {
+            pval = pval_noadj;
+        } else {
+            if (!init) {
+                init = true;
+                for (size_t i = 0; i < n_g; i++) {
+                    const double v = g[i];
+                    if (v > 0) g_pos += v; else g_neg += v;
+                }
+            }
+            double root1, root2;
+            bool conv1, conv2;
+            getroot_K1(g_pos, g_neg, root1, conv1, 0, n_g, mu, g, q);
+            getroot_K1(g_pos, g_neg, root2, conv2, 0, n_g, mu, g, qinv);
+            if (conv1 && conv2) {
+                const double p1 = get_saddle_prob(root1, n_g, mu, g, q);
+                const double p2 = get_saddle_prob(root2, n_g, mu, g, qinv);
+                pval = fabs(p1) + fabs(p2);
+            } else {
+                pval = pval_noadj;
+                converged = false;
+                break;
+            }
+        }
+        if (pval != 0 && pval_noadj / pval > 1000)
+            cutoff *= 2;
+        else
+            break;
+    }
+    return pval;
+}
+
 // The model arrays of .init_nullmod (R/assoc_single.r:17-67); all matrices are K x n, column-major (R layout)
 struct Model {
     int trait;  // 0 binary, 1 quantitative
@@ -400,5 +495,14 @@ int orc_score_test(int trait, long n, int K, const double *tau, const double *y,
 }
 
 double orc_qnorm(double p) { return qnorm_as241(p); }
+
+// Saddle_Prob (SPATest.cpp:232-296), used by saige_GxG_snp_bin
+double orc_saddle_prob(double q, double m1, double var1, long n, const double *mu, const double *g, double cutoff,
+                       int *converged, double *p_noadj) {
+    bool conv = false;
+    const double p = Saddle_Prob(q, m1, var1, (size_t)n, mu, g, cutoff, conv, p_noadj);
+    *converged = conv ? 1 : 0;
+    return p;
+}
 
 }  // extern "C"

@@ -70,6 +70,11 @@ class ScoreModel(C.Structure):
                 ("S_a", C.POINTER(C.c_double)), ("var_ratio", C.c_double)]
 
 
+class GxG(C.Structure):
+    _fields_ = [("beta", C.c_double), ("SE", C.c_double), ("pval", C.c_double), ("p_norm", C.c_double),
+                ("tau_G", C.c_double), ("n_nonzero", C.c_int64), ("converged", C.c_int)]
+
+
 class Stats(C.Structure):
     _fields_ = [("n_products", C.c_int64), ("n_product_launches", C.c_int64), ("n_kernel_launches", C.c_int64),
                 ("n_pcg_solves", C.c_int64), ("n_pcg_iterations", C.c_int64), ("last_product_ms", C.c_double)]
@@ -85,7 +90,7 @@ SYMBOLS = [
     "sgb_copy_from_device", "sgb_free_device", "sgb_time_products_device", "sgb_malloc_device", "sgb_copy_to_device",
     "sgb_set_profiling", "sgb_kernel_times", "sgb_malloc_host", "sgb_free_host",
     "sgb_get_sparse", "sgb_store_sp_geno", "sgb_sparse_to_packed",
-    "sgb_score_test_init", "sgb_score_test_packed", "sgb_score_test_dosage", "sgb_score_test_stored", "sgb_score_test_set_path",
+    "sgb_score_test_init", "sgb_score_test_packed", "sgb_score_test_dosage", "sgb_score_test_stored", "sgb_score_test_set_path", "sgb_GxG_snp_bin",
 ]
 
 

@@ -11,6 +11,7 @@ Names, argument meaning and error behaviour follow the reference:
   get_diag_sigma / PCG_diag_sigma (:543, :582)        Context.get_diag_sigma / PCG_diag_sigma
   saige_fit_AI_PCG_binary / _quant (:949, :1103)      Context.saige_fit_AI_PCG_binary / _quant
   saige_calc_var_ratio_binary / _quant (:1255, :1366) Context.saige_calc_var_ratio_binary / _quant
+  saige_GxG_snp_bin          (:1480)                  Context.saige_GxG_snp_bin
   R driver seqFitNullGLMM_SPA (R/saige_main.r:223)    seqFitNullGLMM_SPA
 
 Everything numeric runs in libsaigegds_b200.so on the GPU; this module only marshals numpy arrays
@@ -285,6 +286,25 @@ class Context:
 
     def saige_calc_var_ratio_quant(self, fit0, glmm, noK, param, marker_list):
         return self._var_ratio(L.lib().sgb_calc_var_ratio_quant, fit0, glmm["tau"], noK, param or make_param(), marker_list)
+
+    def saige_GxG_snp_bin(self, fit0, glmm, inter_term, noK: rsetup.ObjNoK, param=None, verbose=False) -> dict:
+        """saige_GxG_snp_bin (src/saige_fitnull.cpp:1480-1558): score test + full saddle-point approximation of one
+        interaction term under the fitted mixed model.  Returns the columns of the reference's one-row data.frame."""
+        n = len(fit0.y)
+        X1, XV, XXVX_inv = _f64(noK.X1, "F"), _f64(noK.XV, "F"), _f64(noK.XXVX_inv, "F")
+        p = X1.shape[1]
+        y, eta, mu, coef = _f64(fit0.y), _f64(fit0.linear_predictors), _f64(fit0.fitted_values), _f64(fit0.coefficients)
+        f = L.Fit0(n, p, _p(y), None, _p(eta), _p(mu), _p(coef), L.FAMILY[fit0.family])
+        nk = L.NoK(p, _p(X1), _p(XV), _p(XXVX_inv))
+        g = _f64(inter_term)
+        if g.shape != (n,):
+            raise L.InvalidArgument(L.SGB_ERR_INVALID, "inter_term must have one value per sample")
+        tau = _f64(glmm["tau"])
+        out = L.GxG()
+        L.check(L.lib().sgb_GxG_snp_bin(self._h, C.byref(f), _p(tau), _p(g), C.byref(nk), C.byref(param or make_param()),
+                                        C.c_int(int(bool(verbose))), C.byref(out)))
+        return {"beta": out.beta, "SE": out.SE, "n_nonzero": int(out.n_nonzero), "pval": out.pval, "p.norm": out.p_norm,
+                "converged": bool(out.converged), "tau_G": out.tau_G}
 
     # ---- R RNG ----
     def set_seed(self, seed: int):

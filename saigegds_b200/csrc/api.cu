@@ -317,6 +317,11 @@ int sgb_calc_var_ratio_quant(sgb_context *ctx, const sgb_fit0 *fit0, const doubl
     return guarded(ctx, [&] { sgb::calc_var_ratio(*ctx, true, fit0, tau, noK, param, marker_list, n_marker, out); });
 }
 
+int sgb_GxG_snp_bin(sgb_context *ctx, const sgb_fit0 *fit0, const double tau[2], const double *inter_term, const sgb_noK *noK,
+                    const sgb_param *param, int verbose, sgb_gxg *out) {
+    return guarded(ctx, [&] { sgb::gxg_snp_bin(*ctx, fit0, tau, inter_term, noK, param, verbose, out); });
+}
+
 int sgb_score_test_init(sgb_context *ctx, const sgb_score_model *model, double maf, double mac, double missing,
                         double spa_pval) {
     return guarded(ctx, [&] { sgb::score_init(*ctx, model, maf, mac, missing, spa_pval); });

@@ -191,6 +191,12 @@ void grm_mv_device(Context &c, const double *b_device, double *out_device, int k
 void score_init(Context &c, const sgb_score_model *m, double maf, double mac, double missing, double spa_pval);
 void score_release(Context &c);
 void score_set_path(Context &c, int path);
+void saddle_prob_dense(Context &c, const double *g_device, const double *mu_device, int64_t n, double q, double m1, double var1,
+                       double cutoff, double *pval, double *p_noadj, bool *converged);   // Saddle_Prob, SPATest.cpp:232-296
+double qnorm_host(double p);   // R's qnorm5 (AS 241)
+// ---- solver.cu: interaction-term test, saige_GxG_snp_bin (saige_fitnull.cpp:1480-1558) ----
+void gxg_snp_bin(Context &c, const sgb_fit0 *f, const double tau[2], const double *inter_term, const sgb_noK *noK,
+                 const sgb_param *P, int verbose, sgb_gxg *out);
 void score_test_packed(Context &c, const uint8_t *packed_host, int64_t nb, int64_t n_var, double *out, int32_t *valid);
 void score_test_dosage(Context &c, const double *dosage_host, int64_t n_var, double *out, int32_t *valid);
 void score_test_stored(Context &c, int64_t first, int64_t n_var, double *out, int32_t *valid, float *kernel_ms);

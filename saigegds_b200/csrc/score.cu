@@ -400,6 +400,51 @@ ScoreState &state(Context &c, int64_t n_var) {
 
 }  // namespace
 
+// Saddle_Prob (SPATest.cpp:232-296) on device vectors g, mu of length n: one block; result[3] = p-value, normal
+// approximation, converged.
+namespace {
+constexpr int kSaddleThreads = 1024;
+__global__ void __launch_bounds__(kSaddleThreads) saddle_dense_kernel(const double *g, const double *mu, int64_t n, double q,
+                                                                      double m1, double var1, double cutoff, double *result) {
+    __shared__ double red[kSaddleThreads / 32];
+    __shared__ int wsum[kSaddleThreads / 32];
+    BlockEnv env{red, wsum};
+    double gp = 0, gn = 0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = g[i];
+        if (v > 0) gp += v; else gn += v;
+    }
+    gp = env.sum(gp);
+    gn = env.sum(gn);
+    bool converged;
+    double p_noadj;
+    const double pval = score::saddle_prob(env, q, m1, var1, gp, gn, n, g, mu, 0.0, 0.0, cutoff, converged, p_noadj);
+    if (threadIdx.x == 0) {
+        result[0] = pval;
+        result[1] = p_noadj;
+        result[2] = converged ? 1.0 : 0.0;
+    }
+}
+}  // namespace
+
+void saddle_prob_dense(Context &c, const double *g_device, const double *mu_device, int64_t n, double q, double m1, double var1,
+                       double cutoff, double *pval, double *p_noadj, bool *converged) {
+    c.red_out.ensure(256);
+    c.prof_begin();
+    saddle_dense_kernel<<<1, kSaddleThreads, 0, c.stream>>>(g_device, mu_device, n, q, m1, var1, cutoff, c.red_out.get());
+    SGB_CHECK_LAUNCH();
+    c.prof_end("saddle_dense_kernel");
+    c.stats.n_kernel_launches++;
+    double h[3];
+    c.d2h(h, c.red_out.get(), sizeof(h));
+    c.sync();
+    *pval = h[0];
+    *p_noadj = h[1];
+    *converged = h[2] != 0;
+}
+
+double qnorm_host(double p) { return score::qnorm_as241(p); }
+
 void score_release(Context &c) {
     delete c.score;
     c.score = nullptr;

@@ -227,6 +227,43 @@ SGB_HD double get_saddle_prob_fast(Env &env, double t, int64_t nnz, const double
     return pval;
 }
 
+// Saddle_Prob_Fast, SPATest.cpp:298-374, after its set-up loop: the two one-sided sums g_pos / g_neg over all samples and
+// the (g, mu) pairs of the samples kept exactly, the rest summarised by the normal part (NAmu, NAsigma).  With every
+// sample kept and NAmu = NAsigma = 0 this is Saddle_Prob, SPATest.cpp:232-296.  p_noadj: the normal-approximation p-value.
+template <class Env>
+SGB_HD double saddle_prob(Env &env, double q, double m1, double var1, double g_pos, double g_neg, int64_t nnz, const double *g,
+                          const double *mu, double NAmu, double NAsigma, double cutoff, bool &converged, double &p_noadj) {
+    const double sdiff = q - m1, qinv = -sdiff + m1;
+    p_noadj = pchisq1_upper(sdiff * sdiff / var1);
+    double pval;
+    while (true) {
+        converged = true;
+        if (cutoff < 0.1) cutoff = 0.1;
+        if (fabs(q - m1) / sqrt(var1) < cutoff) {
+            pval = p_noadj;
+        } else {
+            double root1, root2;
+            bool conv1, conv2;
+            getroot_K1_fast(env, g_pos, g_neg, root1, conv1, nnz, g, mu, q, NAmu, NAsigma);
+            getroot_K1_fast(env, g_pos, g_neg, root2, conv2, nnz, g, mu, qinv, NAmu, NAsigma);
+            if (conv1 && conv2) {
+                const double p1 = get_saddle_prob_fast(env, root1, nnz, g, mu, q, NAmu, NAsigma);
+                const double p2 = get_saddle_prob_fast(env, root2, nnz, g, mu, qinv, NAmu, NAsigma);
+                pval = fabs(p1) + fabs(p2);
+            } else {
+                pval = p_noadj;
+                converged = false;
+                break;
+            }
+        }
+        if (pval != 0 && p_noadj / pval > 1000)
+            cutoff *= 2;
+        else
+            break;
+    }
+    return pval;
+}
+
 // Filters of saige_main.cpp:197-205 / :297-305 from the allele count AC over Num called samples.
 SGB_HD bool variant_passes(const Model &M, double AC, int Num, double &AF, double &mac) {
     AF = (Num > 0) ? (AC / (2 * Num)) : nan_value();
@@ -370,35 +407,9 @@ SGB_HD bool test_variant(Env &env, const Model &M, const Geno &geno, double *spa
         const double NAsigma = svar2 - env.sum(sub_sigma);
         env.sync();   // the compacted pairs are read by other threads from here on
 
-        // Saddle_Prob_Fast, SPATest.cpp:298-374, with (q, m1, var1) = (qtilde, m1, svar2) and cutoff 2
-        const double sdiff = q - m1, qinv = -sdiff + m1;
-        const double p_na = pchisq1_upper(sdiff * sdiff / svar2);
-        double cutoff = 2;
-        while (true) {
-            converged = true;
-            if (cutoff < 0.1) cutoff = 0.1;
-            if (fabs(q - m1) / sqrt(svar2) < cutoff) {
-                pval = p_na;
-            } else {
-                double root1, root2;
-                bool conv1, conv2;
-                getroot_K1_fast(env, g_pos, g_neg, root1, conv1, nnz, spa_g, spa_mu, q, NAmu, NAsigma);
-                getroot_K1_fast(env, g_pos, g_neg, root2, conv2, nnz, spa_g, spa_mu, qinv, NAmu, NAsigma);
-                if (conv1 && conv2) {
-                    const double p1 = get_saddle_prob_fast(env, root1, nnz, spa_g, spa_mu, q, NAmu, NAsigma);
-                    const double p2 = get_saddle_prob_fast(env, root2, nnz, spa_g, spa_mu, qinv, NAmu, NAsigma);
-                    pval = fabs(p1) + fabs(p2);
-                } else {
-                    pval = p_na;
-                    converged = false;
-                    break;
-                }
-            }
-            if (pval != 0 && p_na / pval > 1000)
-                cutoff *= 2;
-            else
-                break;
-        }
+        // Saddle_Prob_Fast with (q, m1, var1) = (qtilde, m1, svar2) and cutoff 2 (saige_main.cpp:386-388)
+        double p_na;
+        pval = saddle_prob(env, q, m1, svar2, g_pos, g_neg, nnz, spa_g, spa_mu, NAmu, NAsigma, 2.0, converged, p_na);
         if (pval == 0 && pval_noadj > 0) {
             pval = pval_noadj;
             converged = false;

@@ -631,4 +631,82 @@ void calc_var_ratio(Context &c, bool quant, const sgb_fit0 *f, const double tau_
     out->n = num_tested;
 }
 
+
+// saige_GxG_snp_bin, saige_fitnull.cpp:1480-1558: score test of one interaction term under the fitted mixed model, with the
+// full saddle-point approximation.  Same building blocks as the variance-ratio markers (W, Sigma^-1 X, covariate
+// adjustment, one PCG solve, the adj term); the saddle-point step runs on the device vectors (saddle_prob_dense).
+void gxg_snp_bin(Context &c, const sgb_fit0 *f, const double tau_in[2], const double *inter_term, const sgb_noK *noK,
+                 const sgb_param *Pin, int verbose, sgb_gxg *out) {
+    c.require_stored();
+    if (!f || !tau_in || !inter_term || !noK || !out) throw Error(SGB_ERR_INVALID, "NULL argument");
+    if (f->n != c.N) throw Error(SGB_ERR_INVALID, "fit0$y length differs from the number of stored samples");
+    const sgb_param P = checked_param(Pin);
+    const int64_t N = c.N;
+    const int p = noK->p;
+    if (p < 1 || p > kMaxCoef - 1) throw Error(SGB_ERR_INVALID, "unsupported number of columns in obj.noK$X1");
+    const double tau[2] = {tau_in[0], tau_in[1]};
+    Solver S(c, N, p, f->family, P);
+    S.init(noK->X1, f->y, nullptr);
+    DevBuf<double> eta, mu, XVt, XXVX_inv, SiX1, G0, G, SiG, adj, wgt;
+    S.upload(eta, f->linear_predictors, N);
+    S.upload(mu, f->fitted_values, N);
+    family_weights(c, f->family, eta.get(), mu.get(), S.W.get());   // :1499-1502
+    std::vector<double> t((size_t)N * p), h(N);
+    for (int64_t i = 0; i < N; i++) for (int j = 0; j < p; j++) t[(size_t)j * N + i] = noK->XV[(size_t)i * p + j];
+    S.upload(XVt, t.data(), t.size());
+    S.upload(XXVX_inv, noK->XXVX_inv, (size_t)N * p);
+    int64_t n_nonzero = 0;
+    for (int64_t i = 0; i < N; i++) {
+        h[i] = f->fitted_values[i] * (1 - f->fitted_values[i]);
+        if (inter_term[i] != 0) n_nonzero++;
+    }
+    S.upload(wgt, h.data(), N);
+    S.upload(G0, inter_term, N);
+    c.sync();
+    // Sigma_iX = get_sigma_X(W, tau, X1)  (:1507)
+    SiX1.ensure((size_t)N * p);
+    pcg_solve(c, S.pcg, S.W.get(), tau[0], tau[1], S.X.get(), p, P.maxiterPCG, P.tolPCG, SiX1.get(), nullptr);
+    // G = G0 - XXVX_inv (XV G0)  (:1521)
+    G.ensure(N); SiG.ensure(N); adj.ensure(N);
+    {
+        hvec d = S.cols_dot(XVt.get(), p, G0.get());
+        for (double &x : d) x = -x;
+        lincomb(c, G.get(), 1.0, G0.get(), XXVX_inv.get(), N, d);
+    }
+    pcg_solve(c, S.pcg, S.W.get(), tau[0], tau[1], G.get(), 1, P.maxiterPCG, P.tolPCG, SiG.get(), nullptr);   // :1525
+    // adj = Sigma_iX mat_inv(X1' Sigma_iX) X1' Sigma_iG  (:1527)
+    {
+        std::vector<const double *> a, b;
+        for (int j = 0; j < p; j++) for (int i = 0; i < p; i++) { a.push_back(S.X.get() + (size_t)i * N); b.push_back(SiX1.get() + (size_t)j * N); }
+        hvec d(a.size());
+        dot_pairs(c, a, b, d.data());
+        hmat XtS(p, p);
+        for (int j = 0; j < p; j++) for (int i = 0; i < p; i++) XtS(i, j) = d[(size_t)j * p + i];
+        hvec coef = matvec(mat_inv(c, XtS), S.cols_dot(S.X.get(), p, SiG.get()));
+        lincomb(c, adj.get(), 0.0, nullptr, SiX1.get(), N, coef);
+    }
+    // :1529-1536
+    double d[4];
+    dot_pairs(c, {S.y.get(), mu.get(), G.get(), G.get()}, {G.get(), G.get(), SiG.get(), adj.get()}, d);
+    double var2 = 0;
+    weighted_sumsq(c, wgt.get(), G.get(), N, 1, &var2);
+    const double q = d[0], m1 = d[1], Tstat = q - m1;
+    const double var1 = d[2] - d[3];
+    const double beta = Tstat / var1;
+    const double qtilde = Tstat / sqrt(var1) * sqrt(var2) + m1;
+    double pval, pnorm;
+    bool converged;
+    saddle_prob_dense(c, G.get(), mu.get(), N, qtilde, m1, var2, 2.0, &pval, &pnorm, &converged);   // :1539-1542
+    out->beta = beta;
+    out->SE = fabs(beta / qnorm_host(pval / 2));
+    out->n_nonzero = n_nonzero;
+    out->pval = pval;
+    out->p_norm = pnorm;
+    out->converged = converged ? 1 : 0;
+    out->tau_G = tau[1];
+    if (verbose)
+        c.printf("    Nonzero #: %lld(%.3g%%), beta: %.6g, SE: %.6g, pval: %.6g, pnorm: %.6g, tau_G: %.5g\n", (long long)n_nonzero,
+                 100.0 * n_nonzero / N, out->beta, out->SE, pval, pnorm, tau[1]);
+}
+
 }  // namespace sgb
