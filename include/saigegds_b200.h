@@ -206,6 +206,21 @@ int sgb_calc_var_ratio_quant(sgb_context *ctx, const sgb_fit0 *fit0, const doubl
                              const sgb_param *param, const int32_t *marker_list, int64_t n_marker,
                              sgb_var_ratio *out);
 
+/* ---- genotype ingestion from a GDS genotype node (device half) -------------------------------------- */
+/* Replaces SeqArray:::.seqGet2bGeno (call site R/saige_main.r:420) and the seqSetFilterCond(maf=, missing.rate=) call at
+ * :319 for integer genotypes.  allele_bits: the decompressed bytes of SeqArray's `genotype/data` node -- bit2 allele
+ * indices [variant][sample][ploidy = 2], four per byte, no padding between variants: sample s of variant v is nibble
+ * v * n_samp_file + s (allele 1 in bits 0-1, allele 2 in bits 2-3; 0 = reference, 1 / 2 = alternative, 3 = missing).
+ * sample_sel (NULL = all): ascending indices of the n_samp samples of the model.  On the device each nibble becomes a 2-bit
+ * alt-allele dosage (missing if either allele is), alleles are counted per variant (integer, order independent), variants
+ * with MAF >= maf and missing rate <= missing_rate are kept (NaN: no filter) and stored like sgb_store_2b_geno.
+ * Outputs: variant_sel[n_variant_file] 0/1, *n_variant = number kept, optional allele counts [n_variant_file],
+ * buf_std_geno [4 * n_variant_file is always enough] and buf_diag_grm [n_samp] as in sgb_store_2b_geno.  One GPU. */
+int sgb_store_gds_geno(sgb_context *ctx, const uint8_t *allele_bits, int64_t n_samp_file, int64_t n_variant_file,
+                       const int32_t *sample_sel, int64_t n_samp, double maf, double missing_rate, int32_t *variant_sel,
+                       int64_t *n_variant, int32_t *n_valid_alleles, int32_t *n_alt_alleles, double *buf_std_geno,
+                       double *buf_diag_grm);
+
 /* ---- saige_GxG_snp_bin (saige_fitnull.cpp:1480-1558): the interaction-term test of seqGLMM_GxG_spa -------------- */
 typedef struct {   /* the one-row data.frame returned at :1550-1555 */
     double beta, SE, pval, p_norm, tau_G;

@@ -90,7 +90,7 @@ SYMBOLS = [
     "sgb_copy_from_device", "sgb_free_device", "sgb_time_products_device", "sgb_malloc_device", "sgb_copy_to_device",
     "sgb_set_profiling", "sgb_kernel_times", "sgb_malloc_host", "sgb_free_host",
     "sgb_get_sparse", "sgb_store_sp_geno", "sgb_sparse_to_packed",
-    "sgb_score_test_init", "sgb_score_test_packed", "sgb_score_test_dosage", "sgb_score_test_stored", "sgb_score_test_set_path", "sgb_GxG_snp_bin",
+    "sgb_score_test_init", "sgb_score_test_packed", "sgb_score_test_dosage", "sgb_score_test_stored", "sgb_score_test_set_path", "sgb_GxG_snp_bin", "sgb_store_gds_geno",
 ]
 
 

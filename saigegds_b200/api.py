@@ -153,6 +153,29 @@ class Context:
         self.n_samp, self.n_var, self.n_var_total, self.var_offset = int(num_samp), m, total, variant_offset
         return lut, diag
 
+    def store_gds_geno(self, allele_bits: np.ndarray, n_samp_file: int, n_variant_file: int, sample_sel=None,
+                       maf=float("nan"), missing_rate=float("nan")):
+        """Genotypes straight from the bytes of a GDS `genotype/data` node (bit2 allele pairs): 2-bit packing, allele
+        counts and the MAF / missing-rate filter of R/saige_main.r:319 run on the device (replaces
+        SeqArray:::.seqGet2bGeno, :420).  Returns dict(variant_sel, n_valid_alleles, n_alt_alleles, lut, diag)."""
+        bits = np.require(allele_bits, dtype=np.uint8, requirements=["C", "A"]).reshape(-1)
+        if bits.size < (int(n_samp_file) * int(n_variant_file) + 1) // 2:
+            raise L.InvalidArgument(L.SGB_ERR_INVALID, "allele_bits is shorter than n_samp_file * n_variant_file nibbles")
+        sel = None if sample_sel is None else np.require(sample_sel, dtype=np.int32, requirements=["C"])
+        n = int(n_samp_file) if sel is None else len(sel)
+        keep = np.zeros(n_variant_file, dtype=np.int32)
+        nv = np.zeros(n_variant_file, dtype=np.int32)
+        na = np.zeros(n_variant_file, dtype=np.int32)
+        lut = np.empty((n_variant_file, 4))
+        diag = np.empty(n)
+        m = C.c_int64(0)
+        L.check(L.lib().sgb_store_gds_geno(self._h, _p(bits, C.c_ubyte), C.c_int64(n_samp_file), C.c_int64(n_variant_file),
+                                           None if sel is None else _p(sel, C.c_int32), C.c_int64(n), C.c_double(maf),
+                                           C.c_double(missing_rate), _p(keep, C.c_int32), C.byref(m), _p(nv, C.c_int32),
+                                           _p(na, C.c_int32), _p(lut), _p(diag)))
+        self.n_samp, self.n_var, self.n_var_total, self.var_offset = n, int(m.value), int(m.value), 0
+        return dict(variant_sel=keep.astype(bool), n_valid_alleles=nv, n_alt_alleles=na, lut=lut[:m.value].copy(), diag=diag)
+
     def store_synthetic(self, n_samp: int, n_variant_local: int, n_variant_total: int | None = None,
                         variant_offset: int = 0, seed: int = 200, missing_rate: float = 0.005, want_outputs=False):
         """Generate the SURVEY section 8(d) synthetic genotypes directly in HBM and store them."""

@@ -1,4 +1,5 @@
 // extern "C" entry points of include/saigegds_b200.h: argument checks, exception -> status code.
+#include <cmath>
 #include <cstring>
 
 #include "sparse_host.h"
@@ -213,6 +214,54 @@ int sgb_store_sp_geno(sgb_context *ctx, const int32_t *sp_data, const int64_t *s
                 double *p = buf_std_geno + 4 * j;
                 p[1] -= p[0]; p[2] -= p[0]; p[3] -= p[0];
             }
+    });
+}
+
+int sgb_store_gds_geno(sgb_context *ctx, const uint8_t *allele_bits, int64_t n_samp_file, int64_t n_variant_file,
+                       const int32_t *sample_sel, int64_t n_samp, double maf, double missing_rate, int32_t *variant_sel,
+                       int64_t *n_variant, int32_t *n_valid_alleles, int32_t *n_alt_alleles, double *buf_std_geno,
+                       double *buf_diag_grm) {
+    return guarded(ctx, [&] {
+        if (!allele_bits || !variant_sel || !n_variant) throw sgb::Error(SGB_ERR_INVALID, "NULL argument");
+        if (n_samp_file < 1 || n_variant_file < 1) throw sgb::Error(SGB_ERR_INVALID, "empty genotype node");
+        if (!sample_sel) n_samp = n_samp_file;
+        if (n_samp < 1 || n_samp > n_samp_file) throw sgb::Error(SGB_ERR_INVALID, "invalid number of selected samples");
+        if (sample_sel)
+            for (int64_t i = 0; i < n_samp; i++)
+                if (sample_sel[i] < 0 || sample_sel[i] >= n_samp_file) throw sgb::Error(SGB_ERR_INVALID, "sample index out of range");
+        if (ctx->world > 1) throw sgb::Error(SGB_ERR_INVALID, "sgb_store_gds_geno stores an unsharded matrix (one GPU)");
+        const int64_t nb = (n_samp + 3) / 4, mf = n_variant_file;
+        sgb::DevBuf<uint8_t> all;
+        sgb::DevBuf<int32_t> d_valid, d_alt;
+        all.ensure((size_t)nb * mf); d_valid.ensure(mf); d_alt.ensure(mf);
+        sgb::gds_to_dosage(*ctx, allele_bits, n_samp_file, mf, sample_sel, n_samp, all.get(), d_valid.get(), d_alt.get());
+        std::vector<int32_t> hv(mf), ha(mf);
+        ctx->d2h(hv.data(), d_valid.get(), sizeof(int32_t) * mf);
+        ctx->d2h(ha.data(), d_alt.get(), sizeof(int32_t) * mf);
+        ctx->sync();
+        // seqSetFilterCond(maf=, missing.rate=) as called at R/saige_main.r:319 -- allele based, integer counts
+        std::vector<int64_t> rows;
+        for (int64_t v = 0; v < mf; v++) {
+            const double af = hv[v] > 0 ? (double)ha[v] / hv[v] : NAN;
+            const double mf_v = std::min(af, 1 - af), miss = 1.0 - (double)hv[v] / (2.0 * n_samp);
+            bool keep = true;
+            if (std::isfinite(maf)) keep = keep && (mf_v >= maf);
+            if (std::isfinite(missing_rate)) keep = keep && (miss <= missing_rate);
+            variant_sel[v] = keep ? 1 : 0;
+            if (keep) rows.push_back(v);
+        }
+        if (n_valid_alleles) memcpy(n_valid_alleles, hv.data(), sizeof(int32_t) * mf);
+        if (n_alt_alleles) memcpy(n_alt_alleles, ha.data(), sizeof(int32_t) * mf);
+        *n_variant = (int64_t)rows.size();
+        if (rows.empty()) throw sgb::Error(SGB_ERR_INVALID, "no variant passes the MAF / missing-rate filter");
+        const int64_t m = (int64_t)rows.size();
+        store_common(*ctx, n_samp, nb, m, m, 0);
+        sgb::DevBuf<uint8_t> raw;
+        raw.ensure((size_t)nb * m);
+        sgb::gather_rows(*ctx, all.get(), rows.data(), m, nb, raw.get());
+        all.release();
+        sgb::store_device_layout(*ctx, raw.get(), (size_t)nb);
+        store_outputs(*ctx, buf_std_geno, buf_diag_grm);
     });
 }
 

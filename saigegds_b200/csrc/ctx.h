@@ -177,6 +177,11 @@ void store_device_layout(Context &c, const uint8_t *src_device, size_t src_pitch
 void decode_variant(Context &c, int64_t local_idx, double *out_device);             // get_geno_ds, missing -> NaN
 void synth_geno(Context &c, int64_t n_samp, int64_t m_local, int64_t var_offset, uint64_t seed, double miss,
                 uint8_t *out_device);
+// GDS genotype/data block (bit2 allele pairs) -> 2-bit dosage rows [m_file][ceil(N/4)] + per-variant allele counts
+void gds_to_dosage(Context &c, const uint8_t *bits_host, int64_t n_file, int64_t m_file, const int32_t *sample_sel_host,
+                   int64_t N, uint8_t *packed_device, int32_t *n_valid_alleles_device, int32_t *n_alt_alleles_device);
+void gather_rows(Context &c, const uint8_t *src_device, const int64_t *rows_host, int64_t n_rows, int64_t NB,
+                 uint8_t *dst_device);
 // ---- grm_simt.cu ----
 void simt_table_apply(Context &c, const double *tab_device, double *out_device, double scale);
 void simt_grm_mv(Context &c, const double *b_device, double *out_device);  // local shard, scaled by 1/M_total

@@ -7,6 +7,8 @@
 // rewritten to code 3 (missing), whose standardised value is 0, so product kernels never need a
 // tail branch.  The reference's allele counts sweep the raw pad bits (:188-192), so the counts are
 // taken from the raw bytes BEFORE that rewrite -- they are bit-exact with the reference.
+#include <algorithm>
+
 #include "ctx.h"
 
 namespace sgb {
@@ -131,7 +133,100 @@ __global__ void synth_kernel(uint8_t *__restrict__ out, int64_t N, int64_t NB, i
     }
 }
 
+// GDS genotype/data (bit2 allele indices, [variant][sample][ploidy 2], no row padding) -> 2-bit alt-allele dosage rows.
+// One nibble per sample: allele 1 in bits 0-1, allele 2 in bits 2-3; 0 = reference, 1/2 = an alternative allele,
+// 3 = missing.  nib0: nibble index of (first variant of the slab, sample 0) relative to `bits`.  One thread per output
+// byte; per-variant allele counts (all integer) by warp reduction + integer atomics, so they do not depend on the order.
+__global__ void gds_to_dosage_kernel(const uint8_t *__restrict__ bits, int64_t nib0, int64_t n_file,
+                                     const int32_t *__restrict__ sample_sel, int64_t N, int64_t NB, uint8_t *__restrict__ out,
+                                     int32_t *__restrict__ n_valid_alleles, int32_t *__restrict__ n_alt_alleles) {
+    const int64_t v = blockIdx.y;
+    const int64_t base = nib0 + v * n_file;
+    int valid = 0, alt = 0;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < NB; j += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t byte = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t smp = 4 * j + k;
+            uint32_t code = 3;
+            if (smp < N) {
+                const int64_t idx = base + (sample_sel ? (int64_t)sample_sel[smp] : smp);
+                const uint32_t nib = (bits[idx >> 1] >> (4 * (int)(idx & 1))) & 15u;
+                const uint32_t a0 = nib & 3u, a1 = nib >> 2;
+                valid += (a0 != 3u) + (a1 != 3u);
+                alt += (a0 == 1u || a0 == 2u) + (a1 == 1u || a1 == 2u);
+                code = (a0 == 3u || a1 == 3u) ? 3u : (uint32_t)(a0 != 0u) + (uint32_t)(a1 != 0u);
+            }
+            byte |= code << (2 * k);
+        }
+        out[(size_t)v * NB + j] = (uint8_t)byte;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        valid += __shfl_xor_sync(0xffffffffu, valid, o);
+        alt += __shfl_xor_sync(0xffffffffu, alt, o);
+    }
+    if ((threadIdx.x & 31) == 0 && (valid | alt)) {
+        atomicAdd(&n_valid_alleles[v], valid);
+        atomicAdd(&n_alt_alleles[v], alt);
+    }
+}
+
+// dst row r = src row rows[r]
+__global__ void gather_rows_kernel(const uint8_t *__restrict__ src, const int64_t *__restrict__ rows, int64_t NB,
+                                   uint8_t *__restrict__ dst) {
+    const int64_t r = blockIdx.y, sr = rows[r];
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < NB; j += (int64_t)gridDim.x * blockDim.x)
+        dst[(size_t)r * NB + j] = src[(size_t)sr * NB + j];
+}
+
 }  // namespace
+
+void gds_to_dosage(Context &c, const uint8_t *bits_host, int64_t n_file, int64_t m_file, const int32_t *sample_sel_host,
+                   int64_t N, uint8_t *packed_device, int32_t *n_valid_alleles_device, int32_t *n_alt_alleles_device) {
+    const int64_t NB = (N + 3) / 4;
+    DevBuf<int32_t> sel;
+    if (sample_sel_host) {
+        sel.ensure((size_t)N);
+        c.h2d(sel.get(), sample_sel_host, sizeof(int32_t) * N);
+    }
+    SGB_CUDA(cudaMemsetAsync(n_valid_alleles_device, 0, sizeof(int32_t) * m_file, c.stream));
+    SGB_CUDA(cudaMemsetAsync(n_alt_alleles_device, 0, sizeof(int32_t) * m_file, c.stream));
+    // slabs of an even number of variants (a slab then starts on a byte boundary even when n_file is odd), <= ~256 MB
+    int64_t slab = std::max<int64_t>(2, (((int64_t)512 << 20) / std::max<int64_t>(1, n_file)) & ~(int64_t)1);
+    slab = std::min<int64_t>(slab, 32768);            // grid.y limit
+    DevBuf<uint8_t> stage;
+    stage.ensure((size_t)((slab * n_file + 1) / 2 + 1));
+    for (int64_t v0 = 0; v0 < m_file; v0 += slab) {
+        const int64_t mv = std::min(slab, m_file - v0);
+        const int64_t nib_first = v0 * n_file, nib_last = (v0 + mv) * n_file;     // nib_first is even
+        const int64_t byte0 = nib_first >> 1, bytes = ((nib_last + 1) >> 1) - byte0;
+        c.h2d(stage.get(), bits_host + byte0, (size_t)bytes);
+        dim3 grid((unsigned)std::min<int64_t>((NB + 255) / 256, 64), (unsigned)mv);
+        gds_to_dosage_kernel<<<grid, 256, 0, c.stream>>>(stage.get(), 0, n_file, sample_sel_host ? sel.get() : nullptr, N, NB,
+                                                         packed_device + (size_t)v0 * NB, n_valid_alleles_device + v0,
+                                                         n_alt_alleles_device + v0);
+        SGB_CHECK_LAUNCH();
+        c.stats.n_kernel_launches++;
+        c.sync();   // the staging buffer is reused by the next slab
+    }
+}
+
+void gather_rows(Context &c, const uint8_t *src_device, const int64_t *rows_host, int64_t n_rows, int64_t NB,
+                 uint8_t *dst_device) {
+    if (n_rows == 0) return;
+    DevBuf<int64_t> rows;
+    rows.ensure((size_t)n_rows);
+    c.h2d(rows.get(), rows_host, sizeof(int64_t) * n_rows);
+    const int64_t slab = 32768;
+    for (int64_t r0 = 0; r0 < n_rows; r0 += slab) {
+        const int64_t mr = std::min(slab, n_rows - r0);
+        dim3 grid((unsigned)std::min<int64_t>((NB + 255) / 256, 64), (unsigned)mr);
+        gather_rows_kernel<<<grid, 256, 0, c.stream>>>(src_device, rows.get() + r0, NB, dst_device + (size_t)r0 * NB);
+        SGB_CHECK_LAUNCH();
+        c.stats.n_kernel_launches++;
+    }
+    c.sync();
+}
 
 void store_device_layout(Context &c, const uint8_t *src, size_t src_pitch) {
     const int64_t M = c.M, N = c.N, NB = c.NB;
