@@ -48,7 +48,7 @@ def xz_streams(buf):
         pos += 1
 
 
-def read_genotypes(path, n_var=10000, n_samp=1000):
+def read_genotypes(path, n_var=10000, n_samp=1000, want_raw=False):
     buf = open(path, "rb").read()
     streams = list(xz_streams(buf))
     want = n_var * n_samp * 2 // 4
@@ -67,6 +67,8 @@ def read_genotypes(path, n_var=10000, n_samp=1000):
     b = np.frombuffer(raw, dtype=np.uint8)
     vals = np.stack([(b >> s) & 3 for s in (0, 2, 4, 6)], axis=1).reshape(-1)
     alleles = vals.reshape(n_var, n_samp, 2)
+    if want_raw:
+        return alleles, offs, b
     return alleles, offs
 
 

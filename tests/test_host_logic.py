@@ -113,3 +113,26 @@ def test_sharded_product_equals_full_product_gloo(tmp_path):
     outs = [p.communicate(timeout=300)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_fixture_gds_bytes_are_what_store_gds_geno_takes(fx):
+    """The decompressed `genotype/data` bytes of the reference's own GDS file, read the way sgb_store_gds_geno reads them
+    (one nibble per sample, allele 1 in bits 0-1, allele 2 in bits 2-3, no row padding; csrc/store.cu gds_to_dosage_kernel),
+    give the committed 2-bit matrix and the golden variant filter.  Needs /root/reference (build container only)."""
+    path = "/root/reference/inst/extdata/grm1k_10k_snp.gds"
+    if not os.path.exists(path):
+        pytest.skip("the reference tree is not present on this machine")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden import read_genotypes
+    _, _, raw = read_genotypes(path, want_raw=True)
+    n, m = fx.n_samp, len(fx.packed_all)
+    assert raw.size == (n * m + 1) // 2
+    nib = np.stack([raw & 15, raw >> 4], axis=1).reshape(-1)[:n * m].reshape(m, n)
+    a0, a1 = nib & 3, nib >> 2
+    code = np.where((a0 == 3) | (a1 == 3), 3, (a0 != 0).astype(np.uint8) + (a1 != 0)).astype(np.uint8)
+    want = np.stack([(fx.packed_all >> s) & 3 for s in (0, 2, 4, 6)], axis=2).reshape(m, -1)[:, :n]
+    assert np.array_equal(code, want)
+    valid = (a0 != 3).sum(axis=1) + (a1 != 3).sum(axis=1)
+    alt = ((a0 == 1) | (a0 == 2)).sum(axis=1) + ((a1 == 1) | (a1 == 2)).sum(axis=1)
+    af = alt / valid
+    assert np.array_equal(np.minimum(af, 1 - af) >= 0.005, fx.keep)          # seqSetFilterCond(maf=0.005), R/saige_main.r:319
