@@ -230,3 +230,36 @@ def test_gpu_fit_then_gpu_scan_matches_golden_pvalues(gpu, fx):
     assert np.array_equal(ans["id"], pv["id"])
     assert relmax(ans["pval"], pv["pval"]) < 1e-6
     assert relmax(ans["beta"], pv["beta"]) < 1e-6
+
+
+def synthetic_model(rng, n, K, trait):
+    """A self-consistent null model with K fixed-effect columns (what .init_nullmod would hand over)."""
+    from oracle import oracle as orc
+    X = np.column_stack([np.ones(n)] + [rng.standard_normal(n) for _ in range(K - 1)])
+    beta = np.concatenate([[-1.0], rng.normal(0, 0.15, K - 1)])
+    if trait == "binary":
+        mu = 1 / (1 + np.exp(-(X @ beta)))
+        y = (rng.random(n) < mu).astype(np.float64)
+        V = mu * (1 - mu) * rng.uniform(0.9, 1.1, n)          # the glm's V differs slightly from the mixed model's mu(1-mu)
+    else:
+        mu = X @ beta
+        y = mu + rng.standard_normal(n)
+        V = np.ones(n)
+    XVX_inv = np.linalg.inv(X.T @ (X * V[:, None]))
+    return orc.init_nullmod(trait, y, mu, X, (X * V[:, None]).T.copy(), X @ XVX_inv, V, np.array([1.0, 0.4]))
+
+
+@pytest.mark.parametrize("trait", ["binary", "quantitative"])
+@pytest.mark.parametrize("K", [1, 8, 17, 32])
+def test_device_body_matches_oracle_for_other_covariate_counts(body, trait, K):
+    """The fixture has K = 3; the single-pass algebra must hold for any K (1 = intercept only, > 16 = the guarded kernels)."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(100 + K)
+    n = 700
+    m = synthetic_model(rng, n, K, trait)
+    d = random_dosages(rng, n, 200, integer=True)
+    kw = dict(maf=0.002, mac=2.0, missing=0.35, spa_pval=0.3)
+    ref = orc.score_test(m, d, 0.9, **kw)
+    assert ref["valid"].sum() > 100
+    compare(body(m, 0.9, d, **kw), ref, 1e-8)
+    compare(body(m, 0.9, pack(d), **kw), ref, 1e-8)
