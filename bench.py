@@ -386,6 +386,110 @@ def run_fit(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------ association scan
+ASSOC_K = 10           # fixed-effect columns (intercept + 9 covariates)
+
+
+def assoc_null_model(n, K=ASSOC_K, seed=7):
+    """A self-consistent binary null model on synthetic covariates (what seqFitNullGLMM_SPA would hand over); the phenotype is
+    drawn under the null, so ~5 % of the variants take the saddle-point branch."""
+    import saigegds_b200 as sg
+    from saigegds_b200 import rsetup
+    rng = np.random.default_rng(seed)
+    X = np.column_stack([np.ones(n)] + [rng.standard_normal(n) for _ in range(K - 1)])
+    beta = np.concatenate([[-2.0], rng.normal(0, 0.2, K - 1)])
+    mu = 1 / (1 + np.exp(-(X @ beta)))
+    y = (rng.random(n) < mu).astype(np.float64)
+    V = mu * (1 - mu)
+    XVX_inv = np.linalg.inv(X.T @ (X * V[:, None]))
+    noK = rsetup.ObjNoK(y=y, mu=mu, res=y - mu, V=V, X1=X, XV=(X * V[:, None]).T.copy(), XXVX_inv=X @ XVX_inv)
+    return sg.NullModel(coefficients=beta, tau=np.array([1.0, 0.3]), linear_predictors=X @ beta, fitted_values=mu,
+                        residuals=y - mu, cov=XVX_inv, converged=True, obj_noK=noK, var_ratio={"ratio": np.array([1.0])},
+                        trait_type="binary")
+
+
+def cpu_assoc_rate(n, m_sample):
+    """The oracle's score test + SPA (= the reference's algorithm, src/saige_main.cpp:288-407) on all host cores."""
+    from oracle import oracle as orc
+    orc.build()
+    mod = assoc_null_model(n)
+    noK = mod.obj_noK
+    m = orc.init_nullmod("binary", noK.y, mod.fitted_values, noK.X1, noK.XV, noK.XXVX_inv, noK.V, mod.tau)
+    packed = numpy_packed_sample(n, m_sample)
+    d = np.stack([(packed >> s) & 3 for s in (0, 2, 4, 6)], axis=2).reshape(m_sample, -1)[:, :n].astype(np.float64)
+    d[d == 3] = np.nan
+    t0 = time.perf_counter()
+    orc.score_test(m, d, 1.0)
+    dt = time.perf_counter() - t0
+    return dict(value=m_sample / dt, unit="variants/s", cores=orc.max_threads(), kind="port",
+                sample="%d variants x %d samples, K=%d, one timed pass of %.2f s (includes one copy of the dosage block)"
+                       % (m_sample, n, ASSOC_K, dt))
+
+
+def run_assoc(args):
+    """Single-variant score test + SPA scan (seqAssocGLMM_SPA's inner loop) at N = 430K, K = 10, one GPU: variants per second
+    with the genotypes resident in HBM (`value`) and from packed host batches (`e2e`)."""
+    import saigegds_b200 as sg
+    n, m = N_SAMP, args.assoc_m
+    config = {"workload": "synthetic N=%d samples, %d variants, K=%d covariates, binary trait under the null, "
+                          "maf~U(0.005,0.5), 0.5%% missing: score test + SPA per variant" % (n, m, ASSOC_K),
+              "n_samp": n, "n_var": m, "K": ASSOC_K}
+    if args.impl == "reference":
+        cb = cpu_assoc_rate(n, args.assoc_cpu_m)
+        print(json.dumps({"impl": "reference", "metric": "association_variants_per_s", "value": cb["value"],
+                          "unit": "variants/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "higher_is_better": True,
+                          "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": cb, "gpu_launches": 0,
+                          "e2e": {"value": cb["value"], "unit": "variants/s", "h2d_bytes_per_step": 0,
+                                  "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    ctx = sg.Context(0)
+    ctx.store_synthetic(n, m, seed=200, missing_rate=MISSING)
+    st = sg.ScoreTest(sg.init_nullmod(assoc_null_model(n)), ctx)
+    for _ in range(max(1, args.warmup)):
+        st.test_stored(0, min(m, 512))
+    mon = ClockSampler(0)
+    mon.start()
+    ctx.reset_stats()
+    times = []
+    for _ in range(max(1, min(args.steps, 20))):
+        res, ms = st.test_stored(0, m)
+        times.append(ms)
+    launches = ctx.stats()["n_kernel_launches"]
+    host = ctx.synth_to_host(n, m)
+    t0 = time.perf_counter()
+    res_h = st.test(host)
+    e2e_s = time.perf_counter() - t0
+    clocks = mon.stop()
+    assert all(np.array_equal(res[k], res_h[k], equal_nan=True) for k in res)
+    ctx.set_profiling(True)
+    st.test_stored(0, m)
+    kt = ctx.kernel_times()
+    ctx.set_profiling(False)
+    ms = float(np.mean(times))
+    # the kernel that bounds the scan reads n (2K + 2) doubles of model values per variant from shared memory
+    smem_bytes = float(n) * (2 * ASSOC_K + 2) * 8 * m
+    smem_peak = 148 * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9          # GB/s: 128 B/clk/SM
+    tiled_ms = kt.get("score_tiled_kernel", (ms, 1))[0]
+    line = {"metric": "association_variants_per_s", "value": m / (ms * 1e-3), "unit": "variants/s", "n_gpus": 1,
+            "steps": len(times), "warmup": max(1, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": m / e2e_s, "unit": "variants/s", "h2d_bytes_per_step": int(host.nbytes),
+                    "d2h_bytes_per_step": int(m * 8 * 8 + m * 4),
+                    "note": "ScoreTest.test on packed host batches (sgb_score_test_packed): copy in, both kernels, copy out"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "shared-memory", "kernel": "score_tiled_kernel", "achieved": smem_bytes / (tiled_ms * 1e-3) / 1e9,
+                         "peak": smem_peak, "unit": "GB/s", "frac": smem_bytes / (tiled_ms * 1e-3) / 1e9 / smem_peak,
+                         "traffic": None, "peak_source": "148 SMs x 128 B/clk x SM clock under load",
+                         "note": "algorithmic shared-memory bytes = n (2K+2) 8 B per variant; the packed genotypes "
+                                 "(n/4 B per variant from HBM) are 0.1 % of that",
+                         "kernels": {k: {"ms": v[0], "launches": v[1]} for k, v in kt.items()}},
+            "spa_adjusted": int(np.sum(res["pval"][res["valid"]] != res["p.norm"][res["valid"]])),
+            "valid": int(res["valid"].sum())}
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_assoc_rate(n, args.assoc_cpu_m)
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -394,13 +498,18 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", default=None, choices=[None, "auto", "simt", "imma", "imma2"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--mode", default="product", choices=["product", "fit"],
-                    help="product: the headline metric; fit: null-model fit wall time (secondary metric)")
+    ap.add_argument("--mode", default="product", choices=["product", "fit", "assoc"],
+                    help="product: the headline metric; fit: null-model fit wall time; assoc: score test + SPA scan "
+                         "(secondary metrics)")
+    ap.add_argument("--assoc-m", type=int, default=9472, help="variants in the association-scan benchmark")
+    ap.add_argument("--assoc-cpu-m", type=int, default=192, help="variants the CPU arm of --mode assoc times")
     ap.add_argument("--fit-n", type=int, default=50000)
     ap.add_argument("--fit-m", type=int, default=100000)
     ap.add_argument("--fit-traits", default="binary,quantitative")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.mode == "assoc":
+        run_assoc(args)
+    elif args.impl == "reference":
         run_reference(args)
     elif args.mode == "fit":
         run_fit(args)
