@@ -42,7 +42,7 @@ enum { SGB_FAMILY_BINOMIAL = 0, SGB_FAMILY_GAUSSIAN = 1 };
 
 /* Product kernels selectable at run time (debug / measurement); default SGB_KERNEL_AUTO. */
 enum { SGB_KERNEL_AUTO = 0, SGB_KERNEL_SIMT = 1, SGB_KERNEL_IMMA = 2 /* fused single pass if possible */,
-       SGB_KERNEL_IMMA_TWOPASS = 3 };
+       SGB_KERNEL_IMMA_TWOPASS = 3, SGB_KERNEL_UMMA = 4 /* batched tcgen05 path even for one column */ };
 
 /* The `param` list built at R/saige_main.r:442-453 and read at saige_fitnull.cpp:954-966. */
 typedef struct {

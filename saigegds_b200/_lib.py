@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 
 SGB_OK, SGB_ERR_INVALID, SGB_ERR_CUDA, SGB_ERR_OVERFLOW, SGB_ERR_COMM, SGB_ERR_STATE = range(6)
 FAMILY = {"binomial": 0, "gaussian": 1}
-KERNEL = {"auto": 0, "simt": 1, "imma": 2, "imma2": 3}
+KERNEL = {"auto": 0, "simt": 1, "imma": 2, "imma2": 3, "umma": 4}
 
 
 class SgbError(RuntimeError):

@@ -107,7 +107,7 @@ int sgb_set_callbacks(sgb_context *ctx, void (*print_fn)(const char *),
 
 int sgb_set_kernel(sgb_context *ctx, int kernel) {
     return guarded(ctx, [&] {
-        if (kernel < SGB_KERNEL_AUTO || kernel > SGB_KERNEL_IMMA_TWOPASS) throw sgb::Error(SGB_ERR_INVALID, "unknown kernel id");
+        if (kernel < SGB_KERNEL_AUTO || kernel > SGB_KERNEL_UMMA) throw sgb::Error(SGB_ERR_INVALID, "unknown kernel id");
         ctx->kernel = kernel;
     });
 }

@@ -66,6 +66,8 @@ struct ImmaPlan {
     // [k][lane] of 16-bit offsets padded to the longest row of the group with kSpTile (a zero slot of the vector tile)
     DevBuf<int64_t> mv_gstart, ms_gstart;   // [n_tiles * n_groups + 1] block starts (entries, multiples of 32)
     DevBuf<uint16_t> mv_ell, ms_ell;
+    int um_gather_cols = 8;  // batched path: more columns than this take the row-gather sparse kernel (env SGB_UMMA_GATHER_COLS)
+    int um_min_cols = 2;     // AUTO: batched tcgen05 path from this many columns (env SGB_UMMA_MIN_COLS; 0 disables)
     bool use_csr = false;    // env SGB_SPARSE_CSR: the older row-per-thread kernel (comparison only)
     int n_stiles = 0, n_vtiles = 0;
     int opt_fork = 1, opt_fork_fused = -1, opt_grid_mult = 2, opt_stages = 3;   // tuning knobs (env: SGB_SPARSE_FORK, SGB_SPARSE_GRID_MULT, SGB_DOTS_STAGES)
@@ -95,6 +97,26 @@ struct ImmaPlan {
     DevBuf<double> scal;     // [16] device scalars
     DevBuf<double> red;      // reduction partials
     DevBuf<unsigned int> counter;
+    // batched K-RHS product on tcgen05 (grm_umma.cuh); prepared lazily by the first multi-column product
+    struct Umma {
+        bool ready = false, failed = false;
+        DevBuf<uint8_t> pt;              // sample-major copy of the packed matrix [N][pitch_t]
+        size_t pitch_t = 0;
+        int64_t cpad_a = 0, cpad_b = 0;  // contraction capacity of phase A (samples) / phase B (variants), multiples of 512
+        int boxes_a = 0, boxes_b = 0, split_a = 1, split_b = 1;
+        DevBuf<int8_t> db, de;           // digit matrices [224][cpad]
+        DevBuf<unsigned long long> t_lo, t_hi, r_lo, r_hi;   // exact limbs [32][M], [32][N]
+        DevBuf<double> e, hm, u, corr;   // [32][M], [32][M], [32][M], [32][N]
+        DevBuf<double> part;             // sparse partial sums of one column chunk: [4][tiles][rows]
+        DevBuf<double> vt;               // transposed vector block [max(N, M)][32] of the row-gather kernel
+        DevBuf<double> scal, red;
+        DevBuf<unsigned int> counter;
+        DevBuf<int> err;
+        DevBuf<long long> prof;
+        PinBuf<int> herr;
+        CUtensorMap tmap_p, tmap_pt, tmap_db[15], tmap_de[15];
+        bool have_d[15] = {false};
+    } um;
 };
 
 namespace {
@@ -981,6 +1003,7 @@ __global__ void miss_by_sample_kernel(const uint8_t *__restrict__ packed, size_t
 }
 
 #include "grm_fused.cuh"
+#include "grm_umma.cuh"
 
 int pick_split(int64_t tiles, int slots, int max_split) {
     int best = 1;
@@ -1009,6 +1032,242 @@ void launch_sparse(Context &c, ImmaPlan *p, bool by_variant, const double *vec, 
                                                                   part);
     }
     SGB_CHECK_LAUNCH();
+}
+
+
+// ---- batched K-RHS product: host side (grm_umma.cuh) -----------------------------------------------------------------------
+CUresult encode_tmap_2d(CUtensorMap *tm, const void *base, uint64_t inner_bytes, uint64_t rows, uint64_t stride_bytes, uint32_t box_inner,
+                        uint32_t box_rows, CUtensorMapSwizzle swz) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                 CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        SGB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres));
+        if (!f || qres != cudaDriverEntryPointSuccess) throw Error(SGB_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+        fn = (EncodeFn)f;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)inner_bytes, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)stride_bytes};
+    const cuuint32_t box[2] = {box_inner, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+// out[c][r] = sum over tiles of part[c][t][r] (fixed order).  grid (ceil(R / 256), ncols)
+__global__ void sum_tiles_multi_kernel(const double *__restrict__ part, int n_tiles, int64_t R, double *__restrict__ out, int64_t ldo) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const int c = blockIdx.y;
+    double s = 0;
+    for (int t = 0; t < n_tiles; t++) s += part[((size_t)c * n_tiles + t) * R + r];
+    out[(size_t)c * ldo + r] = s;
+}
+
+// split of the contraction range: fewest estimated "box times" (a CTA costs ~2 boxes of fixed overhead), int32 accumulators safe
+int umma_pick_split(int64_t row_blocks, int boxes, int sms) {
+    int best = 1;
+    double best_t = 1e300;
+    for (int s = 1; s <= 32 && s <= boxes; s++) {
+        const int per = (boxes + s - 1) / s;
+        const int64_t units = row_blocks * ((boxes + per - 1) / per);
+        const double t = (double)((units + sms - 1) / sms) * (per + 2.0);
+        if (t < best_t * 0.97) { best_t = t; best = s; }
+    }
+    while ((int64_t)((boxes + best - 1) / best) * kUBoxElems * 192 >= (1ll << 31)) best++;
+    return best;
+}
+
+void umma_prepare(Context &c, ImmaPlan *p) {
+    ImmaPlan::Umma &u = p->um;
+    if (u.ready || u.failed) return;
+    const int64_t M = c.M, N = c.N;
+    try {
+        u.pitch_t = (size_t)(((M + 3) / 4 + 255) / 256) * 256;
+        u.cpad_a = (int64_t)c.pitch * 4;
+        u.cpad_b = (int64_t)u.pitch_t * 4;
+        u.boxes_a = (int)((N + kUBoxElems - 1) / kUBoxElems);
+        u.boxes_b = (int)((M + kUBoxElems - 1) / kUBoxElems);
+        u.pt.ensure((size_t)N * u.pitch_t);
+        transpose_2bit_kernel<<<dim3((unsigned)(c.pitch / 128), (unsigned)((M + 127) / 128)), 512, 0, c.stream>>>(c.packed.get(), c.pitch, M, N,
+                                                                                                        u.pt.get(), u.pitch_t);
+        SGB_CHECK_LAUNCH();
+        c.stats.n_kernel_launches++;
+        u.db.ensure((size_t)kUMaxN * u.cpad_a);
+        u.de.ensure((size_t)kUMaxN * u.cpad_b);
+        SGB_CUDA(cudaMemsetAsync(u.db.get(), 0, (size_t)kUMaxN * u.cpad_a, c.stream));
+        SGB_CUDA(cudaMemsetAsync(u.de.get(), 0, (size_t)kUMaxN * u.cpad_b, c.stream));
+        u.t_lo.ensure((size_t)kUMaxCols * M); u.t_hi.ensure((size_t)kUMaxCols * M);
+        u.r_lo.ensure((size_t)kUMaxCols * N); u.r_hi.ensure((size_t)kUMaxCols * N);
+        u.e.ensure((size_t)kUMaxCols * M); u.hm.ensure((size_t)kUMaxCols * M); u.u.ensure((size_t)kUMaxCols * M);
+        u.corr.ensure((size_t)kUMaxCols * N);
+        u.part.ensure((size_t)4 * std::max((size_t)p->n_stiles * M, (size_t)p->n_vtiles * N));
+        u.vt.ensure((size_t)32 * std::max(M, N));
+        u.scal.ensure((size_t)kUMaxCols * kUScal);
+        u.red.ensure((size_t)kUMaxCols * 2 * 1024);
+        u.counter.ensure(kUMaxCols);
+        u.err.ensure(1);
+        u.herr.ensure(1);
+        *u.herr.p = 0;
+        SGB_CUDA(cudaMemsetAsync(u.counter.get(), 0, sizeof(unsigned int) * kUMaxCols, c.stream));
+        SGB_CUDA(cudaMemsetAsync(u.err.get(), 0, sizeof(int), c.stream));
+        CUresult r = encode_tmap_2d(&u.tmap_p, c.packed.get(), c.pitch, (uint64_t)M, c.pitch, kUBoxBytes, kURows, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (r == CUDA_SUCCESS)
+            r = encode_tmap_2d(&u.tmap_pt, u.pt.get(), u.pitch_t, (uint64_t)N, u.pitch_t, kUBoxBytes, kURows, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (r != CUDA_SUCCESS) throw Error(SGB_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+        SGB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmemBytes));
+        SGB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmemBytes));
+        SGB_CUDA(cudaFuncSetAttribute(sparse_ell_multi_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, em_smem<4>()));
+        SGB_CUDA(cudaFuncSetAttribute(sparse_ell_multi_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, em_smem<2>()));
+        u.split_a = umma_pick_split((M + kURows - 1) / kURows, u.boxes_a, c.sm_count);
+        u.split_b = umma_pick_split((N + kURows - 1) / kURows, u.boxes_b, c.sm_count);
+        if (const char *e = getenv("SGB_UMMA_SPLIT_A")) u.split_a = std::max(1, atoi(e));
+        if (const char *e = getenv("SGB_UMMA_SPLIT_B")) u.split_b = std::max(1, atoi(e));
+        c.sync();
+        u.ready = true;
+    } catch (const Error &e) {
+        // e.g. no room for the second orientation of the packed matrix: multi-column products stay on the single-RHS kernels
+        cudaGetLastError();
+        u.failed = true;
+        u.pt.release(); u.db.release(); u.de.release(); u.part.release();
+        c.printf("note: batched tensor-core product unavailable (%s); using the single-RHS kernels per column\n", e.what());
+    }
+}
+
+// multi-column missing-genotype sums into out[c][row] (rows = variants gathering b, or samples gathering hm)
+void launch_sparse_multi(Context &c, ImmaPlan *p, bool by_variant, const double *vec, int64_t ldv, int ncols, double *out, int64_t ldo) {
+    ImmaPlan::Umma &u = p->um;
+    const int64_t R = by_variant ? c.M : c.N, Cn = by_variant ? c.N : c.M;
+    if (ncols > p->um_gather_cols) {
+        // many columns: transpose the block once, then one coalesced W * 8 byte load per entry out of L2
+        const int64_t *ptr = (by_variant ? p->mv_ptr : p->ms_ptr).get();
+        const int32_t *idx = (by_variant ? p->mv_idx : p->ms_idx).get();
+        const int grid = c.sm_count * 8;
+        c.prof_begin();
+        if (ncols > 16) {
+            transpose_cols_kernel<32><<<(unsigned)((Cn + 255) / 256), 256, 0, c.stream>>>(vec, ldv, ncols, Cn, u.vt.get());
+            sparse_rows_gather_kernel<32><<<grid, 256, 0, c.stream>>>(ptr, idx, u.vt.get(), ncols, R, out, ldo);
+        } else {
+            transpose_cols_kernel<16><<<(unsigned)((Cn + 255) / 256), 256, 0, c.stream>>>(vec, ldv, ncols, Cn, u.vt.get());
+            sparse_rows_gather_kernel<16><<<grid, 256, 0, c.stream>>>(ptr, idx, u.vt.get(), ncols, R, out, ldo);
+        }
+        SGB_CHECK_LAUNCH();
+        c.prof_end(by_variant ? "sparse_rows_gather_kernel (U)" : "sparse_rows_gather_kernel (corr)");
+        c.stats.n_kernel_launches += 2;
+        return;
+    }
+    const int nt = by_variant ? p->n_stiles : p->n_vtiles;
+    const int64_t G = 2 * ((R + 63) / 64);
+    const int64_t *gs = (by_variant ? p->mv_gstart : p->ms_gstart).get();
+    const uint16_t *ell = (by_variant ? p->mv_ell : p->ms_ell).get();
+    for (int c0 = 0; c0 < ncols; c0 += 4) {
+        const int nc = std::min(4, ncols - c0);
+        c.prof_begin();
+        if (nc > 2)
+            sparse_ell_multi_kernel<4><<<c.sm_count, kEmThreads, em_smem<4>(), c.stream>>>(gs, ell, vec + (size_t)c0 * ldv, ldv, nc, R, Cn, G, nt,
+                                                                                           u.part.get());
+        else
+            sparse_ell_multi_kernel<2><<<c.sm_count, kEmThreads, em_smem<2>(), c.stream>>>(gs, ell, vec + (size_t)c0 * ldv, ldv, nc, R, Cn, G, nt,
+                                                                                           u.part.get());
+        SGB_CHECK_LAUNCH();
+        c.prof_end(by_variant ? "sparse_ell_multi_kernel (U)" : "sparse_ell_multi_kernel (corr)");
+        c.prof_begin();
+        sum_tiles_multi_kernel<<<dim3((unsigned)((R + 255) / 256), nc), 256, 0, c.stream>>>(u.part.get(), nt, R, out + (size_t)c0 * ldo, ldo);
+        SGB_CHECK_LAUNCH();
+        c.prof_end("sum_tiles_multi_kernel");
+        c.stats.n_kernel_launches += 2;
+    }
+}
+
+const CUtensorMap *umma_digit_map(ImmaPlan::Umma &u, bool phase_b, int ng) {
+    const int i = ng / 16;
+    CUtensorMap *tm = phase_b ? &u.tmap_de[i] : &u.tmap_db[i];
+    bool &have = u.have_d[i];
+    if (!have) {
+        CUresult r = encode_tmap_2d(&u.tmap_db[i], u.db.get(), (uint64_t)u.cpad_a, kUMaxN, (uint64_t)u.cpad_a, 128, (uint32_t)ng, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (r == CUDA_SUCCESS)
+            r = encode_tmap_2d(&u.tmap_de[i], u.de.get(), (uint64_t)u.cpad_b, kUMaxN, (uint64_t)u.cpad_b, 128, (uint32_t)ng, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (r != CUDA_SUCCESS) throw Error(SGB_ERR_CUDA, "cuTensorMapEncodeTiled (digit tiles) failed (" + std::to_string((int)r) + ")");
+        have = true;
+    }
+    return tm;
+}
+
+// one pass: ncols <= 32 columns
+void umma_grm_mv_pass(Context &c, ImmaPlan *p, const double *b, double *out, int ncols) {
+    ImmaPlan::Umma &u = p->um;
+    const int64_t M = c.M, N = c.N;
+    const int ng = ((kUND * ncols + 15) / 16) * 16;
+    c.prof_begin();
+    umma_colstats_kernel<<<ncols, 1024, 0, c.stream>>>(b, N, u.scal.get());
+    SGB_CHECK_LAUNCH();
+    umma_digits_kernel<<<dim3((unsigned)((u.cpad_a + 255) / 256), ncols), 256, 0, c.stream>>>(b, N, N, u.cpad_a, u.scal.get(), 0, u.db.get());
+    SGB_CHECK_LAUNCH();
+    SGB_CUDA(cudaMemsetAsync(u.t_lo.get(), 0, sizeof(unsigned long long) * (size_t)ncols * M, c.stream));
+    SGB_CUDA(cudaMemsetAsync(u.t_hi.get(), 0, sizeof(unsigned long long) * (size_t)ncols * M, c.stream));
+    SGB_CUDA(cudaMemsetAsync(u.r_lo.get(), 0, sizeof(unsigned long long) * (size_t)ncols * N, c.stream));
+    SGB_CUDA(cudaMemsetAsync(u.r_hi.get(), 0, sizeof(unsigned long long) * (size_t)ncols * N, c.stream));
+    c.prof_end("umma_prep_b (colstats+digits+memsets)");
+    launch_sparse_multi(c, p, true, b, N, ncols, u.u.get(), M);
+    UmmaArgs a;
+    a.ncols = ncols; a.ng = ng; a.err = u.err.get();
+    // phase A: rows = variants, contraction over samples
+    a.R = M; a.boxes_total = u.boxes_a; a.boxes_per_split = (u.boxes_a + u.split_a - 1) / u.split_a;
+    a.out_lo = u.t_lo.get(); a.out_hi = u.t_hi.get(); a.ldo = M;
+    const int ns_a = (u.boxes_a + a.boxes_per_split - 1) / a.boxes_per_split;
+    c.prof_begin();
+    const bool prof = getenv("SGB_UMMA_PROF") != nullptr;
+    a.prof = nullptr;
+    if (prof) {
+        u.prof.ensure((size_t)16 * 65536);
+        SGB_CUDA(cudaMemsetAsync(u.prof.get(), 0, sizeof(long long) * 16 * 65536, c.stream));
+        a.prof = u.prof.get();
+    }
+    if (prof)
+        umma_gemm_kernel<true><<<dim3((unsigned)((M + kURows - 1) / kURows), ns_a), kUThreads, kUSmemBytes, c.stream>>>(u.tmap_p, *umma_digit_map(u, false, ng), a);
+    else
+        umma_gemm_kernel<false><<<dim3((unsigned)((M + kURows - 1) / kURows), ns_a), kUThreads, kUSmemBytes, c.stream>>>(u.tmap_p, *umma_digit_map(u, false, ng), a);
+    if (prof) {
+        // debugging aid: cycle counters of the issuer thread and of one expander warp, averaged over the CTAs of phase A
+        const size_t ncta = (size_t)((M + kURows - 1) / kURows) * ns_a;
+        std::vector<long long> h(ncta * 16);
+        c.d2h(h.data(), u.prof.get(), sizeof(long long) * ncta * 16);
+        c.sync();
+        double s[16] = {0};
+        for (size_t i = 0; i < ncta; i++) for (int k = 0; k < 16; k++) s[k] += (double)h[i * 16 + k];
+        const double ks = s[5] > 0 ? s[5] : 1;
+        c.printf("umma prof (clk per k-step, %zu CTAs): issuer total %.0f = wait_b %.0f + wait_a %.0f + mma %.0f + commit %.0f | expander total %.0f = "
+                 "wait_p %.0f + load/expand %.0f + wait_empty %.0f + st/wait::st %.0f + arrive %.0f\n", ncta, s[0] / ks, s[1] / ks, s[2] / ks, s[3] / ks,
+                 s[4] / ks, s[8] / ks, s[9] / ks, s[10] / ks, s[11] / ks, s[12] / ks, s[13] / ks);
+    }
+    SGB_CHECK_LAUNCH();
+    c.prof_end("umma_gemm_kernel (phase A)");
+    c.prof_begin();
+    const int Gm = (int)std::min<int64_t>(1024, std::max<int64_t>(1, (M + 255) / 256));
+    umma_finalize_kernel<<<dim3(Gm, ncols), 256, 0, c.stream>>>(u.t_lo.get(), u.t_hi.get(), u.u.get(), 1, c.lut.get(), M, 1.0 / (double)c.M_total,
+                                                                u.e.get(), u.hm.get(), u.red.get(), u.counter.get(), u.scal.get());
+    SGB_CHECK_LAUNCH();
+    umma_digits_kernel<<<dim3((unsigned)((u.cpad_b + 255) / 256), ncols), 256, 0, c.stream>>>(u.e.get(), M, M, u.cpad_b, u.scal.get(), 1, u.de.get());
+    SGB_CHECK_LAUNCH();
+    c.prof_end("umma_finalize+digits_e");
+    launch_sparse_multi(c, p, false, u.hm.get(), M, ncols, u.corr.get(), N);
+    // phase B: rows = samples, contraction over variants (sample-major copy)
+    a.R = N; a.boxes_total = u.boxes_b; a.boxes_per_split = (u.boxes_b + u.split_b - 1) / u.split_b;
+    a.out_lo = u.r_lo.get(); a.out_hi = u.r_hi.get(); a.ldo = N;
+    const int ns_b = (u.boxes_b + a.boxes_per_split - 1) / a.boxes_per_split;
+    c.prof_begin();
+    umma_gemm_kernel<false><<<dim3((unsigned)((N + kURows - 1) / kURows), ns_b), kUThreads, kUSmemBytes, c.stream>>>(u.tmap_pt, *umma_digit_map(u, true, ng), a);
+    SGB_CHECK_LAUNCH();
+    c.prof_end("umma_gemm_kernel (phase B)");
+    c.prof_begin();
+    umma_combine_kernel<<<dim3((unsigned)((N + 255) / 256), ncols), 256, 0, c.stream>>>(u.r_lo.get(), u.r_hi.get(), N, u.corr.get(), 1, u.scal.get(), out);
+    SGB_CHECK_LAUNCH();
+    c.prof_end("umma_combine_kernel");
+    c.stats.n_kernel_launches += 7;
+    c.stats.n_product_launches += 1;
 }
 
 }  // namespace
@@ -1110,7 +1369,7 @@ void imma_prepare(Context &c) {
         p->use_csr = getenv("SGB_SPARSE_CSR") != nullptr;   // comparison switch: the row-per-thread kernel everywhere
         SGB_CUDA(cudaFuncSetAttribute(sparse_ell_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEllSmem));
         // the row-major 32-bit lists are only needed to build the tile-major ones
-        p->mv_idx.release(); p->ms_idx.release();
+        // (kept: the row-gather kernel of the batched product walks them)
         SGB_CUDA(cudaFuncSetAttribute(sparse_tile_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmem));
         p->rpart.ensure((size_t)p->split_b * N);
         {
@@ -1191,6 +1450,8 @@ void imma_prepare(Context &c) {
                 }
             }
         }
+        if (const char *e = getenv("SGB_UMMA_MIN_COLS")) { p->um_min_cols = atoi(e); if (p->um_min_cols <= 0) p->um_min_cols = INT_MAX; }
+        if (const char *e = getenv("SGB_UMMA_GATHER_COLS")) p->um_gather_cols = atoi(e);
         if (const char *e = getenv("SGB_SPARSE_FORK")) p->opt_fork = atoi(e);
         if (const char *e = getenv("SGB_FUSED_FORK")) p->opt_fork_fused = atoi(e);
         if (const char *e = getenv("SGB_SPARSE_GRID_MULT")) p->opt_grid_mult = std::max(1, atoi(e));
@@ -1217,6 +1478,24 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
     // HBM passes when every CTA's slice is (nearly) full: SGB_KERNEL_AUTO takes it from 10 of the 12 K-steps per CTA upwards
     // (N >= ~380K on 148 SMs) and the two-pass kernels otherwise; SGB_KERNEL_IMMA forces it whenever the shape allows.
     const bool use_fused = p->fused_ok && (c.kernel == SGB_KERNEL_IMMA || (c.kernel == SGB_KERNEL_AUTO && p->f_ks_per_cta >= 10));
+    // several right-hand sides: one pass over the packed matrix for all of them on tcgen05 (grm_umma.cuh)
+    if ((c.kernel == SGB_KERNEL_UMMA || (c.kernel == SGB_KERNEL_AUTO && k >= p->um_min_cols)) && !p->um.failed) {
+        umma_prepare(c, p);
+        if (p->um.ready) {
+            c.async_err = p->um.herr.p;
+            c.async_err_dev = p->um.err.get();
+            // balanced passes of at most 32 columns
+            const int n_pass = (k + kUMaxCols - 1) / kUMaxCols;
+            int done = 0;
+            for (int ps = 0; ps < n_pass; ps++) {
+                const int nc = (k - done + (n_pass - ps) - 1) / (n_pass - ps);
+                umma_grm_mv_pass(c, p, b_all + (size_t)done * N, out_all + (size_t)done * N, nc);
+                done += nc;
+            }
+            SGB_CUDA(cudaMemcpyAsync(p->um.herr.p, p->um.err.get(), sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+            return;
+        }
+    }
     if (use_fused) {
         c.async_err = p->f_herr.p;
         c.async_err_dev = p->f_err.get();

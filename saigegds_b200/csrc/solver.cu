@@ -17,7 +17,7 @@ namespace sgb {
 
 void grm_mv_device(Context &c, const double *b, double *out, int k) {
     c.require_stored();
-    const bool use_imma = (c.kernel == SGB_KERNEL_IMMA) || (c.kernel == SGB_KERNEL_IMMA_TWOPASS) ||
+    const bool use_imma = (c.kernel == SGB_KERNEL_IMMA) || (c.kernel == SGB_KERNEL_IMMA_TWOPASS) || (c.kernel == SGB_KERNEL_UMMA) ||
                           (c.kernel == SGB_KERNEL_AUTO && imma_available(c));
     if (use_imma) {
         imma_grm_mv(c, b, out, k);
