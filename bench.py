@@ -14,8 +14,13 @@ e2e    : the same step through the C-ABI entry point sgb_grm_mv with pinned HOST
          device->host copy of the result inside the timed region) -- the call an R user's .Call makes.
 roofline: algorithmic bytes = ceil(N/4)*M_local packed bytes per product over the measured
          product time, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
-cpu_baseline: the CPU oracle's product (same algorithm and threading as the reference) on all host cores,
-         on a bounded variant sample, extrapolated linearly in M to the full shape.
+cpu_baseline: the CPU oracle's product (same algorithm and threading as the reference) on all host cores, on the first
+         variants of the SAME bytes the GPU stores (oracle generator == device generator), scaled linearly in M.
+batched: the same product for K = 30 right-hand sides at once (the trace step of the fit) through the tcgen05 path.
+fit    : wall time of the C3 binary null-model fit + variance ratio on the stored shard(s) (second half of the metric).
+
+  python bench.py --mode batched   # C5: N=430K, M=300K, K=30, tensor roofline
+  python bench.py --mode fit       # fit wall times only (also under torch.distributed.run)
 """
 from __future__ import annotations
 
@@ -109,11 +114,26 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def load_oracle(cores):
+    """torch.distributed.run exports OMP_NUM_THREADS=1; the CPU arm sets the thread count itself, before libgomp loads."""
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    from oracle import oracle as orc
+    orc.build()
+    return orc
+
+
 def numpy_packed_sample(n_samp, n_var, seed=200):
-    """Same distribution as the device generator (store.cu synth_kernel); bytes differ, timing does not."""
+    """Used by --mode assoc only: same distribution as the device generator, 64 distinct variants tiled."""
     rng = np.random.default_rng(seed)
     nb = (n_samp + 3) // 4
-    pool_n = min(n_var, 64)          # 64 distinct variants, tiled: the loop's cost does not depend on the codes
+    pool_n = min(n_var, 64)
     pool = np.empty((pool_n, nb), dtype=np.uint8)
     for j in range(pool_n):
         maf = rng.uniform(0.005, 0.5)
@@ -125,41 +145,76 @@ def numpy_packed_sample(n_samp, n_var, seed=200):
     return np.ascontiguousarray(pool[np.arange(n_var) % pool_n])
 
 
-def cpu_product_rate(steps, warmup, m_sample=None):
-    """Time the oracle's get_crossprod_b_grm on all host cores over a variant sample; extrapolate to N_VAR."""
-    from oracle.oracle import Oracle, build, max_threads
-    build()
-    cores = max_threads()
-    if m_sample is None:
-        # ~0.9 G genotypes/s/core (BASELINE.md): aim at ~1 s per sampled product
-        m_sample = int(max(64, min(N_VAR, 1.0 * 0.6e9 * cores / N_SAMP)))
-    packed = numpy_packed_sample(N_SAMP, m_sample)
-    o = Oracle()
-    o.store_2b_geno(packed, N_SAMP, num_thread=cores)
-    b = np.random.default_rng(1).standard_normal(N_SAMP)
+def cpu_product_rate(steps, warmup, budget_s, b_host=None):
+    """Time the oracle's get_crossprod_b_grm on all host cores.  The genotypes are the first m_s variants of the very matrix the
+    GPU arm stores (the oracle's generator is bit-identical to the device one, tests/test_batched_product.py); m_s = all N_VAR
+    variants when (warmup + steps) products fit the time budget, otherwise the largest prefix that does (said in `sample`)."""
+    cores = host_cores()
+    orc = load_oracle(cores)
+    b = np.random.default_rng(1).standard_normal(N_SAMP) if b_host is None else b_host
+    # calibration on 1,024 variants (stored separately; ~0.3 s)
+    o = orc.Oracle()
+    cal = orc.synth_geno(N_SAMP, min(4096, N_VAR), 0, 200, MISSING, cores)
+    o.store_2b_geno(cal, N_SAMP, num_thread=cores, borrow=True, want_diag=False)
+    o.grm_mv(b)
+    t0 = time.perf_counter()
+    o.grm_mv(b)
+    per_var = (time.perf_counter() - t0) / len(cal)
+    gen_per_var = 4.0e-4 * 8 / max(cores, 1) * (N_SAMP / 430000.0)                  # ~1.9 G genotypes/s on 8 cores
+    m_s = int(min(N_VAR, max(1024, budget_s / ((steps + warmup) * per_var + gen_per_var))))
+    t0 = time.perf_counter()
+    packed = orc.synth_geno(N_SAMP, m_s, 0, 200, MISSING, cores) if m_s != len(cal) else cal
+    t_gen = time.perf_counter() - t0
+    o.store_2b_geno(packed, N_SAMP, num_thread=cores, borrow=True, want_diag=False)
     for _ in range(warmup):
         o.grm_mv(b)
     t0 = time.perf_counter()
     for _ in range(steps):
-        o.grm_mv(b)
+        out = o.grm_mv(b)
     dt = (time.perf_counter() - t0) / steps
-    full = dt * (N_VAR / m_sample)
+    full = dt * (N_VAR / m_s)
+    what = "all %d variants (full product measured, no extrapolation)" % N_VAR if m_s == N_VAR else \
+        "the first %d of %d variants, scaled linearly in M" % (m_s, N_VAR)
     return dict(value=1.0 / full, unit=UNIT, cores=cores, kind="port",
-                sample="%d of %d variants x %d samples, %d timed products of %.3f s each, scaled linearly in M"
-                       % (m_sample, N_VAR, N_SAMP, steps, dt)), full
+                sample="%s x %d samples, same bytes and same b as the GPU arm; %d warm-up + %d timed products of %.3f s each "
+                       "(matrix generated on the host in %.1f s, not timed)" % (what, N_SAMP, warmup, steps, dt, t_gen),
+                b_dot_out_sample=float(b @ out) * (m_s / N_VAR), m_sample=m_s), full
+
+
+def product_config(world, kernel):
+    m_local = sg_shard(N_VAR, 0, world)
+    return {"workload": workload_name(), "n_samp": N_SAMP, "n_var": N_VAR, "n_var_per_gpu": m_local,
+            "parallelism": "variant-sharded x%d + sum all-reduce of the N-vector" % world,
+            "l2": "inputs (%.2f GB packed per GPU) exceed the 126 MB L2; no flush needed" % (((N_SAMP + 3) // 4) * m_local / 1e9),
+            "kernel": kernel or "auto"}
+
+
+def sg_shard(m, rank, world):
+    """Variants of rank `rank` (same split as saigegds_b200.shard_range, restated so the CPU arm does not import the package)."""
+    base, rem = divmod(int(m), int(world))
+    return base + (1 if rank < rem else 0)
+
+
+ARITHMETIC = ("FP64 in / FP64 out; the two matrix-vector halves are exact integer arithmetic on int8 tensor cores: b and e are "
+              "quantised to 56-bit fixed point relative to their largest element (8 signed base-128 digits, mma.sync u8 x s8 -> s32) "
+              "in the single-RHS kernels, 46-bit (6 signed base-256 digits, tcgen05.mma kind::i8) in the batched path; "
+              "dot / e / h and all scalings in FP64; <= 1e-10 of ||out||_inf vs the FP64 oracle (tests)")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 5))
-    cb, full = cpu_product_rate(steps, max(1, min(args.warmup, 1)))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    cb, full = cpu_product_rate(steps, warmup, float(os.environ.get("SGB_BENCH_CPU_BUDGET_S", 300)))
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": 1, "ms_per_step": full * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(), "n_samp": N_SAMP, "n_var": N_VAR},
+            "warmup": warmup, "ms_per_step": full * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": product_config(max(1, args.gpus), args.kernel),
             "cpu_baseline": cb, "gpu_launches": 0,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if cb["m_sample"] == N_VAR:
+        # same bytes, same b: this equals the GPU arm's result_invariants.b_dot_out up to rounding
+        line["result_invariants"] = {"b_dot_out": cb["b_dot_out_sample"]}
     print(json.dumps(line), flush=True)
 
 
@@ -226,8 +281,8 @@ def run_gpu(args):
     else:
         for _ in range(150):                 # every rank must issue the same number of products (each ends in a collective)
             ctx.grm_mv_device(d_b, d_out, 1)
-    if rank == 0:
-        sampler.lines.clear()
+    # (the samples of the warm-up stay in: the timed region of 20 products lasts ~70 ms, one nvidia-smi period; the warm-up
+    #  runs the same product back to back, so the clocks line describes the same load)
     note("warm-up done")
     ctx.reset_stats()
     barrier()
@@ -266,6 +321,34 @@ def run_gpu(args):
     ctx.set_profiling(False)
     note("profiling pass done")
 
+    # ---- the same product for K = 30 right-hand sides at once (trace step of the fit; saige_fitnull.cpp:646-654) ----
+    batched = None
+    if not args.no_batched:
+        kb = 30
+        Bh = np.asfortranarray(np.random.default_rng(2).standard_normal((N_SAMP, kb)))
+        Bh[:, 0] = b_host
+        d_B = ctx.device_vector(Bh.reshape(-1, order="F"))
+        d_O = ctx.device_empty(8 * N_SAMP * kb)
+        for _ in range(2):
+            ctx.grm_mv_device(d_B, d_O, kb)
+        barrier()
+        reps = 5
+        msb = max_over_ranks(ctx.time_products_device(d_B, d_O, kb, reps)) / reps
+        barrier()
+        col0 = ctx.get_crossprod_b_grm(Bh[:, :2])[:, 0]            # k = 2: batched path, through the host entry point
+        batched = {"k": kb, "ms_per_call": msb, "products_per_s": kb * 1e3 / msb,
+                   "col0_vs_single_rhs_relinf": float(np.max(np.abs(col0 - out_host)) / np.max(np.abs(out_host))),
+                   "note": "tcgen05.mma kind::i8, accumulators in TMEM; one pass over both orientations of the packed matrix "
+                           "serves all K columns (csrc/grm_umma.cuh); device-resident, all-reduce included"}
+        d_B.free(); d_O.free()
+        note("batched done")
+
+    # ---- null-model fit on the stored shard(s): second half of the metric ----
+    fit = None
+    if not args.no_fit:
+        fit = fit_on_stored(ctx, N_SAMP, N_VAR, a, m_local, rank, world, dist, ["binary"])["binary"]
+        note("fit done")
+
     # orderly teardown on every rank: library communicator first, then torch's process group
     d_b.free(); d_out.free()
     ctx.close()
@@ -279,18 +362,28 @@ def run_gpu(args):
     alg_bytes = ((N_SAMP + 3) // 4) * m_local
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
     kern = {k: {"ms_per_launch": v[0] / v[1], "launches_per_product": v[1] / 3.0,
-                "gbs_on_packed_bytes": alg_bytes / (v[0] / v[1] * 1e-3) / 1e9} for k, v in ktimes.items()}
+                "gbs_on_packed_bytes": alg_bytes / (v[0] / v[1] * 1e-3) / 1e9} for k, v in ktimes.items() if v[0] > 0}
     # dominant kernel = the one with the largest share of the step (event-timed, serialised pass above)
     dom = max(kern, key=lambda k: kern[k]["ms_per_launch"] * kern[k]["launches_per_product"])
     dom_gbs = kern[dom]["gbs_on_packed_bytes"]
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_ncu_fused_summary.json")
+    tp = os.path.join(ROOT, "profiles", "r02_ncu_fused_summary.json")
+    if not os.path.exists(tp):
+        tp = os.path.join(ROOT, "profiles", "r01_ncu_fused_summary.json")
     if os.path.exists(tp) and world == 1 and N_SAMP == 430000 and N_VAR == 100000:
         tj = json.load(open(tp))
         if tj.get("kernel") == dom:
             traffic = tj.get("dram_bytes_per_launch")
+    # the three floors of the single-RHS kernel: HBM stream, tensor pipe (16 int8 MACs per genotype = 8 digit
+    # planes x 2 phases, legacy mma.sync IMMA measured at 2,048 MAC/clk/SM = 595 TMAC/s at 1,965 MHz) and the half-rate integer
+    # pipe that forms the operands (LOP3: 7 per 16 genotypes in phase A + B, 64 lanes/clk/SM)
+    geno = float(N_SAMP) * m_local
+    floors = {"hbm_ms": alg_bytes / (peak * 1e9) * 1e3, "imma_pipe_ms": 16.0 * geno / (2048.0 * 148 * 1.965e9) * 1e3,
+              "int_pipe_ms": (7.0 / 16.0) * geno / (64.0 * 148 * 1.965e9) * 1e3,
+              "note": "HBM: packed bytes / measured copy bandwidth; tensor: 16 MAC per genotype / measured mma.sync IMMA rate "
+                      "(profiles/r01_microbench_b200.txt); integer: operand-forming LOP3s at 64 lanes/clk/SM"}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak,
-                "traffic": traffic, "peak_source": peak_src,
+                "traffic": traffic, "peak_source": peak_src, "floors": floors,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "dominant kernel: algorithmic bytes = ceil(N/4)*M_local packed bytes (read once) / its event-timed launch; "
                         "traffic = dram read+write bytes of one launch from the committed ncu --set full capture",
@@ -301,56 +394,80 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(), "n_samp": N_SAMP, "n_var": N_VAR, "n_var_per_gpu": m_local,
-                   "parallelism": "variant-sharded x%d + sum all-reduce of the N-vector" % world,
-                   "l2": "inputs (%.2f GB packed per GPU) exceed the 126 MB L2; no flush needed" % (alg_bytes / 1e9),
-                   "kernel": args.kernel or "auto"},
+        "config": product_config(world, args.kernel),
+        "arithmetic": ARITHMETIC,
         "clocks": clocks,
         "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * N_SAMP, "d2h_bytes_per_step": 8 * N_SAMP,
                 "ms_per_step": e2e_s * 1e3, "note": "sgb_grm_mv with pinned host b/out (sgb_malloc_host); genotypes resident as in the reference"},
         "gpu_launches": launches,
         "roofline": roofline,
-        "result_checksum": float(np.sum(out_host)),
+        # b'(GRM b) = (1/M) sum_j (g_j'b)^2 > 0: a checksum that does not cancel, identical for every number of GPUs up to rounding
+        "result_invariants": {"b_dot_out": float(b_host @ out_host), "out_l2": float(np.linalg.norm(out_host)),
+                              "out_absmax": float(np.max(np.abs(out_host)))},
     }
+    if batched is not None:
+        line["batched"] = batched
+    if fit is not None:
+        line["fit"] = fit
     if world == 1 and not args.no_cpu:
-        cb, _ = cpu_product_rate(3, 1)
+        cb, _ = cpu_product_rate(2, 1, float(os.environ.get("SGB_BENCH_CPU_BUDGET_S", 25)), b_host)
+        # the same invariant on the CPU: b'(GRM_s b) over the sampled variants, against the GPU's value restricted to them is not
+        # available, so report it for the record only
         line["cpu_baseline"] = cb
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------------------------------ null-model fit (secondary metric)
-def synth_phenotype(ctx, n, m, seed=7, n_causal=1000):
-    """x1 ~ N(0,1), x2 ~ Bernoulli(0.5), g = sqrt(0.3) * standardised sum of causal columns."""
+# ------------------------------------------------------------------------------------------ null-model fit (second half of the metric)
+def synth_phenotype(ctx, n, m_total, var_offset=0, m_local=None, dist=None, seed=7, n_causal=1000):
+    """x1 ~ N(0,1), x2 ~ Bernoulli(0.5), g = sqrt(0.3) * standardised sum of causal columns.  With the
+    variants sharded over ranks every rank adds the causal columns it owns and the partial sums are all-reduced, so all ranks
+    hold the same phenotype."""
+    m_local = m_total if m_local is None else m_local
     rng = np.random.default_rng(seed)
     x1, x2 = rng.standard_normal(n), (rng.random(n) < 0.5).astype(np.float64)
+    causal = rng.choice(m_total, size=min(n_causal, m_total), replace=False)
+    effect = rng.standard_normal(len(causal))
     g = np.zeros(n)
-    for j in rng.choice(m, size=min(n_causal, m), replace=False):
-        ds = ctx.get_geno_ds(int(j))
-        ds = np.where(np.isnan(ds), np.nanmean(ds), ds)
-        sd = ds.std()
-        if sd > 0:
-            g += (ds - ds.mean()) / sd * rng.standard_normal()
+    for j, beta in zip(causal, effect):
+        if var_offset <= j < var_offset + m_local:
+            ds = ctx.get_geno_ds(int(j - var_offset))
+            ds = np.where(np.isnan(ds), np.nanmean(ds), ds)
+            sd = ds.std()
+            if sd > 0:
+                g += (ds - ds.mean()) / sd * beta
+    if dist is not None:
+        import torch
+        t = torch.from_numpy(g).cuda()
+        dist.all_reduce(t)
+        torch.cuda.synchronize()
+        g = t.cpu().numpy()
     g = np.sqrt(0.3) * (g - g.mean()) / g.std()
-    y = (rng.random(n) < 1 / (1 + np.exp(-(-2 + 0.5 * x1 + 0.5 * x2 + g)))).astype(np.float64)
-    yy = x1 + x2 + g + rng.standard_normal(n)
+    u, e = rng.random(n), rng.standard_normal(n)
+    y = (u < 1 / (1 + np.exp(-(-2 + 0.5 * x1 + 0.5 * x2 + g)))).astype(np.float64)
+    yy = x1 + x2 + g + e
     return dict(x1=x1, x2=x2, y=y, yy=yy)
 
 
-def run_fit(args):
-    """Null-model fit wall time (saige_fit_AI_PCG_* + saige_calc_var_ratio_*) on synthetic data, one GPU."""
+def fit_on_stored(ctx, n, m_total, var_offset, m_local, rank, world, dist, traits):
+    """saige_fit_AI_PCG_* + saige_calc_var_ratio_* (saige_fitnull.cpp:949-1474) on the genotypes already stored in `ctx`
+    (every rank its shard); wall-clock seconds, max over ranks."""
     import saigegds_b200 as sg
     from saigegds_b200 import rsetup
-    n, m = args.fit_n, args.fit_m
-    ctx = sg.Context(0)
-    t0 = time.perf_counter()
-    ctx.store_synthetic(n, m, seed=200, missing_rate=MISSING)
-    t_store = time.perf_counter() - t0
-    ph = synth_phenotype(ctx, n, m)
+
+    def wall_max(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        torch.cuda.synchronize()
+        return float(t.item())
+
+    ph = synth_phenotype(ctx, n, m_total, var_offset, m_local, dist)
     X, _ = rsetup.qr_transform(rsetup.model_matrix(ph, ["x1", "x2"]))
-    param = sg.make_param(verbose=bool(os.environ.get("SGB_BENCH_VERBOSE")))
+    param = sg.make_param(verbose=bool(os.environ.get("SGB_BENCH_VERBOSE")) and rank == 0)
     out = {}
-    for trait in args.fit_traits.split(","):
-        ctx.reset_stats()
+    for trait in traits:
         # host-side restatement of the R set-up (glm start values, SPAtest null object): numpy on the box's shared cores,
         # reported separately from the native fit
         t0 = time.perf_counter()
@@ -362,27 +479,240 @@ def run_fit(args):
             fit0 = rsetup.glm_gaussian(X, rsetup.rank_norm(f.residuals) * rsetup.sd(f.residuals))
             noK = rsetup.null_model_quant(X, fit0)
         t_setup = time.perf_counter() - t0
-        t0 = time.perf_counter()
+        res = None
+        for rep in range(2):          # first pass: lazy one-time set-up (sample-major copy, work buffers); second pass: reported
+            ctx.reset_stats()
+            t0 = time.perf_counter()
+            if trait == "binary":
+                glmm = ctx.saige_fit_AI_PCG_binary(fit0, X, rsetup.initial_tau_binary(), param)
+            else:
+                glmm = ctx.saige_fit_AI_PCG_quant(fit0, noK.X1, rsetup.initial_tau_quant(fit0), param)
+            t_fit = time.perf_counter() - t0
+            st_fit = ctx.stats()
+            t0 = time.perf_counter()
+            ctx.set_seed(200)
+            fn = ctx.saige_calc_var_ratio_binary if trait == "binary" else ctx.saige_calc_var_ratio_quant
+            vr = fn(fit0, glmm, noK, param, ctx.sample_int(m_total))
+            t_vr = time.perf_counter() - t0
+            st = ctx.stats()
+            cur = {"fit_s": wall_max(t_fit), "var_ratio_s": wall_max(t_vr)}
+            if rep == 0:
+                first = cur
+            res = cur
+        out[trait] = {"fit_s": res["fit_s"], "var_ratio_s": res["var_ratio_s"], "first_call_fit_s": first["fit_s"],
+                      "host_setup_s": t_setup, "tau": [float(x) for x in glmm["tau"]], "converged": bool(glmm["converged"]),
+                      "products_fit": int(st_fit["n_products"]), "products_total": int(st["n_products"]),
+                      "pcg_solves": int(st["n_pcg_solves"]), "pcg_iterations": int(st["n_pcg_iterations"]),
+                      "var_ratio_mean": float(np.mean(vr["ratio"])), "n_markers": int(len(vr["ratio"])),
+                      "workload": "synthetic N=%d M=%d %s trait, y ~ x1 + x2, h2 ~ 0.3 from 1,000 causal variants; "
+                                  "seqFitNullGLMM_SPA defaults (nrun 30, tol 0.02, tolPCG 1e-5)" % (n, m_total, trait),
+                      "note": "fit_s = saige_fit_AI_PCG_%s, var_ratio_s = saige_calc_var_ratio_%s; second call on the stored "
+                              "genotypes (first_call_fit_s includes building the sample-major copy once)" % (trait, trait)}
+    return out
+
+
+def cpu_fit_times(n, m, traits, cores):
+    """The oracle's full fit (= the reference's algorithm, all host cores) on a shape it finishes in seconds, for the record."""
+    orc = load_oracle(cores)
+    from saigegds_b200 import rsetup
+    packed = orc.synth_geno(n, m, 0, 200, MISSING, cores)
+    o = orc.Oracle()
+    t0 = time.perf_counter()
+    o.store_2b_geno(packed, n, num_thread=cores)
+    t_store = time.perf_counter() - t0
+
+    class _Ctx:          # the phenotype generator only needs get_geno_ds
+        def get_geno_ds(self, j):
+            return o.get_geno_ds(j)
+    ph = synth_phenotype(_Ctx(), n, m)
+    X, _ = rsetup.qr_transform(rsetup.model_matrix(ph, ["x1", "x2"]))
+    out = {"n": n, "m": m, "cores": cores, "store_s": t_store}
+    for trait in traits:
         if trait == "binary":
-            glmm = ctx.saige_fit_AI_PCG_binary(fit0, X, rsetup.initial_tau_binary(), param)
+            fit0 = rsetup.glm_binomial(X, ph["y"])
+            tau0 = rsetup.initial_tau_binary()
         else:
-            glmm = ctx.saige_fit_AI_PCG_quant(fit0, noK.X1, rsetup.initial_tau_quant(fit0), param)
-        t_fit = time.perf_counter() - t0
-        st_fit = ctx.stats()
+            f = rsetup.glm_gaussian(X, ph["yy"])
+            fit0 = rsetup.glm_gaussian(X, rsetup.rank_norm(f.residuals) * rsetup.sd(f.residuals))
+            tau0 = rsetup.initial_tau_quant(fit0)
         t0 = time.perf_counter()
-        ctx.set_seed(200)
-        fn = ctx.saige_calc_var_ratio_binary if trait == "binary" else ctx.saige_calc_var_ratio_quant
-        vr = fn(fit0, glmm, noK, param, ctx.sample_int(m))
-        t_vr = time.perf_counter() - t0
-        st = ctx.stats()
-        out[trait] = {"fit_s": t_fit, "host_setup_s": t_setup, "var_ratio_s": t_vr, "tau": [float(x) for x in glmm["tau"]],
-                      "converged": glmm["converged"], "products_fit": int(st_fit["n_products"]),
-                      "products_total": int(st["n_products"]), "pcg_solves": int(st["n_pcg_solves"]),
-                      "pcg_iterations": int(st["n_pcg_iterations"]), "var_ratio_mean": float(np.mean(vr["ratio"])),
-                      "n_markers": int(len(vr["ratio"]))}
-    line = {"metric": "null_model_fit_wall_s", "unit": "s", "n_gpus": 1, "higher_is_better": False, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": "synthetic N=%d M=%d null fit + variance ratio" % (n, m)},
+        r = o.fit_AI_PCG(trait if trait == "binary" else "quantitative", fit0, X, tau0)
+        out[trait] = {"fit_s": time.perf_counter() - t0, "tau": [float(x) for x in r["tau"]], "products": int(o.num_products())
+                      if hasattr(o, "num_products") else None}
+    return out
+
+
+def run_fit(args):
+    """Null-model fit wall time on synthetic data at N GPUs (variants sharded; launch with torch.distributed.run for N > 1)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import saigegds_b200 as sg
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n, m = args.fit_n, args.fit_m
+    ctx = sg.Context(local_rank)
+    if world > 1:
+        sg.init_comm_from_torch(ctx)
+    a, b_end = sg.shard_range(m, rank, world)
+    t0 = time.perf_counter()
+    ctx.store_synthetic(n, b_end - a, m, a, seed=200, missing_rate=MISSING)
+    t_store = time.perf_counter() - t0
+    out = fit_on_stored(ctx, n, m, a, b_end - a, rank, world, dist, args.fit_traits.split(","))
+    ctx.close()
+    if dist is not None:
+        import torch
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {"metric": "null_model_fit_wall_s", "value": out[args.fit_traits.split(",")[0]]["fit_s"], "unit": "s", "n_gpus": world,
+            "higher_is_better": False, "scaling": "strong", "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic N=%d M=%d null fit + variance ratio" % (n, m),
+                       "parallelism": "variant-sharded x%d" % world},
             "store_s": t_store, "traits": out}
+    if args.cpu_fit and world == 1:
+        cn, cm = [int(x) for x in args.cpu_fit.split("x")]
+        line["cpu_fit"] = cpu_fit_times(cn, cm, args.fit_traits.split(","), host_cores())
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ batched K-RHS product (BASELINE config 5)
+def run_batched(args):
+    """K right-hand sides per step through the batched tcgen05 path (the trace estimation of the fit: 30 Rademacher vectors per
+    PCG iteration, saige_fitnull.cpp:646-654) at N = 430K, M = 300K (C5).  value = columns (products) per second."""
+    global N_VAR
+    N_VAR = int(os.environ.get("SGB_BENCH_M5", 300000))
+    K = int(os.environ.get("SGB_BENCH_K", 30))
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "synthetic N=%d M=%d, K=%d right-hand sides per step (batched multi-RHS GRM product, trace estimation), "
+                          "maf~U(0.005,0.5), %.1f%% missing" % (N_SAMP, N_VAR, K, 100 * MISSING),
+              "n_samp": N_SAMP, "n_var": N_VAR, "k": K, "n_var_per_gpu": sg_shard(N_VAR, 0, world),
+              "parallelism": "variant-sharded x%d + sum all-reduce of the N x K block" % world,
+              "l2": "inputs (%.1f GB packed per GPU, both orientations) exceed the 126 MB L2; no flush needed"
+                    % (2 * ((N_SAMP + 3) // 4) * sg_shard(N_VAR, 0, world) / 1e9)}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps, warmup = max(1, args.steps), max(0, args.warmup)
+        cb, full = cpu_product_rate(max(1, min(steps, 3)), min(warmup, 1), float(os.environ.get("SGB_BENCH_CPU_BUDGET_S", 120)))
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": steps, "warmup": warmup, "ms_per_step": full * K * 1e3, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": cb,
+                          "gpu_launches": 0, "note": "the reference has no batched product: K columns cost K single products",
+                          "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    import saigegds_b200 as sg
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = sg.Context(local_rank)
+    if world > 1:
+        sg.init_comm_from_torch(ctx)
+    a, b_end = sg.shard_range(N_VAR, rank, world)
+    m_local = b_end - a
+    ctx.store_synthetic(N_SAMP, m_local, N_VAR, a, seed=200, missing_rate=MISSING)
+
+    def barrier():
+        if dist is not None:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    rng = np.random.default_rng(1)
+    B = np.asfortranarray(rng.integers(0, 2, (N_SAMP, K)) * 2.0 - 1.0)          # Rademacher columns, as in get_trace
+    d_B = ctx.device_vector(B.reshape(-1, order="F"))
+    d_O = ctx.device_empty(8 * N_SAMP * K)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    warm = max(3, args.warmup)
+    for _ in range(warm):
+        ctx.grm_mv_device(d_B, d_O, K)
+    ctx.reset_stats()
+    barrier()
+    steps = max(1, args.steps)
+    ms = max_over_ranks(ctx.time_products_device(d_B, d_O, K, steps)) / steps
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = int(ctx.stats()["n_kernel_launches"])
+    # e2e: the C-ABI entry point with pinned host blocks (N x K in, N x K out)
+    b_pin, o_pin = ctx.pinned_empty((N_SAMP, K)), ctx.pinned_empty((N_SAMP, K))
+    b_pin[:] = B
+    ctx.get_crossprod_b_grm(b_pin, out=o_pin)
+    barrier()
+    t0 = time.perf_counter()
+    e_steps = max(1, min(steps, 5))
+    for _ in range(e_steps):
+        ctx.get_crossprod_b_grm(b_pin, out=o_pin)
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / e_steps)
+    out_host = np.array(o_pin)
+    # single-RHS kernel on two of the columns: the batched result must agree with it
+    ctx.set_kernel("imma")
+    chk = max(float(np.max(np.abs(ctx.get_crossprod_b_grm(B[:, c]) - out_host[:, c])) / np.max(np.abs(out_host[:, c]))) for c in (0, K - 1))
+    ctx.set_kernel("auto")
+    ctx.set_profiling(True)
+    ctx.grm_mv_device(d_B, d_O, K)
+    kt = ctx.kernel_times()
+    ctx.set_profiling(False)
+    d_B.free(); d_O.free()
+    ctx.close()
+    if dist is not None:
+        barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    gemm_ms = sum(v[0] / v[1] for k, v in kt.items() if k.startswith("umma_gemm_kernel"))
+    macs = 2.0 * float(N_SAMP) * m_local * 6 * K                    # both phases, 6 digit columns per right-hand side
+    pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    bf16 = float(pk.get("bf16_tflops", 1590.0))
+    probe_tops = 4179.0          # tools/umma_probe.cu on this pool's B200: back-to-back kind::i8 MMAs, A from TMEM, N = 240
+    peak_tops = max(2.0 * bf16, probe_tops)
+    ach_tops = 2.0 * macs / (gemm_ms * 1e-3) / 1e12
+    hbm, hbm_src = measured_peaks()
+    line = {"metric": METRIC, "value": K * 1e3 / ms, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8 digits / f64",
+            "arithmetic": ARITHMETIC, "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * N_SAMP * K, "d2h_bytes_per_step": 8 * N_SAMP * K,
+                    "ms_per_step": e2e_s * 1e3, "note": "sgb_grm_mv with K pinned host columns in and out"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "umma_gemm_kernel (phase A + phase B)", "achieved": ach_tops, "peak": peak_tops,
+                         "unit": "TOP/s", "frac": ach_tops / peak_tops, "traffic": None,
+                         "peak_source": "measured int8 tensor rate of this part: 4,179 TOP/s for back-to-back tcgen05.mma kind::i8 (tools/umma_probe.cu, "
+                                        "profiles/r02_umma_probe_b200.txt); MEASURED_PEAKS.json has no int8 figure -- 2 x its bf16_tflops would be "
+                                        "%.0f TOP/s, which this kernel exceeds; nominal 4,500" % (2.0 * bf16),
+                         "executed_over_algorithmic": (((6 * K + 15) // 16) * 16) / (6.0 * K),
+                         "algorithmic_macs_per_step": macs,
+                         "note": "algorithmic int8 MACs = 2 phases x N x M_local x 6 digit columns x K, over the event-timed duration of the "
+                                 "two GEMM launches (serialised profiling pass)",
+                         "hbm": {"packed_bytes_both_orientations": 2 * ((N_SAMP + 3) // 4) * m_local,
+                                 "achieved_gbs": 2 * ((N_SAMP + 3) // 4) * m_local / (gemm_ms * 1e-3) / 1e9, "peak_gbs": hbm, "peak_source": hbm_src},
+                         "kernels": {k: {"ms_per_launch": v[0] / v[1], "launches": v[1]} for k, v in kt.items() if v[0] > 0}},
+            "batched_vs_single_rhs_relinf": chk,
+            "result_invariants": {"b_dot_out_col0": float(B[:, 0] @ out_host[:, 0]), "out_l2": float(np.linalg.norm(out_host))}}
+    if world == 1 and not args.no_cpu:
+        cb, _ = cpu_product_rate(2, 1, float(os.environ.get("SGB_BENCH_CPU_BUDGET_S", 25)))
+        line["cpu_baseline"] = cb
     print(json.dumps(line), flush=True)
 
 
@@ -496,9 +826,9 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--kernel", default=None, choices=[None, "auto", "simt", "imma", "imma2"])
+    ap.add_argument("--kernel", default=None, choices=[None, "auto", "simt", "imma", "imma2", "umma"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--mode", default="product", choices=["product", "fit", "assoc"],
+    ap.add_argument("--mode", default="product", choices=["product", "batched", "fit", "assoc"],
                     help="product: the headline metric; fit: null-model fit wall time; assoc: score test + SPA scan "
                          "(secondary metrics)")
     ap.add_argument("--assoc-m", type=int, default=9472, help="variants in the association-scan benchmark")
@@ -506,9 +836,14 @@ def main():
     ap.add_argument("--fit-n", type=int, default=50000)
     ap.add_argument("--fit-m", type=int, default=100000)
     ap.add_argument("--fit-traits", default="binary,quantitative")
+    ap.add_argument("--cpu-fit", default="", help="--mode fit: also time the CPU oracle's fit at NxM (e.g. 1000x9976 or 50000x10000)")
+    ap.add_argument("--no-batched", action="store_true", help="product mode: skip the K = 30 batched leg")
+    ap.add_argument("--no-fit", action="store_true", help="product mode: skip the null-model fit leg")
     args = ap.parse_args()
     if args.mode == "assoc":
         run_assoc(args)
+    elif args.mode == "batched":
+        run_batched(args)
     elif args.impl == "reference":
         run_reference(args)
     elif args.mode == "fit":

@@ -75,15 +75,17 @@ class Oracle:
         except Exception:
             pass
 
-    def store_2b_geno(self, packed: np.ndarray, n_samp: int, num_thread: int = 1):
-        """packed: [M][ceil(N/4)] uint8 (one row per variant == R RawMatrix column)."""
+    def store_2b_geno(self, packed: np.ndarray, n_samp: int, num_thread: int = 1, borrow: bool = False, want_diag: bool = True):
+        """packed: [M][ceil(N/4)] uint8 (one row per variant == R RawMatrix column).  borrow: keep a pointer to `packed`
+        instead of copying it (what the reference does with R's matrix); want_diag=False skips the serial diag(GRM) pass."""
         packed = np.ascontiguousarray(packed, dtype=np.uint8)
         m, nb = packed.shape
         self.n, self.m = int(n_samp), int(m)
         lut = np.empty(4 * m)
         diag = np.empty(self.n)
-        lib().orc_store_2b_geno(self.h, _p(packed, C.c_ubyte), C.c_long(self.n), C.c_long(nb), C.c_long(m),
-                                C.c_int(num_thread), _p(lut), _p(diag))
+        self._borrowed = packed if borrow else None
+        lib().orc_store_2b_geno_ex(self.h, _p(packed, C.c_ubyte), C.c_long(self.n), C.c_long(nb), C.c_long(m),
+                                   C.c_int(num_thread), _p(lut), _p(diag), C.c_int(int(borrow)), C.c_int(int(not want_diag)))
         return lut.reshape(m, 4), diag
 
     def store_sp_geno(self, sp_geno_list, n_samp: int, num_thread: int = 1):
@@ -280,3 +282,14 @@ def qnorm(p):
 
 def max_threads():
     return lib().orc_max_threads()
+
+
+def synth_geno(n_samp: int, n_var: int, var_offset: int = 0, seed: int = 200, missing_rate: float = 0.005,
+               num_thread: int | None = None) -> np.ndarray:
+    """The synthetic genotypes of SURVEY.md 8(d) on the CPU: bit-identical to the device generator
+    (Context.store_synthetic / synth_to_host), so both arms of bench.py consume the same bytes."""
+    nb = (n_samp + 3) // 4
+    out = np.empty((n_var, nb), dtype=np.uint8)
+    lib().orc_synth_geno(C.c_long(n_samp), C.c_long(n_var), C.c_long(var_offset), C.c_ulonglong(seed), C.c_double(missing_rate),
+                         _p(out, C.c_ubyte), C.c_int(num_thread or max_threads()))
+    return out

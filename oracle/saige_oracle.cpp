@@ -155,9 +155,12 @@ struct Oracle {
     }
 
     // saige_store_2b_geno, saige_fitnull.cpp:159-230
-    void store_2b_geno(const BYTE *packed, size_t n_samp, size_t n_packed, size_t n_var, int nthread) {
-        owned.assign(packed, packed + n_packed * n_var);
-        Geno_PackedRaw = owned.data();
+    // borrow: keep the caller's pointer like the reference does (saige_fitnull.cpp:170); skip_diag: bench.py's product timing does not
+    // need diag(GRM), whose pass is serial in the reference (:205-227)
+    void store_2b_geno(const BYTE *packed, size_t n_samp, size_t n_packed, size_t n_var, int nthread, bool borrow = false,
+                       bool skip_diag = false) {
+        if (borrow) { owned.clear(); owned.shrink_to_fit(); Geno_PackedRaw = packed; }
+        else { owned.assign(packed, packed + n_packed * n_var); Geno_PackedRaw = owned.data(); }
         sparse = false; Geno_Sparse.clear();
         Geno_NumSamp = n_samp; Geno_PackedNumSamp = n_packed; Geno_NumVariant = n_var;
         NumThreads = nthread;
@@ -182,7 +185,7 @@ struct Oracle {
         }
         // :205-227 diag(GRM), serial in the reference
         buf_diag_grm.assign(n_samp, 0.0);
-        for (size_t i = 0; i < n_var; i++) {
+        for (size_t i = 0; i < (skip_diag ? 0 : n_var); i++) {
             const BYTE *g = Geno_PackedRaw + Geno_PackedNumSamp * i;
             const double *base = &buf_std_geno[4 * i];
             size_t n = Geno_NumSamp; double *p = buf_diag_grm.data();
@@ -637,6 +640,50 @@ const char *orc_last_error(void *h) { return ((Oracle *)h)->last_error.c_str(); 
 long orc_num_products(void *h) { return ((Oracle *)h)->n_products; }
 long orc_num_pcg(void *h) { return ((Oracle *)h)->n_pcg; }
 long orc_num_pcg_iter(void *h) { return ((Oracle *)h)->n_pcg_iter; }
+// Synthetic genotypes of SURVEY.md section 8(d): a CPU restatement of the device generator (saigegds_b200/csrc/store.cu,
+// synth_kernel) so that the CPU arm of bench.py and the parity tests consume the very bytes the GPU stores.  Counter based:
+// a genotype depends only on (seed, global variant index, sample index).  The floating-point expressions are written with
+// explicit fma() where the device code contracts them (checked in its PTX), so the thresholds agree to the last bit.
+static inline uint64_t synth_mix64(uint64_t z) {
+    z += 0x9e3779b97f4a7c15ULL;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+// one variant row; integer thresholds are equivalent to the device's floating-point comparisons (u24 / 2^24 < q <=> u24 < ceil(q 2^24))
+__attribute__((target_clones("arch=skylake-avx512", "avx2", "default"), optimize("O3")))
+static void synth_row(uint64_t base, long n_samp, long NB, uint32_t t0, uint32_t t1, uint32_t tm, unsigned char *row) {
+    constexpr long CH = 1024;
+    unsigned char code[CH];
+    for (long n0 = 0; n0 < NB * 4; n0 += CH) {
+        const long cnt = std::min(CH, NB * 4 - n0);
+        for (long k = 0; k < cnt; k++) {
+            uint64_t z = base + (uint64_t)(n0 + k) * 0xD1B54A32D192ED03ULL + 0x9e3779b97f4a7c15ULL;
+            z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+            z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+            z ^= z >> 31;
+            const uint32_t u = (uint32_t)(z >> 40), um = (uint32_t)(z >> 8) & 0xFFFFFFu;
+            unsigned c = (unsigned)(u >= t0) + (unsigned)(u >= t1);
+            c = (um < tm) ? 3u : c;
+            code[k] = (unsigned char)((n0 + k < n_samp) ? c : 3u);
+        }
+        for (long k = 0; k < cnt; k += 4) row[(n0 + k) >> 2] = (unsigned char)(code[k] | (code[k + 1] << 2) | (code[k + 2] << 4) | (code[k + 3] << 6));
+    }
+}
+int orc_synth_geno(long n_samp, long n_var, long var_offset, unsigned long long seed, double miss, unsigned char *out, int num_thread) {
+    const long NB = (n_samp + 3) / 4;
+    const uint32_t tm = (uint32_t)std::ceil(miss * 16777216.0);
+#pragma omp parallel for schedule(dynamic, 16) num_threads(num_thread > 0 ? num_thread : 1)
+    for (long j = 0; j < n_var; j++) {
+        const uint64_t gj = (uint64_t)(j + var_offset);
+        const double x = (double)(synth_mix64(seed ^ (0xA5A5A5A5ULL + gj * 0x632BE59BD9B4E019ULL)) >> 11) * (1.0 / 9007199254740992.0);
+        const double maf = fma(x, 0.495, 0.005);
+        const double om = 1.0 - maf, q0 = om * om, q1 = fma(maf + maf, om, q0);
+        synth_row(seed + gj * 0x9E3779B97F4A7C15ULL, n_samp, NB, (uint32_t)std::ceil(q0 * 16777216.0), (uint32_t)std::ceil(q1 * 16777216.0), tm,
+                  out + (size_t)j * NB);
+    }
+    return 0;
+}
 int orc_max_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();
@@ -649,6 +696,14 @@ int orc_store_2b_geno(void *h, const unsigned char *packed, long n_samp, long n_
                       double *buf_std_geno, double *buf_diag) {
     Oracle &o = *(Oracle *)h;
     o.store_2b_geno(packed, n_samp, n_packed, n_var, num_thread);
+    if (buf_std_geno) memcpy(buf_std_geno, o.buf_std_geno.data(), sizeof(double) * 4 * n_var);
+    if (buf_diag) memcpy(buf_diag, o.buf_diag_grm.data(), sizeof(double) * n_samp);
+    return 0;
+}
+int orc_store_2b_geno_ex(void *h, const unsigned char *packed, long n_samp, long n_packed, long n_var, int num_thread,
+                         double *buf_std_geno, double *buf_diag, int borrow, int skip_diag) {
+    Oracle &o = *(Oracle *)h;
+    o.store_2b_geno(packed, n_samp, n_packed, n_var, num_thread, borrow != 0, skip_diag != 0);
     if (buf_std_geno) memcpy(buf_std_geno, o.buf_std_geno.data(), sizeof(double) * 4 * n_var);
     if (buf_diag) memcpy(buf_diag, o.buf_diag_grm.data(), sizeof(double) * n_samp);
     return 0;

@@ -25,11 +25,23 @@ int guarded(sgb_context *ctx, F &&fn, bool need_ctx = true) {
             if (!ctx) throw sgb::Error(SGB_ERR_INVALID, "context is NULL");
             SGB_CUDA(cudaSetDevice(ctx->dev));
         }
-        fn();
+        try {
+            fn();
+        } catch (const sgb::Error &e) {
+            // A kernel with cross-CTA waits (the fused single-pass product) ran out of its wall-clock bound -- a time-sliced,
+            // throttled or instrumented GPU.  The entry points are functions of their arguments, so redo the call once on the
+            // kernels that have no such waits (two HBM passes); report an error only if that fails too.  Not with several ranks:
+            // they could no longer agree on the sequence of collectives.
+            if (e.code != sgb::SGB_INTERNAL_RETRY_NO_WAIT_KERNELS || !ctx || ctx->world > 1 || ctx->fused_disabled) throw;
+            ctx->fused_disabled = true;
+            ctx->printf("note: %s; redoing the call with the two-pass kernels (used from now on)\n", e.what());
+            cudaStreamSynchronize(ctx->stream);
+            fn();
+        }
         return SGB_OK;
     } catch (const sgb::Error &e) {
         g_last_error = e.what();
-        return e.code;
+        return e.code == sgb::SGB_INTERNAL_RETRY_NO_WAIT_KERNELS ? SGB_ERR_CUDA : e.code;
     } catch (const std::exception &e) {
         g_last_error = e.what();
         return SGB_ERR_INVALID;

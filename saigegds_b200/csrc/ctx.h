@@ -30,6 +30,9 @@ struct Error : std::runtime_error {
 
 #define SGB_CHECK_LAUNCH() SGB_CUDA(cudaGetLastError())
 
+// internal: a kernel with cross-CTA waits timed out; the C-ABI layer redoes the call on kernels without such waits (api.cu)
+constexpr int SGB_INTERNAL_RETRY_NO_WAIT_KERNELS = -1000;
+
 // Owning device buffer (cudaMalloc / cudaFree), resizable without preserving contents.
 template <typename T>
 struct DevBuf {
@@ -152,6 +155,7 @@ struct Context {
     void require_stored() const {
         if (!stored) throw Error(SGB_ERR_STATE, "no genotypes stored: call sgb_store_2b_geno first");
     }
+    bool fused_disabled = false;         // set after a time-out of the fused kernel: the two-pass kernels take over
     volatile int *async_err = nullptr;   // pinned flag copied back after every fused-kernel launch
     int *async_err_dev = nullptr;        // its device-side source (cleared after an error was reported)
     void sync() {
@@ -160,8 +164,9 @@ struct Context {
             const int code = *async_err;
             *async_err = 0;
             if (async_err_dev) cudaMemsetAsync(async_err_dev, 0, sizeof(int), stream);
-            throw Error(SGB_ERR_CUDA, code == 2 ? "the fused GRM kernel found |e_j| above its a-priori bound (internal error)"
-                                                : "the fused GRM kernel timed out waiting for another CTA (bounded spin)");
+            if (code == 2) throw Error(SGB_ERR_CUDA, "the fused GRM kernel found |e_j| above its a-priori bound (internal error)");
+            throw Error(SGB_INTERNAL_RETRY_NO_WAIT_KERNELS, "a GRM kernel timed out waiting for another CTA or warp (wall-clock bound, "
+                                                             "SGB_WAIT_TIMEOUT_MS)");
         }
     }
     void h2d(void *dst, const void *src, size_t bytes) {

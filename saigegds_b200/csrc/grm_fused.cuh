@@ -46,7 +46,16 @@ constexpr int kFNE = 10;                // e-digit ring (>= kFNBuf: phase B may 
 constexpr int kFNPart = 1;              // partial-dot slots (the publisher drains a slot ~10x faster than a tile takes)
 constexpr int kFHpw = 3;                // half-steps (128 samples) per compute warp: 24 / 8
 constexpr int kFRbw = 6;                // 64-sample row-blocks per compute warp: 48 / 8
-constexpr long long kFSpinMax = 1ll << 22;
+// Cross-CTA / cross-warp waits are bounded by WALL CLOCK (%globaltimer), not by iteration counts: a time-sliced, throttled or
+// instrumented GPU (MPS, compute-sanitizer, cuda-gdb) slows a valid run down by orders of magnitude and must not turn it into an
+// error.  On expiry the kernel raises its error flag and drains; the host then redoes the call with the two-pass kernels, which
+// have no inter-CTA waits (api.cu, guarded()).  Default 2 s, env SGB_WAIT_TIMEOUT_MS.
+__device__ unsigned long long g_wait_timeout_ns = 2000000000ull;
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 constexpr unsigned long long kFArrive = 1ull << 52;   // arrival count lives above bit 52 of a limb
 
 struct FusedSmem {
@@ -67,32 +76,26 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *b) {
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
-// bounded wait; returns false on time-out
-__device__ __forceinline__ bool mbar_wait(unsigned long long *b, unsigned parity, volatile int *err) {
-    const unsigned a = smem_u32(b);
-    for (long long it = 0; it < kFSpinMax; it++) {
+// bounded wait; returns false on time-out (or when another role has already raised the error flag)
+__device__ __forceinline__ bool mbar_wait_a(unsigned a, unsigned parity, volatile int *err) {
+    unsigned long long t0 = 0;
+    for (unsigned it = 0;; it++) {
         unsigned ok;
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(ok) : "r"(a), "r"(parity) : "memory");
         if (ok) return true;
-        if ((it & 1023) == 1023 && *err) return false;
+        if ((it & 255) == 255) {       // warp-uniform decision: the callers go on to warp-collective instructions
+            const unsigned long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            const bool expired = now - t0 > g_wait_timeout_ns;
+            if (__any_sync(__activemask(), expired)) *err = 1;
+            if (__any_sync(__activemask(), *err != 0)) return false;
+        }
     }
-    *err = 1;
-    return false;
 }
+__device__ __forceinline__ bool mbar_wait(unsigned long long *b, unsigned parity, volatile int *err) { return mbar_wait_a(smem_u32(b), parity, err); }
 __device__ __forceinline__ void mbar_arrive_a(unsigned a) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
-}
-__device__ __forceinline__ bool mbar_wait_a(unsigned a, unsigned parity, volatile int *err) {
-    for (long long it = 0; it < kFSpinMax; it++) {
-        unsigned ok;
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-        if (ok) return true;
-        if ((it & 1023) == 1023 && *err) return false;
-    }
-    *err = 1;
-    return false;
 }
 __device__ __forceinline__ bool mbar_test_a(unsigned a, unsigned parity) {
     unsigned ok;
@@ -244,6 +247,7 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
                 unsigned long long x0 = 0, x1 = 0;
                 bool ok = true;
                 // optimistic full read; while the tile is incomplete only lane 0 probes (its two limbs), backing off in between
+                unsigned long long t_poll = 0;
                 for (int it = 0;;) {
                     x0 = ld_relaxed_u64(src);
                     x1 = ld_relaxed_u64(src + A.acc_stride);
@@ -256,7 +260,11 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
                             const unsigned long long p0 = ld_relaxed_u64(src), p1 = ld_relaxed_u64(src + A.acc_stride);
                             probe = ((p0 + (kFArrive >> 1)) >> 52) == want && ((p1 + (kFArrive >> 1)) >> 52) == want;
                         }
-                        if (++it >= (1 << 20) || ((it & 255) == 0 && *err)) { *err = 1; ok = false; probe = true; }
+                        if ((++it & 63) == 0) {
+                            const unsigned long long now = global_ns();
+                            if (t_poll == 0) t_poll = now;
+                            if (*err || now - t_poll > g_wait_timeout_ns) { *err = 1; ok = false; probe = true; }
+                        }
                         probe = __shfl_sync(0xffffffffu, probe ? 1 : 0, 0) != 0;
                         ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
                     }
@@ -306,9 +314,15 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
             if (3 < T) w3 = ld_relaxed_u64(gd + 96);
             bool ok = true;
             for (int64_t tb = 0; tb < T; tb++) {
+                unsigned long long t_poll = 0;
                 for (int it = 0; !__all_sync(0xffffffffu, w0 != 0); it++) {
                     __nanosleep(poll_ns);
-                    if (it >= (1 << 20) || ((it & 255) == 255 && *err)) { *err = 1; ok = false; break; }
+                    if ((it & 63) == 63) {
+                        const unsigned long long now = global_ns();
+                        if (t_poll == 0) t_poll = now;
+                        const bool bad = *err || now - t_poll > g_wait_timeout_ns;
+                        if (__any_sync(0xffffffffu, bad)) { *err = 1; ok = false; break; }
+                    }
                     if (w0 == 0) w0 = ld_relaxed_u64(gd + tb * 32);
                 }
                 if (!ok) break;

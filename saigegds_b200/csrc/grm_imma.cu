@@ -1450,6 +1450,10 @@ void imma_prepare(Context &c) {
                 }
             }
         }
+        if (const char *e = getenv("SGB_WAIT_TIMEOUT_MS")) {
+            const unsigned long long ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
+            SGB_CUDA(cudaMemcpyToSymbolAsync(g_wait_timeout_ns, &ns, sizeof(ns), 0, cudaMemcpyHostToDevice, c.stream));
+        }
         if (const char *e = getenv("SGB_UMMA_MIN_COLS")) { p->um_min_cols = atoi(e); if (p->um_min_cols <= 0) p->um_min_cols = INT_MAX; }
         if (const char *e = getenv("SGB_UMMA_GATHER_COLS")) p->um_gather_cols = atoi(e);
         if (const char *e = getenv("SGB_SPARSE_FORK")) p->opt_fork = atoi(e);
@@ -1477,9 +1481,9 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
     // The fused kernel pays ~1 us of cross-CTA latency per 32-variant tile whatever the slice width, so it only beats the two
     // HBM passes when every CTA's slice is (nearly) full: SGB_KERNEL_AUTO takes it from 10 of the 12 K-steps per CTA upwards
     // (N >= ~380K on 148 SMs) and the two-pass kernels otherwise; SGB_KERNEL_IMMA forces it whenever the shape allows.
-    const bool use_fused = p->fused_ok && (c.kernel == SGB_KERNEL_IMMA || (c.kernel == SGB_KERNEL_AUTO && p->f_ks_per_cta >= 10));
+    const bool use_fused = p->fused_ok && !c.fused_disabled && (c.kernel == SGB_KERNEL_IMMA || (c.kernel == SGB_KERNEL_AUTO && p->f_ks_per_cta >= 10));
     // several right-hand sides: one pass over the packed matrix for all of them on tcgen05 (grm_umma.cuh)
-    if ((c.kernel == SGB_KERNEL_UMMA || (c.kernel == SGB_KERNEL_AUTO && k >= p->um_min_cols)) && !p->um.failed) {
+    if ((c.kernel == SGB_KERNEL_UMMA || (c.kernel == SGB_KERNEL_AUTO && k >= p->um_min_cols)) && !p->um.failed && !c.fused_disabled) {
         umma_prepare(c, p);
         if (p->um.ready) {
             c.async_err = p->um.herr.p;

@@ -26,6 +26,11 @@ void grm_mv_device(Context &c, const double *b, double *out, int k) {
         c.stats.n_product_launches += k;
     }
     if (c.world > 1) comm_allreduce_sum(c, out, (size_t)c.N * k);
+    if (c.profiling) {
+        char nm[48];
+        snprintf(nm, sizeof(nm), "[calls] grm_mv k=%02d", k);
+        c.ktimes[nm].second += 1;
+    }
     c.stats.n_products += k;
 }
 

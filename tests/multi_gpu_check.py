@@ -43,6 +43,17 @@ def main():
         err = np.max(np.abs(got - want)) / np.max(np.abs(want))
         assert err < 1e-12, (kern, err)
     ctx.set_kernel("auto"); ref.set_kernel("auto")
+    # batched tcgen05 path on the shards (k >= 2) against the single-GPU single-RHS kernel, and N-invariance of b'(GRM b)
+    B = np.random.default_rng(4).standard_normal((n, 6))
+    gotB = ctx.get_crossprod_b_grm(B)
+    ref.set_kernel("imma2")
+    for c in range(6):
+        wantc = ref.get_crossprod_b_grm(B[:, c])
+        errc = np.max(np.abs(gotB[:, c] - wantc)) / np.max(np.abs(wantc))
+        assert errc < 1e-11, ("batched", c, errc)
+    ref.set_kernel("auto")
+    inv = float(vec @ ctx.get_crossprod_b_grm(vec)), float(vec @ ref.get_crossprod_b_grm(vec))
+    assert abs(inv[0] - inv[1]) / inv[1] < 1e-12, inv
     w = np.full(n, 0.2)
     x, it = ctx.PCG_diag_sigma(w, np.array([1.0, 0.5]), vec)
     xr, itr = ref.PCG_diag_sigma(w, np.array([1.0, 0.5]), vec)
@@ -61,7 +72,8 @@ def main():
     assert np.allclose(vr["ratio"][order], g["vr_ratio"], rtol=1e-6)
     dist.barrier()
     if rank == 0:
-        print("multi-GPU check ok: world=%d tau=%r" % (world, glmm["tau"]))
+        print("multi-GPU check ok: world=%d tau=%r b'Ab sharded=%.15g single=%.15g (sharded product, batched product, PCG, fit, "
+              "variance ratio vs single GPU / reference golden)" % (world, glmm["tau"], inv[0], inv[1]))
     dist.destroy_process_group()
 
 

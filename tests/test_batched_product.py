@@ -169,3 +169,12 @@ def test_full_size_batched_product(gpu):
     finally:
         gpu.set_kernel("auto")
         gpu.store_synthetic(1024, 64)
+
+
+def test_synthetic_generator_matches_the_oracle_generator(gpu):
+    """bench.py feeds the CPU arm with the oracle's restatement of the device generator: the bytes must be identical."""
+    from oracle import oracle as orc
+    for n, m, off, seed in ((1003, 64, 0, 11), (4099, 130, 977, 200), (50000, 96, 12345, 200)):
+        dev = gpu.synth_to_host(n, m, off, seed=seed, missing_rate=0.005)
+        cpu = orc.synth_geno(n, m, off, seed, 0.005)
+        assert np.array_equal(dev, cpu), (n, m, off, seed)

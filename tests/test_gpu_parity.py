@@ -364,8 +364,9 @@ def test_error_behaviour(gpu, fx):
     c.close()
 
 
-def test_two_gpu_sharding_matches_single_gpu():
-    """Variant-sharded product / PCG / fit over NCCL on 2 GPUs (skipped on a 1-GPU box)."""
+def test_multi_gpu_sharding_matches_single_gpu():
+    """Variant-sharded product (single-RHS and batched) / PCG / fit / variance ratio over NCCL on all GPUs of the box (2, 4 or 8;
+    skipped on a 1-GPU box).  tests/multi_gpu_check.py can also be launched by hand; its log is kept under profiles/."""
     import os
     import subprocess
     import sys
@@ -373,7 +374,7 @@ def test_two_gpu_sharding_matches_single_gpu():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(torch.cuda.device_count()), "--master-addr", "127.0.0.1",
            "--master-port", "29517", os.path.join(root, "tests", "multi_gpu_check.py")]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
     assert r.returncode == 0, r.stdout.decode()[-3000:]

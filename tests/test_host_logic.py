@@ -136,3 +136,20 @@ def test_fixture_gds_bytes_are_what_store_gds_geno_takes(fx):
     alt = ((a0 == 1) | (a0 == 2)).sum(axis=1) + ((a1 == 1) | (a1 == 2)).sum(axis=1)
     af = alt / valid
     assert np.array_equal(np.minimum(af, 1 - af) >= 0.005, fx.keep)          # seqSetFilterCond(maf=0.005), R/saige_main.r:319
+
+
+def test_oracle_synthetic_generator_is_shard_invariant_and_calibrated():
+    """The CPU restatement of the device generator (bench.py's CPU arm): a shard equals the rows of the full matrix, pad codes
+    are 3, ~0.5 % missing, allele frequencies spread over (0.005, 0.5)."""
+    from oracle import oracle as orc
+    orc.build()
+    full = orc.synth_geno(1003, 64, 0, 11, 0.005, 2)
+    part = orc.synth_geno(1003, 20, 30, 11, 0.005, 1)
+    assert np.array_equal(full[30:50], part)
+    codes = np.stack([(full >> s) & 3 for s in (0, 2, 4, 6)], axis=2).reshape(64, -1)
+    assert np.all(codes[:, 1003:] == 3)
+    assert 0.0 < np.mean(codes[:, :1003] == 3) < 0.02
+    big = orc.synth_geno(20000, 200, 0, 200, 0.005, 2)
+    c = np.stack([(big >> s) & 3 for s in (0, 2, 4, 6)], axis=2).reshape(200, -1)[:, :20000]
+    af = np.where(c == 3, 0, c).sum(1) / (2.0 * (c != 3).sum(1))
+    assert 0.004 < af.min() < 0.05 and 0.4 < af.max() < 0.51

@@ -263,3 +263,24 @@ def test_device_body_matches_oracle_for_other_covariate_counts(body, trait, K):
     assert ref["valid"].sum() > 100
     compare(body(m, 0.9, d, **kw), ref, 1e-8)
     compare(body(m, 0.9, pack(d), **kw), ref, 1e-8)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("trait", ["binary", "quantitative"])
+@pytest.mark.parametrize("K", [1, 8, 17, 32])
+def test_gpu_score_test_for_other_covariate_counts(gpu, trait, K):
+    """The CUDA kernels for covariate counts other than the fixture's K = 3: exact-K instantiations (1, 8) and the guarded
+    K > 16 variant with 128-sample tiles (17, 32), both kernel paths, dosage and packed input, against the oracle."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(100 + K)
+    n = 700
+    m = synthetic_model(rng, n, K, trait)
+    d = random_dosages(rng, n, 200, integer=True)
+    kw = dict(maf=0.002, mac=2.0, missing=0.35, spa_pval=0.3)
+    ref = orc.score_test(m, d, 0.9, **kw)
+    assert ref["valid"].sum() > 100
+    st = sg.ScoreTest(dict(m, var_ratio=0.9, **kw), gpu)
+    for path in ("tiled", "per_variant"):
+        st.set_path(path)
+        compare(st.test(d), ref, 1e-8)
+        compare(st.test(pack(d)), ref, 1e-8)
