@@ -8,6 +8,7 @@ from .api import (Context, DeviceArray, NullModel, default_context, make_param, 
                   seqFitNullGLMM_SPA, sparse_to_packed)
 from .assoc import ScoreTest, init_nullmod, seqAssocGLMM_SPA  # noqa: F401
 from .dist import init_comm_from_torch, shard_range  # noqa: F401
+from .gds import GdsFormatError, read_gds_genotypes, store_from_gds  # noqa: F401
 
 __all__ = ["Context", "DeviceArray", "NullModel", "default_context", "make_param", "seqFitNullGLMM_SPA", "saige_get_sparse", "sparse_to_packed", "ScoreTest", "init_nullmod", "seqAssocGLMM_SPA",
-           "init_comm_from_torch", "shard_range", "build", "SgbError", "InvalidArgument", "OverflowErrorSGB"]
+           "init_comm_from_torch", "shard_range", "read_gds_genotypes", "store_from_gds", "GdsFormatError", "build", "SgbError", "InvalidArgument", "OverflowErrorSGB"]

@@ -76,22 +76,32 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *b) {
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
-// bounded wait; returns false on time-out (or when another role has already raised the error flag)
-__device__ __forceinline__ bool mbar_wait_a(unsigned a, unsigned parity, volatile int *err) {
-    unsigned long long t0 = 0;
+// bounded wait; returns false on time-out (or when another role has already raised the error flag).  The hot path is a bare
+// try_wait loop (each try_wait already suspends the thread for a while); only a wait that outlasts it enters the wall-clock
+// bounded slow path, which is kept out of line so that it costs the callers neither registers nor instructions.
+__device__ __forceinline__ bool mbar_wait_slow(unsigned a, unsigned parity, volatile int *err) {
+    const unsigned long long t0 = global_ns();
     for (unsigned it = 0;; it++) {
         unsigned ok;
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(ok) : "r"(a), "r"(parity) : "memory");
         if (ok) return true;
-        if ((it & 255) == 255) {       // warp-uniform decision: the callers go on to warp-collective instructions
-            const unsigned long long now = global_ns();
-            if (t0 == 0) t0 = now;
-            const bool expired = now - t0 > g_wait_timeout_ns;
+        if ((it & 63) == 63) {         // warp-uniform decision: the callers go on to warp-collective instructions
+            const bool expired = global_ns() - t0 > g_wait_timeout_ns;
             if (__any_sync(__activemask(), expired)) *err = 1;
             if (__any_sync(__activemask(), *err != 0)) return false;
         }
     }
+}
+__device__ __forceinline__ bool mbar_wait_a(unsigned a, unsigned parity, volatile int *err) {
+#pragma unroll 1
+    for (int it = 0; it < 1024; it++) {
+        unsigned ok;
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    return mbar_wait_slow(a, parity, err);
 }
 __device__ __forceinline__ bool mbar_wait(unsigned long long *b, unsigned parity, volatile int *err) { return mbar_wait_a(smem_u32(b), parity, err); }
 __device__ __forceinline__ void mbar_arrive_a(unsigned a) {

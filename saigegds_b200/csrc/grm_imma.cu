@@ -1105,7 +1105,7 @@ void umma_prepare(Context &c, ImmaPlan *p) {
         u.e.ensure((size_t)kUMaxCols * M); u.hm.ensure((size_t)kUMaxCols * M); u.u.ensure((size_t)kUMaxCols * M);
         u.corr.ensure((size_t)kUMaxCols * N);
         u.part.ensure((size_t)4 * std::max((size_t)p->n_stiles * M, (size_t)p->n_vtiles * N));
-        u.vt.ensure((size_t)32 * std::max(M, N));
+        u.vt.ensure((size_t)32 * (std::max(M, N) + 1));
         u.scal.ensure((size_t)kUMaxCols * kUScal);
         u.red.ensure((size_t)kUMaxCols * 2 * 1024);
         u.counter.ensure(kUMaxCols);
@@ -1148,11 +1148,11 @@ void launch_sparse_multi(Context &c, ImmaPlan *p, bool by_variant, const double 
         const int grid = c.sm_count * 8;
         c.prof_begin();
         if (ncols > 16) {
-            transpose_cols_kernel<32><<<(unsigned)((Cn + 255) / 256), 256, 0, c.stream>>>(vec, ldv, ncols, Cn, u.vt.get());
-            sparse_rows_gather_kernel<32><<<grid, 256, 0, c.stream>>>(ptr, idx, u.vt.get(), ncols, R, out, ldo);
+            transpose_cols_kernel<32><<<(unsigned)((Cn + 256) / 256), 256, 0, c.stream>>>(vec, ldv, ncols, Cn, u.vt.get());
+            sparse_rows_gather_kernel<32><<<grid, 256, 0, c.stream>>>(ptr, idx, u.vt.get(), Cn, ncols, R, out, ldo);
         } else {
-            transpose_cols_kernel<16><<<(unsigned)((Cn + 255) / 256), 256, 0, c.stream>>>(vec, ldv, ncols, Cn, u.vt.get());
-            sparse_rows_gather_kernel<16><<<grid, 256, 0, c.stream>>>(ptr, idx, u.vt.get(), ncols, R, out, ldo);
+            transpose_cols_kernel<16><<<(unsigned)((Cn + 256) / 256), 256, 0, c.stream>>>(vec, ldv, ncols, Cn, u.vt.get());
+            sparse_rows_gather_kernel<16><<<grid, 256, 0, c.stream>>>(ptr, idx, u.vt.get(), Cn, ncols, R, out, ldo);
         }
         SGB_CHECK_LAUNCH();
         c.prof_end(by_variant ? "sparse_rows_gather_kernel (U)" : "sparse_rows_gather_kernel (corr)");

@@ -560,42 +560,46 @@ __global__ void __launch_bounds__(kEmThreads) sparse_ell_multi_kernel(const int6
 // load -- no shared-memory bank conflicts, no partial sums, the summation order of a row is its list order (deterministic).
 template <int W>
 __global__ void __launch_bounds__(256) sparse_rows_gather_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx,
-                                                                 const double *__restrict__ vt, int ncols, int64_t R, double *__restrict__ out,
-                                                                 int64_t ldo) {
+                                                                 const double *__restrict__ vt, int64_t zero_row, int ncols, int64_t R,
+                                                                 double *__restrict__ out, int64_t ldo) {
     constexpr int RPW = 32 / W;                       // rows per warp
+    constexpr int NB = 16;                            // loads in flight per lane: the gather is bound by L2 latency x occupancy
     const int lane = threadIdx.x & 31, sub = lane / W, col = lane % W;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const double *vcol = vt + col;
     for (int64_t rb = warp0 * RPW; rb < R; rb += n_warps * RPW) {
         const int64_t r = rb + sub;
         int64_t e0 = 0, e1 = 0;
         if (r < R) { e0 = ptr[r]; e1 = ptr[r + 1]; }
         int64_t len = e1 - e0, maxlen = len;
         if (RPW > 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 16));
-        double a0 = 0, a1 = 0;
+        double acc = 0;
         for (int64_t base = 0; base < maxlen; base += W) {
             const int64_t me = base + col;
-            const int my = (me < len) ? idx[e0 + me] : -1;
+            const int64_t my = (me < len) ? (int64_t)idx[e0 + me] : zero_row;     // padding reads the all-zero row: no predicates below
             const int cnt = (int)min((int64_t)W, maxlen - base);
-#pragma unroll 8
-            for (int t = 0; t < cnt; t += 2) {
-                const int i0 = __shfl_sync(0xffffffffu, my, t, W), i1 = __shfl_sync(0xffffffffu, my, t + 1, W);
-                const double v0 = (i0 >= 0) ? vt[(size_t)i0 * W + col] : 0.0;
-                const double v1 = (i1 >= 0 && t + 1 < cnt) ? vt[(size_t)i1 * W + col] : 0.0;
-                a0 += v0;
-                a1 += v1;
+            for (int t0 = 0; t0 < cnt; t0 += NB) {
+                double v[NB];
+#pragma unroll
+                for (int u = 0; u < NB; u++) {
+                    const int64_t i = __shfl_sync(0xffffffffu, (t0 + u < W) ? my : zero_row, (t0 + u) & (W - 1), W);
+                    v[u] = __ldg(vcol + (size_t)((t0 + u < cnt) ? i : zero_row) * W);
+                }
+#pragma unroll
+                for (int u = 0; u < NB; u++) acc += v[u];                        // list order: deterministic
             }
         }
-        if (r < R && col < ncols) out[(size_t)col * ldo + r] = a0 + a1;
+        if (r < R && col < ncols) out[(size_t)col * ldo + r] = acc;
     }
 }
-// dst[i][c] = src[c][i] for c < ncols, 0 for ncols <= c < W.  grid ceil(n / 256)
+// dst[i][c] = src[c][i] for c < ncols, 0 for ncols <= c < W; row n is the all-zero row.  grid ceil((n + 1) / 256)
 template <int W>
 __global__ void transpose_cols_kernel(const double *__restrict__ src, int64_t ld, int ncols, int64_t n, double *__restrict__ dst) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i > n) return;
     double v[W];
 #pragma unroll
-    for (int c = 0; c < W; c++) v[c] = (c < ncols) ? src[(size_t)c * ld + i] : 0.0;
+    for (int c = 0; c < W; c++) v[c] = (c < ncols && i < n) ? src[(size_t)c * ld + i] : 0.0;
     double2 *d = reinterpret_cast<double2 *>(dst + (size_t)i * W);
 #pragma unroll
     for (int c = 0; c < W; c += 2) d[c >> 1] = make_double2(v[c], v[c + 1]);
