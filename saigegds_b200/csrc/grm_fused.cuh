@@ -60,6 +60,7 @@ constexpr unsigned long long kFArrive = 1ull << 52;   // arrival count lives abo
 
 struct FusedSmem {
     unsigned long long full[kFNBuf], empty[kFNBuf], part_full[kFNPart], part_free[kFNPart], ready[kFNE];
+    unsigned long long deadline;        // %globaltimer value after which every wait of this CTA gives up
     alignas(16) int part[kFNPart][kFComputeWarps][kFV * 8];   // per-warp partial dots x 64: [variant][digit plane]
     alignas(16) unsigned char efrag[kFNE][256];
 };
@@ -77,33 +78,25 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned b
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
 // bounded wait; returns false on time-out (or when another role has already raised the error flag).  The hot path is a bare
-// try_wait loop (each try_wait already suspends the thread for a while); only a wait that outlasts it enters the wall-clock
-// bounded slow path, which is kept out of line so that it costs the callers neither registers nor instructions.
-__device__ __forceinline__ bool mbar_wait_slow(unsigned a, unsigned parity, volatile int *err) {
-    const unsigned long long t0 = global_ns();
-    for (unsigned it = 0;; it++) {
-        unsigned ok;
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-        if (ok) return true;
-        if ((it & 63) == 63) {         // warp-uniform decision: the callers go on to warp-collective instructions
-            const bool expired = global_ns() - t0 > g_wait_timeout_ns;
-            if (__any_sync(__activemask(), expired)) *err = 1;
-            if (__any_sync(__activemask(), *err != 0)) return false;
-        }
-    }
-}
-__device__ __forceinline__ bool mbar_wait_a(unsigned a, unsigned parity, volatile int *err) {
+// try_wait loop (a try_wait already suspends the thread for a while); every 1,024 misses the error flag and the kernel's
+// wall-clock deadline (a shared-memory word written at kernel start: nothing extra stays live in registers) are looked at.
+__device__ __forceinline__ bool mbar_wait_a(unsigned a, unsigned parity, volatile int *err, const volatile unsigned long long *deadline) {
+    for (;;) {
 #pragma unroll 1
-    for (int it = 0; it < 1024; it++) {
-        unsigned ok;
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-        if (ok) return true;
+        for (int it = 0; it < 1024; it++) {
+            unsigned ok;
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+            if (ok) return true;
+        }
+        // warp-uniform decision: the callers go on to warp-collective instructions
+        if (__any_sync(__activemask(), global_ns() > *deadline)) *err = 1;
+        if (__any_sync(__activemask(), *err != 0)) return false;
     }
-    return mbar_wait_slow(a, parity, err);
 }
-__device__ __forceinline__ bool mbar_wait(unsigned long long *b, unsigned parity, volatile int *err) { return mbar_wait_a(smem_u32(b), parity, err); }
+__device__ __forceinline__ bool mbar_wait(unsigned long long *b, unsigned parity, volatile int *err, const volatile unsigned long long *deadline) {
+    return mbar_wait_a(smem_u32(b), parity, err, deadline);
+}
 __device__ __forceinline__ void mbar_arrive_a(unsigned a) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
 }
@@ -182,7 +175,9 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
     const int lag = A.lag;
     volatile int *err = A.err;
 
+    const volatile unsigned long long *dl = &S.deadline;
     if (tid == 0) {
+        S.deadline = global_ns() + g_wait_timeout_ns;
         if (smem_u32(smem_raw) & 1023u) *A.err = 3;     // SWIZZLE_128B needs 1 KB aligned tiles
         for (int i = 0; i < kFNBuf; i++) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], kFComputeWarps); }
         for (int i = 0; i < kFNPart; i++) { mbar_init(&S.part_full[i], kFComputeWarps); mbar_init(&S.part_free[i], 1); }
@@ -199,7 +194,7 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
         for (int64_t t = 0; t < T; t++) {
             const int b = (int)(t % kFNBuf);
-            if (t >= kFNBuf && !mbar_wait(&S.empty[b], (unsigned)(((t / kFNBuf) - 1) & 1), err)) break;
+            if (t >= kFNBuf && !mbar_wait(&S.empty[b], (unsigned)(((t / kFNBuf) - 1) & 1), err, dl)) break;
             if (lane == 0) mbar_expect_tx(&S.full[b], kFTileBytes);     // out-of-bounds rows / columns are zero-filled and counted
             __syncwarp();
             if (lane < kFPanels)
@@ -210,7 +205,7 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
         // ------------------------------------------------------------------ publisher: lane <-> variant
         for (int64_t s = 0; s < T; s++) {
             const int a = (int)(s % kFNPart);
-            if (!mbar_wait(&S.part_full[a], (unsigned)((s / kFNPart) & 1), err)) break;
+            if (!mbar_wait(&S.part_full[a], (unsigned)((s / kFNPart) & 1), err, dl)) break;
             int x[8];
 #pragma unroll
             for (int l = 0; l < 8; l++) x[l] = 0;
@@ -257,7 +252,6 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
                 unsigned long long x0 = 0, x1 = 0;
                 bool ok = true;
                 // optimistic full read; while the tile is incomplete only lane 0 probes (its two limbs), backing off in between
-                unsigned long long t_poll = 0;
                 for (int it = 0;;) {
                     x0 = ld_relaxed_u64(src);
                     x1 = ld_relaxed_u64(src + A.acc_stride);
@@ -270,11 +264,7 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
                             const unsigned long long p0 = ld_relaxed_u64(src), p1 = ld_relaxed_u64(src + A.acc_stride);
                             probe = ((p0 + (kFArrive >> 1)) >> 52) == want && ((p1 + (kFArrive >> 1)) >> 52) == want;
                         }
-                        if ((++it & 63) == 0) {
-                            const unsigned long long now = global_ns();
-                            if (t_poll == 0) t_poll = now;
-                            if (*err || now - t_poll > g_wait_timeout_ns) { *err = 1; ok = false; probe = true; }
-                        }
+                        if ((++it & 255) == 0 && (*err || global_ns() > *dl)) { *err = 1; ok = false; probe = true; }
                         probe = __shfl_sync(0xffffffffu, probe ? 1 : 0, 0) != 0;
                         ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
                     }
@@ -324,15 +314,9 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
             if (3 < T) w3 = ld_relaxed_u64(gd + 96);
             bool ok = true;
             for (int64_t tb = 0; tb < T; tb++) {
-                unsigned long long t_poll = 0;
                 for (int it = 0; !__all_sync(0xffffffffu, w0 != 0); it++) {
                     __nanosleep(poll_ns);
-                    if ((it & 63) == 63) {
-                        const unsigned long long now = global_ns();
-                        if (t_poll == 0) t_poll = now;
-                        const bool bad = *err || now - t_poll > g_wait_timeout_ns;
-                        if (__any_sync(0xffffffffu, bad)) { *err = 1; ok = false; break; }
-                    }
+                    if ((it & 255) == 255 && __any_sync(0xffffffffu, *err || global_ns() > *dl)) { *err = 1; ok = false; break; }
                     if (w0 == 0) w0 = ld_relaxed_u64(gd + tb * 32);
                 }
                 if (!ok) break;
@@ -447,10 +431,10 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
             uint32_t fa[2][kFHpw][4], fb[kFRbw][4], bfx = 0, bfy = 0;
             int accA[2][4][4];
             if (DA) {
-                if (!mbar_wait_a(full0 + bA * 8, (unsigned)phA, err)) return false;
+                if (!mbar_wait_a(full0 + bA * 8, (unsigned)phA, err, dl)) return false;
             }
             if (DB) {
-                if (!mbar_wait_a(ready0 + eB * 8, (unsigned)phE, err)) return false;
+                if (!mbar_wait_a(ready0 + eB * 8, (unsigned)phE, err, dl)) return false;
             }
             if (DA) {
                 // A fragments ([16 variants x 32 bytes]: matrices (rows 0-7 | 8-15) x (bytes 0-15 | 16-31)); half-steps beyond
@@ -501,7 +485,7 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
             if (DA) {
                 // partial dots -> this warp's slot: rows g / g+8 of each row-block, digit planes 2tq, 2tq+1.
                 // ((a0*4 + a1)*4 + a2)*4 + a3 = 64 * (sum of the four planes with their 4^t factors removed)
-                if (s >= 1 && !mbar_wait_a(pfree0, (unsigned)phP, err)) return false;
+                if (s >= 1 && !mbar_wait_a(pfree0, (unsigned)phP, err, dl)) return false;
 #pragma unroll
                 for (int r = 0; r < 2; r++)
 #pragma unroll

@@ -58,6 +58,7 @@ constexpr unsigned kUStageCol = 384;    // A-operand slots: column 384 + 64 mt +
 
 struct UmmaSmem {
     unsigned long long p_full[kUNP], p_empty[kUNP], b_full[kUNB], a_full[2][2], mma_done[2][kUNB], acc_full[2];
+    unsigned long long deadline;        // %globaltimer value after which every wait of this CTA gives up
     unsigned tmem_base;
 };
 constexpr int kUSmemBytes = kUNP * kUPackBytes + kUNB * kUMaxN * 128 + 1024 /* alignment slack */ + (int)sizeof(UmmaSmem);
@@ -123,7 +124,9 @@ __global__ void __launch_bounds__(kUThreads, 1) umma_gemm_kernel(const __grid_co
     const int n_st = n_box * 4;                             // stages of 128 contraction elements
     const int row0 = blockIdx.x * kURows;
 
+    const volatile unsigned long long *dl = &S.deadline;
     if (tid == 0) {
+        S.deadline = global_ns() + g_wait_timeout_ns;
         for (int i = 0; i < kUNP; i++) { mbar_init(&S.p_full[i], 1); mbar_init(&S.p_empty[i], kUExpWarps); }
         for (int i = 0; i < kUNB; i++) { mbar_init(&S.b_full[i], 1); mbar_init(&S.mma_done[0][i], 1); mbar_init(&S.mma_done[1][i], 1); }
         for (int i = 0; i < 2; i++) { mbar_init(&S.a_full[0][i], 4); mbar_init(&S.a_full[1][i], 4); mbar_init(&S.acc_full[i], 1); }
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(kUThreads, 1) umma_gemm_kernel(const __grid_co
             bool ok = true;
             for (int bx = 0; bx < n_box && ok; bx++) {
                 const int ps = bx % kUNP;
-                if (bx >= kUNP) ok = mbar_wait(&S.p_empty[ps], (unsigned)(((bx / kUNP) - 1) & 1), err);
+                if (bx >= kUNP) ok = mbar_wait(&S.p_empty[ps], (unsigned)(((bx / kUNP) - 1) & 1), err, dl);
                 if (!ok) break;
                 mbar_expect_tx(&S.p_full[ps], kUPackBytes);
                 tma_load_2d(pack + (size_t)ps * kUPackBytes, &tmap_p, (box0 + bx) * kUBoxBytes, row0, &S.p_full[ps], policy);
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(kUThreads, 1) umma_gemm_kernel(const __grid_co
                     const int st = bx * 4 + s4, bs = st % kUNB;
                     if (st >= kUNB) {     // the tile's previous user (stage st - 4) must be through both M-tiles
                         const unsigned par = (unsigned)(((st / kUNB) - 1) & 1);
-                        ok = mbar_wait(&S.mma_done[0][bs], par, err) && mbar_wait(&S.mma_done[1][bs], par, err);
+                        ok = mbar_wait(&S.mma_done[0][bs], par, err, dl) && mbar_wait(&S.mma_done[1][bs], par, err, dl);
                     }
                     if (!ok) break;
                     mbar_expect_tx(&S.b_full[bs], btile_bytes);
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(kUThreads, 1) umma_gemm_kernel(const __grid_co
             for (int st = 0; st < n_st && ok; st++) {
                 const int bs = st % kUNB, as = st & 1;
                 if (PROF) t0 = clock64();
-                ok = mbar_wait(&S.a_full[mt][as], (unsigned)((st >> 1) & 1), err);
+                ok = mbar_wait(&S.a_full[mt][as], (unsigned)((st >> 1) & 1), err, dl);
                 if (!ok) break;
                 if (PROF) { t1 = clock64(); c_wa += t1 - t0; }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(kUThreads, 1) umma_gemm_kernel(const __grid_co
         for (int st = es; st < n_st && ok; st += 2) {
             const int bx = st >> 2, ps = bx % kUNP, bs = st % kUNB;
             if (PROF) t0 = clock64();
-            if ((st & 3) < 2) ok = mbar_wait(&S.p_full[ps], (unsigned)((bx / kUNP) & 1), err);     // first stage of this set in the box
+            if ((st & 3) < 2) ok = mbar_wait(&S.p_full[ps], (unsigned)((bx / kUNP) & 1), err, dl);     // first stage of this set in the box
             if (!ok) break;
             if (PROF) { t1 = clock64(); c_wp += t1 - t0; }
             const uint8_t *src = pack + (size_t)ps * kUPackBytes + prow;
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(kUThreads, 1) umma_gemm_kernel(const __grid_co
                 for (int t = 0; t < 4; t++) x[4 * i + t] = (ws[i] >> (2 * t)) & 0x03030303u;
             if (PROF) { t0 = clock64(); c_ld += t0 - t1; }
             // A slot `es` is free when the MMAs of stage st - 2 (this M-tile) are done
-            if (st >= 2) ok = mbar_wait(&S.mma_done[mt][(st - 2) % kUNB], (unsigned)(((st - 2) / kUNB) & 1), err);
+            if (st >= 2) ok = mbar_wait(&S.mma_done[mt][(st - 2) % kUNB], (unsigned)(((st - 2) / kUNB) & 1), err, dl);
             if (!ok) break;
             if (PROF) { t1 = clock64(); c_we += t1 - t0; }
             tmem_st32(tb + lane_base + kUStageCol + mt * 64 + es * 32, x);
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(kUThreads, 1) umma_gemm_kernel(const __grid_co
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             if (PROF) { t0 = clock64(); c_st += t0 - t1; }
             // the issuer waits on a_full only: make sure the stage's digit tile has landed before handing over
-            ok = mbar_wait(&S.b_full[bs], (unsigned)((st / kUNB) & 1), err);
+            ok = mbar_wait(&S.b_full[bs], (unsigned)((st / kUNB) & 1), err, dl);
             if (!ok) break;
             __syncwarp();
             if (lane == 0) {
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(kUThreads, 1) umma_gemm_kernel(const __grid_co
             o[8] = clock64() - t_begin; o[9] = c_wp; o[10] = c_ld; o[11] = c_we; o[12] = c_st; o[13] = c_ar;
         }
         // ------------------------------------------------------------------ epilogue: set es takes the column groups g % 2 == es
-        if (ok) ok = mbar_wait(&S.acc_full[mt], 0u, err);
+        if (ok) ok = mbar_wait(&S.acc_full[mt], 0u, err, dl);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (ok) {
             const int64_t row = (int64_t)row0 + r;
