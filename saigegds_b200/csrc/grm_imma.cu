@@ -66,6 +66,7 @@ struct ImmaPlan {
     // [k][lane] of 16-bit offsets padded to the longest row of the group with kSpTile (a zero slot of the vector tile)
     DevBuf<int64_t> mv_gstart, ms_gstart;   // [n_tiles * n_groups + 1] block starts (entries, multiples of 32)
     DevBuf<uint16_t> mv_ell, ms_ell;
+    int um_gather_w = 16;    // columns per pass of the row-gather kernel: 8, 16 or 32 (env SGB_UMMA_GATHER_W)
     int um_gather_cols = 8;  // batched path: more columns than this take the row-gather sparse kernel (env SGB_UMMA_GATHER_COLS)
     int um_min_cols = 2;     // AUTO: batched tcgen05 path from this many columns (env SGB_UMMA_MIN_COLS; 0 disables)
     bool use_csr = false;    // env SGB_SPARSE_CSR: the older row-per-thread kernel (comparison only)
@@ -1147,16 +1148,27 @@ void launch_sparse_multi(Context &c, ImmaPlan *p, bool by_variant, const double 
         const int32_t *idx = (by_variant ? p->mv_idx : p->ms_idx).get();
         const int grid = c.sm_count * 8;
         c.prof_begin();
-        if (ncols > 16) {
-            transpose_cols_kernel<32><<<(unsigned)((Cn + 256) / 256), 256, 0, c.stream>>>(vec, ldv, ncols, Cn, u.vt.get());
-            sparse_rows_gather_kernel<32><<<grid, 256, 0, c.stream>>>(ptr, idx, u.vt.get(), Cn, ncols, R, out, ldo);
-        } else {
-            transpose_cols_kernel<16><<<(unsigned)((Cn + 256) / 256), 256, 0, c.stream>>>(vec, ldv, ncols, Cn, u.vt.get());
-            sparse_rows_gather_kernel<16><<<grid, 256, 0, c.stream>>>(ptr, idx, u.vt.get(), Cn, ncols, R, out, ldo);
+        // passes of W columns: narrower rows keep the transposed block smaller (better L2 hit rate) at the price of re-reading the
+        // index lists; measured best at W = 16 (profiles/r02_multicol_*.json)
+        const int W = p->um_gather_w;
+        for (int c0 = 0; c0 < ncols; c0 += W) {
+            const int nc = std::min(W, ncols - c0);
+            const double *v0 = vec + (size_t)c0 * ldv;
+            double *o0 = out + (size_t)c0 * ldo;
+            if (W == 32) {
+                transpose_cols_kernel<32><<<(unsigned)((Cn + 256) / 256), 256, 0, c.stream>>>(v0, ldv, nc, Cn, u.vt.get());
+                sparse_rows_gather_kernel<32><<<grid, 256, 0, c.stream>>>(ptr, idx, u.vt.get(), Cn, nc, R, o0, ldo);
+            } else if (W == 16) {
+                transpose_cols_kernel<16><<<(unsigned)((Cn + 256) / 256), 256, 0, c.stream>>>(v0, ldv, nc, Cn, u.vt.get());
+                sparse_rows_gather_kernel<16><<<grid, 256, 0, c.stream>>>(ptr, idx, u.vt.get(), Cn, nc, R, o0, ldo);
+            } else {
+                transpose_cols_kernel<8><<<(unsigned)((Cn + 256) / 256), 256, 0, c.stream>>>(v0, ldv, nc, Cn, u.vt.get());
+                sparse_rows_gather_kernel<8><<<grid, 256, 0, c.stream>>>(ptr, idx, u.vt.get(), Cn, nc, R, o0, ldo);
+            }
+            c.stats.n_kernel_launches += 2;
         }
         SGB_CHECK_LAUNCH();
         c.prof_end(by_variant ? "sparse_rows_gather_kernel (U)" : "sparse_rows_gather_kernel (corr)");
-        c.stats.n_kernel_launches += 2;
         return;
     }
     const int nt = by_variant ? p->n_stiles : p->n_vtiles;
@@ -1456,6 +1468,7 @@ void imma_prepare(Context &c) {
         }
         if (const char *e = getenv("SGB_UMMA_MIN_COLS")) { p->um_min_cols = atoi(e); if (p->um_min_cols <= 0) p->um_min_cols = INT_MAX; }
         if (const char *e = getenv("SGB_UMMA_GATHER_COLS")) p->um_gather_cols = atoi(e);
+        if (const char *e = getenv("SGB_UMMA_GATHER_W")) { const int w = atoi(e); if (w == 8 || w == 16 || w == 32) p->um_gather_w = w; }
         if (const char *e = getenv("SGB_SPARSE_FORK")) p->opt_fork = atoi(e);
         if (const char *e = getenv("SGB_FUSED_FORK")) p->opt_fork_fused = atoi(e);
         if (const char *e = getenv("SGB_SPARSE_GRID_MULT")) p->opt_grid_mult = std::max(1, atoi(e));

@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(256) sparse_rows_gather_kernel(const int64_t *
                                                                  const double *__restrict__ vt, int64_t zero_row, int ncols, int64_t R,
                                                                  double *__restrict__ out, int64_t ldo) {
     constexpr int RPW = 32 / W;                       // rows per warp
-    constexpr int NB = 16;                            // loads in flight per lane: the gather is bound by L2 latency x occupancy
+    constexpr int NB = W < 16 ? W : 16;               // loads in flight per lane: the gather is bound by L2 latency x occupancy
     const int lane = threadIdx.x & 31, sub = lane / W, col = lane % W;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const double *vcol = vt + col;
@@ -576,6 +576,7 @@ __global__ void __launch_bounds__(256) sparse_rows_gather_kernel(const int64_t *
         if (r < R) { e0 = ptr[r]; e1 = ptr[r + 1]; }
         int64_t len = e1 - e0, maxlen = len;
         if (RPW > 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 16));
+        if (RPW > 2) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 8));
         double acc = 0;
         for (int64_t base = 0; base < maxlen; base += W) {
             const int64_t me = base + col;
