@@ -66,6 +66,7 @@ struct ImmaPlan {
     // [k][lane] of 16-bit offsets padded to the longest row of the group with kSpTile (a zero slot of the vector tile)
     DevBuf<int64_t> mv_gstart, ms_gstart;   // [n_tiles * n_groups + 1] block starts (entries, multiples of 32)
     DevBuf<uint16_t> mv_ell, ms_ell;
+    int um_fork = 0;         // batched path: sparse corrections on the side stream beside the GEMMs (env SGB_UMMA_FORK)
     int um_gather_w = 16;    // columns per pass of the row-gather kernel: 8, 16 or 32 (env SGB_UMMA_GATHER_W)
     int um_gather_cols = 8;  // batched path: more columns than this take the row-gather sparse kernel (env SGB_UMMA_GATHER_COLS)
     int um_min_cols = 2;     // AUTO: batched tcgen05 path from this many columns (env SGB_UMMA_MIN_COLS; 0 disables)
@@ -1139,7 +1140,8 @@ void umma_prepare(Context &c, ImmaPlan *p) {
 }
 
 // multi-column missing-genotype sums into out[c][row] (rows = variants gathering b, or samples gathering hm)
-void launch_sparse_multi(Context &c, ImmaPlan *p, bool by_variant, const double *vec, int64_t ldv, int ncols, double *out, int64_t ldo) {
+void launch_sparse_multi(Context &c, ImmaPlan *p, bool by_variant, const double *vec, int64_t ldv, int ncols, double *out, int64_t ldo,
+                         cudaStream_t st) {
     ImmaPlan::Umma &u = p->um;
     const int64_t R = by_variant ? c.M : c.N, Cn = by_variant ? c.N : c.M;
     if (ncols > p->um_gather_cols) {
@@ -1156,14 +1158,14 @@ void launch_sparse_multi(Context &c, ImmaPlan *p, bool by_variant, const double 
             const double *v0 = vec + (size_t)c0 * ldv;
             double *o0 = out + (size_t)c0 * ldo;
             if (W == 32) {
-                transpose_cols_kernel<32><<<(unsigned)((Cn + 256) / 256), 256, 0, c.stream>>>(v0, ldv, nc, Cn, u.vt.get());
-                sparse_rows_gather_kernel<32><<<grid, 256, 0, c.stream>>>(ptr, idx, u.vt.get(), Cn, nc, R, o0, ldo);
+                transpose_cols_kernel<32><<<(unsigned)((Cn + 256) / 256), 256, 0, st>>>(v0, ldv, nc, Cn, u.vt.get());
+                sparse_rows_gather_kernel<32><<<grid, 256, 0, st>>>(ptr, idx, u.vt.get(), Cn, nc, R, o0, ldo);
             } else if (W == 16) {
-                transpose_cols_kernel<16><<<(unsigned)((Cn + 256) / 256), 256, 0, c.stream>>>(v0, ldv, nc, Cn, u.vt.get());
-                sparse_rows_gather_kernel<16><<<grid, 256, 0, c.stream>>>(ptr, idx, u.vt.get(), Cn, nc, R, o0, ldo);
+                transpose_cols_kernel<16><<<(unsigned)((Cn + 256) / 256), 256, 0, st>>>(v0, ldv, nc, Cn, u.vt.get());
+                sparse_rows_gather_kernel<16><<<grid, 256, 0, st>>>(ptr, idx, u.vt.get(), Cn, nc, R, o0, ldo);
             } else {
-                transpose_cols_kernel<8><<<(unsigned)((Cn + 256) / 256), 256, 0, c.stream>>>(v0, ldv, nc, Cn, u.vt.get());
-                sparse_rows_gather_kernel<8><<<grid, 256, 0, c.stream>>>(ptr, idx, u.vt.get(), Cn, nc, R, o0, ldo);
+                transpose_cols_kernel<8><<<(unsigned)((Cn + 256) / 256), 256, 0, st>>>(v0, ldv, nc, Cn, u.vt.get());
+                sparse_rows_gather_kernel<8><<<grid, 256, 0, st>>>(ptr, idx, u.vt.get(), Cn, nc, R, o0, ldo);
             }
             c.stats.n_kernel_launches += 2;
         }
@@ -1179,15 +1181,15 @@ void launch_sparse_multi(Context &c, ImmaPlan *p, bool by_variant, const double 
         const int nc = std::min(4, ncols - c0);
         c.prof_begin();
         if (nc > 2)
-            sparse_ell_multi_kernel<4><<<c.sm_count, kEmThreads, em_smem<4>(), c.stream>>>(gs, ell, vec + (size_t)c0 * ldv, ldv, nc, R, Cn, G, nt,
+            sparse_ell_multi_kernel<4><<<c.sm_count, kEmThreads, em_smem<4>(), st>>>(gs, ell, vec + (size_t)c0 * ldv, ldv, nc, R, Cn, G, nt,
                                                                                            u.part.get());
         else
-            sparse_ell_multi_kernel<2><<<c.sm_count, kEmThreads, em_smem<2>(), c.stream>>>(gs, ell, vec + (size_t)c0 * ldv, ldv, nc, R, Cn, G, nt,
+            sparse_ell_multi_kernel<2><<<c.sm_count, kEmThreads, em_smem<2>(), st>>>(gs, ell, vec + (size_t)c0 * ldv, ldv, nc, R, Cn, G, nt,
                                                                                            u.part.get());
         SGB_CHECK_LAUNCH();
         c.prof_end(by_variant ? "sparse_ell_multi_kernel (U)" : "sparse_ell_multi_kernel (corr)");
         c.prof_begin();
-        sum_tiles_multi_kernel<<<dim3((unsigned)((R + 255) / 256), nc), 256, 0, c.stream>>>(u.part.get(), nt, R, out + (size_t)c0 * ldo, ldo);
+        sum_tiles_multi_kernel<<<dim3((unsigned)((R + 255) / 256), nc), 256, 0, st>>>(u.part.get(), nt, R, out + (size_t)c0 * ldo, ldo);
         SGB_CHECK_LAUNCH();
         c.prof_end("sum_tiles_multi_kernel");
         c.stats.n_kernel_launches += 2;
@@ -1213,6 +1215,18 @@ void umma_grm_mv_pass(Context &c, ImmaPlan *p, const double *b, double *out, int
     ImmaPlan::Umma &u = p->um;
     const int64_t M = c.M, N = c.N;
     const int ng = ((kUND * ncols + 15) / 16) * 16;
+    // The sparse corrections can run on the side stream beside the tensor-core GEMMs (env SGB_UMMA_FORK=1): U beside phase A, corr
+    // beside phase B.  Measured on the B200: no gain (19.6 vs 19.2 ms at K = 30) -- next to a GEMM CTA (640 threads, 46 K registers)
+    // only one 8-warp gather block fits per SM, and the gather lives on having ~64 warps x 16 loads in flight -- so the default is
+    // serial on the main stream.
+    cudaStream_t side = (c.profiling || !p->um_fork) ? c.stream : p->side;
+    const bool fork = side != c.stream;
+    if (fork) {
+        SGB_CUDA(cudaEventRecord(p->ev_in, c.stream));
+        SGB_CUDA(cudaStreamWaitEvent(side, p->ev_in, 0));
+    }
+    launch_sparse_multi(c, p, true, b, N, ncols, u.u.get(), M, side);
+    if (fork) SGB_CUDA(cudaEventRecord(p->ev_u, side));
     c.prof_begin();
     umma_colstats_kernel<<<ncols, 1024, 0, c.stream>>>(b, N, u.scal.get());
     SGB_CHECK_LAUNCH();
@@ -1223,7 +1237,6 @@ void umma_grm_mv_pass(Context &c, ImmaPlan *p, const double *b, double *out, int
     SGB_CUDA(cudaMemsetAsync(u.r_lo.get(), 0, sizeof(unsigned long long) * (size_t)ncols * N, c.stream));
     SGB_CUDA(cudaMemsetAsync(u.r_hi.get(), 0, sizeof(unsigned long long) * (size_t)ncols * N, c.stream));
     c.prof_end("umma_prep_b (colstats+digits+memsets)");
-    launch_sparse_multi(c, p, true, b, N, ncols, u.u.get(), M);
     UmmaArgs a;
     a.ncols = ncols; a.ng = ng; a.err = u.err.get();
     // phase A: rows = variants, contraction over samples
@@ -1251,21 +1264,27 @@ void umma_grm_mv_pass(Context &c, ImmaPlan *p, const double *b, double *out, int
         double s[16] = {0};
         for (size_t i = 0; i < ncta; i++) for (int k = 0; k < 16; k++) s[k] += (double)h[i * 16 + k];
         const double ks = s[5] > 0 ? s[5] : 1;
-        c.printf("umma prof (clk per k-step, %zu CTAs): issuer total %.0f = wait_b %.0f + wait_a %.0f + mma %.0f + commit %.0f | expander total %.0f = "
-                 "wait_p %.0f + load/expand %.0f + wait_empty %.0f + st/wait::st %.0f + arrive %.0f\n", ncta, s[0] / ks, s[1] / ks, s[2] / ks, s[3] / ks,
-                 s[4] / ks, s[8] / ks, s[9] / ks, s[10] / ks, s[11] / ks, s[12] / ks, s[13] / ks);
+        c.printf("umma prof (clk per stage, %zu CTAs): issuer total %.0f = wait_a %.0f + mma %.0f + commit %.0f | expander (per own stage) total %.0f = "
+                 "wait_p %.0f + load/expand %.0f + wait_empty %.0f + st/wait::st %.0f + wait_b/arrive %.0f\n", ncta, s[0] / ks, s[2] / ks, s[3] / ks,
+                 s[4] / ks, 2 * s[8] / ks, 2 * s[9] / ks, 2 * s[10] / ks, 2 * s[11] / ks, 2 * s[12] / ks, 2 * s[13] / ks);
     }
     SGB_CHECK_LAUNCH();
     c.prof_end("umma_gemm_kernel (phase A)");
+    if (fork) SGB_CUDA(cudaStreamWaitEvent(c.stream, p->ev_u, 0));
     c.prof_begin();
     const int Gm = (int)std::min<int64_t>(1024, std::max<int64_t>(1, (M + 255) / 256));
     umma_finalize_kernel<<<dim3(Gm, ncols), 256, 0, c.stream>>>(u.t_lo.get(), u.t_hi.get(), u.u.get(), 1, c.lut.get(), M, 1.0 / (double)c.M_total,
                                                                 u.e.get(), u.hm.get(), u.red.get(), u.counter.get(), u.scal.get());
     SGB_CHECK_LAUNCH();
+    if (fork) {
+        SGB_CUDA(cudaEventRecord(p->ev_hm, c.stream));
+        SGB_CUDA(cudaStreamWaitEvent(side, p->ev_hm, 0));
+    }
     umma_digits_kernel<<<dim3((unsigned)((u.cpad_b + 255) / 256), ncols), 256, 0, c.stream>>>(u.e.get(), M, M, u.cpad_b, u.scal.get(), 1, u.de.get());
     SGB_CHECK_LAUNCH();
     c.prof_end("umma_finalize+digits_e");
-    launch_sparse_multi(c, p, false, u.hm.get(), M, ncols, u.corr.get(), N);
+    launch_sparse_multi(c, p, false, u.hm.get(), M, ncols, u.corr.get(), N, side);
+    if (fork) SGB_CUDA(cudaEventRecord(p->ev_corr, side));
     // phase B: rows = samples, contraction over variants (sample-major copy)
     a.R = N; a.boxes_total = u.boxes_b; a.boxes_per_split = (u.boxes_b + u.split_b - 1) / u.split_b;
     a.out_lo = u.r_lo.get(); a.out_hi = u.r_hi.get(); a.ldo = N;
@@ -1274,6 +1293,7 @@ void umma_grm_mv_pass(Context &c, ImmaPlan *p, const double *b, double *out, int
     umma_gemm_kernel<false><<<dim3((unsigned)((N + kURows - 1) / kURows), ns_b), kUThreads, kUSmemBytes, c.stream>>>(u.tmap_pt, *umma_digit_map(u, true, ng), a);
     SGB_CHECK_LAUNCH();
     c.prof_end("umma_gemm_kernel (phase B)");
+    if (fork) SGB_CUDA(cudaStreamWaitEvent(c.stream, p->ev_corr, 0));
     c.prof_begin();
     umma_combine_kernel<<<dim3((unsigned)((N + 255) / 256), ncols), 256, 0, c.stream>>>(u.r_lo.get(), u.r_hi.get(), N, u.corr.get(), 1, u.scal.get(), out);
     SGB_CHECK_LAUNCH();
@@ -1467,6 +1487,7 @@ void imma_prepare(Context &c) {
             SGB_CUDA(cudaMemcpyToSymbolAsync(g_wait_timeout_ns, &ns, sizeof(ns), 0, cudaMemcpyHostToDevice, c.stream));
         }
         if (const char *e = getenv("SGB_UMMA_MIN_COLS")) { p->um_min_cols = atoi(e); if (p->um_min_cols <= 0) p->um_min_cols = INT_MAX; }
+        if (const char *e = getenv("SGB_UMMA_FORK")) p->um_fork = atoi(e);
         if (const char *e = getenv("SGB_UMMA_GATHER_COLS")) p->um_gather_cols = atoi(e);
         if (const char *e = getenv("SGB_UMMA_GATHER_W")) { const int w = atoi(e); if (w == 8 || w == 16 || w == 32) p->um_gather_w = w; }
         if (const char *e = getenv("SGB_SPARSE_FORK")) p->opt_fork = atoi(e);
