@@ -276,10 +276,10 @@ def run_gpu(args):
         ctx.grm_mv_device(d_b, d_out, 1)
     if world == 1:
         t_wait = time.perf_counter()
-        while len(sampler.lines) < 2 and time.perf_counter() - t_wait < 3.0:
+        while len(sampler.lines) < 6 and time.perf_counter() - t_wait < 3.0:
             ctx.grm_mv_device(d_b, d_out, 1)
     else:
-        for _ in range(150):                 # every rank must issue the same number of products (each ends in a collective)
+        for _ in range(600):                 # every rank must issue the same number of products (each ends in a collective)
             ctx.grm_mv_device(d_b, d_out, 1)
     # (the samples of the warm-up stay in: the timed region of 20 products lasts ~70 ms, one nvidia-smi period; the warm-up
     #  runs the same product back to back, so the clocks line describes the same load)

@@ -141,8 +141,8 @@ __device__ __forceinline__ void ldsm_t8(uint32_t (&r)[4], unsigned addr) {
 }
 
 struct FusedArgs {
-    const uint8_t *packed; size_t pitch; int64_t M, N, ksteps;
-    int ks_per_cta;                     // K-steps per CTA (<= kFMaxKs)
+    const uint8_t *packed; size_t pitch; int64_t M, N, hsteps;        // hsteps = half-steps of 128 samples = 2 ceil(N / 256)
+    int hs_per_cta;                     // half-steps per CTA slice (<= 2 kFMaxKs); slicing by half-steps puts 147 of 148 SMs to work at N = 430K
     int lag;                            // phase B runs `lag` tiles behind phase A (1 .. kFNBuf - 2)
     int poll_ns;                        // back-off between two polls of a tile's limbs
     int64_t n_tiles;
@@ -169,8 +169,8 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
     FusedSmem &S = *reinterpret_cast<FusedSmem *>(smem_raw + kFNBuf * kFTileBytes);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
     const int n_cta = gridDim.x;
-    const int64_t ks0 = (int64_t)blockIdx.x * A.ks_per_cta;
-    const int ks_n = (int)min((int64_t)A.ks_per_cta, A.ksteps - ks0);        // >= 1 by construction of the grid
+    const int64_t hs0 = (int64_t)blockIdx.x * A.hs_per_cta;
+    const int hs_n = (int)min((int64_t)A.hs_per_cta, A.hsteps - hs0);        // >= 1 by construction of the grid
     const int64_t T = A.n_tiles;
     const int lag = A.lag;
     volatile int *err = A.err;
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
             if (lane == 0) mbar_expect_tx(&S.full[b], kFTileBytes);     // out-of-bounds rows / columns are zero-filled and counted
             __syncwarp();
             if (lane < kFPanels)
-                tma_load_2d(tiles + (size_t)b * kFTileBytes + lane * kFPanelBytes, &tmap, (int)(ks0 * 64) + lane * 128, (int)(t * kFV),
+                tma_load_2d(tiles + (size_t)b * kFTileBytes + lane * kFPanelBytes, &tmap, (int)(hs0 * 32) + lane * 128, (int)(t * kFV),
                             &S.full[b], policy);
         }
       } else if (warp == kFComputeWarps + 1) {
@@ -344,8 +344,8 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
 #pragma unroll
         for (int i = 0; i < kFHpw; i++) {
             const int hs = warp + i * kFComputeWarps;                 // half-step inside the slice
-            const bool on = hs < 2 * ks_n;
-            const uint4 *src = reinterpret_cast<const uint4 *>(A.dfrag128 + ((size_t)(ks0 * 2 + hs)) * 1024 + lane * 32);
+            const bool on = hs < hs_n;
+            const uint4 *src = reinterpret_cast<const uint4 *>(A.dfrag128 + ((size_t)(hs0 + hs)) * 1024 + lane * 32);
             uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
             if (on) { v0 = src[0]; v1 = src[1]; }
             bfr[i][0] = v0.x; bfr[i][1] = v0.y; bfr[i][2] = v0.z; bfr[i][3] = v0.w;
@@ -392,8 +392,8 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
                         double v = w0 * (double)s0 + w1 * (double)s1;
                         v += __shfl_xor_sync(0xffffffffu, v, 1);
                         v += __shfl_xor_sync(0xffffffffu, v, 2);
-                        const int64_t n = (ks0 * 64 + (warp * kFRbw + r) * 16 + g + hh * 8) * 4 + t;
-                        if (tq == 0 && n < A.N && (warp * kFRbw + r) < 4 * ks_n) {
+                        const int64_t n = (hs0 * 32 + (warp * kFRbw + r) * 16 + g + hh * 8) * 4 + t;
+                        if (tq == 0 && n < A.N && (warp * kFRbw + r) < 2 * hs_n) {
                             double *dst = A.rout + n;
                             *dst = first_flush ? v : (*dst + v);
                         }

@@ -75,7 +75,7 @@ struct ImmaPlan {
     int opt_fork = 1, opt_fork_fused = -1, opt_grid_mult = 2, opt_stages = 3;   // tuning knobs (env: SGB_SPARSE_FORK, SGB_SPARSE_GRID_MULT, SGB_DOTS_STAGES)
     // fused single-pass kernel (grm_fused.cuh)
     bool fused_ok = false;
-    int f_ks_per_cta = 0, f_grid = 0;
+    int f_ks_per_cta = 0, f_grid = 0;   // half-steps (128 samples) per CTA slice, number of CTAs
     int64_t f_tiles = 0;
     DevBuf<int8_t> dfrag128;
     DevBuf<unsigned long long> f_acc;
@@ -1419,16 +1419,17 @@ void imma_prepare(Context &c) {
         if (4 * kAStageBytes <= 227 * 1024)
             SGB_CUDA(cudaFuncSetAttribute(imma_dots_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kAStageBytes));
         {
-            const int ks_per = (int)((p->ksteps + c.sm_count - 1) / c.sm_count);
+            const int64_t hsteps = 2 * p->ksteps;
+            const int ks_per = (int)((hsteps + c.sm_count - 1) / c.sm_count);      // half-steps (128 samples) per CTA slice
             int coop = 0;
             SGB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.dev));
             const char *fe = getenv("SGB_FUSED");
-            if (coop && ks_per >= 1 && ks_per <= kFMaxKs && !(fe && atoi(fe) == 0)) {
+            if (coop && ks_per >= 1 && ks_per <= 2 * kFMaxKs && !(fe && atoi(fe) == 0)) {
                 SGB_CUDA(cudaFuncSetAttribute(imma_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmemBytes));
                 int per_sm = 0;
                 SGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, imma_fused_kernel, kFThreads, kFSmemBytes));
                 p->f_ks_per_cta = ks_per;
-                p->f_grid = (int)((p->ksteps + ks_per - 1) / ks_per);
+                p->f_grid = (int)((hsteps + ks_per - 1) / ks_per);
                 p->f_tiles = (M + kFV - 1) / kFV;
                 if (per_sm >= 1 && p->f_grid <= per_sm * c.sm_count) {
                     p->dfrag128.ensure((size_t)p->ksteps * 2048);
@@ -1515,7 +1516,7 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
     // The fused kernel pays ~1 us of cross-CTA latency per 32-variant tile whatever the slice width, so it only beats the two
     // HBM passes when every CTA's slice is (nearly) full: SGB_KERNEL_AUTO takes it from 10 of the 12 K-steps per CTA upwards
     // (N >= ~380K on 148 SMs) and the two-pass kernels otherwise; SGB_KERNEL_IMMA forces it whenever the shape allows.
-    const bool use_fused = p->fused_ok && !c.fused_disabled && (c.kernel == SGB_KERNEL_IMMA || (c.kernel == SGB_KERNEL_AUTO && p->f_ks_per_cta >= 10));
+    const bool use_fused = p->fused_ok && !c.fused_disabled && (c.kernel == SGB_KERNEL_IMMA || (c.kernel == SGB_KERNEL_AUTO && p->f_ks_per_cta >= 20));
     // several right-hand sides: one pass over the packed matrix for all of them on tcgen05 (grm_umma.cuh)
     if ((c.kernel == SGB_KERNEL_UMMA || (c.kernel == SGB_KERNEL_AUTO && k >= p->um_min_cols)) && !p->um.failed && !c.fused_disabled) {
         umma_prepare(c, p);
@@ -1569,8 +1570,8 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
             c.prof_end("sum_tiles_kernel");
             if (fork) SGB_CUDA(cudaStreamWaitEvent(c.stream, p->ev_u, 0));
             FusedArgs fa;
-            fa.packed = c.packed.get(); fa.pitch = c.pitch; fa.M = M; fa.N = N; fa.ksteps = p->ksteps;
-            fa.ks_per_cta = p->f_ks_per_cta; fa.n_tiles = p->f_tiles; fa.dfrag128 = p->dfrag128.get();
+            fa.packed = c.packed.get(); fa.pitch = c.pitch; fa.M = M; fa.N = N; fa.hsteps = 2 * p->ksteps;
+            fa.hs_per_cta = p->f_ks_per_cta; fa.n_tiles = p->f_tiles; fa.dfrag128 = p->dfrag128.get();
             fa.acc_t = p->f_acc.get(); fa.acc_stride = p->f_acc_stride; fa.u = p->f_u.get(); fa.poll_ns = p->f_poll_ns; fa.lag = p->f_lag;
             fa.lut = c.lut.get(); fa.inv_mtotal = 1.0 / (double)c.M_total; fa.scal = p->scal.get(); fa.hm = p->hm.get();
             fa.h_part = p->f_hpart.get(); fa.edig = p->f_edig.get(); fa.rout = p->f_rout.get(); fa.err = p->f_err.get();
