@@ -445,7 +445,11 @@ def seqFitNullGLMM_SPA(formula: str, data: dict, packed_geno: np.ndarray, trait_
     `packed_geno` replaces the GDS file + the genotype loading at R/saige_main.r:388-421: either a uint8 array
     [n_variant][ceil(n_samp/4)] in the 2-bit format (geno.sparse=FALSE, SeqArray:::.seqGet2bGeno) or a list of
     `saige_get_sparse` vectors (geno.sparse=TRUE, the reference's default).  Sample/variant filtering, which the
-    reference does through SeqArray (:305-333), is the caller's job.
+    reference does through SeqArray (:305-333), is the caller's job (or `saigegds_b200.store_from_gds`).
+    Linearly dependent covariate columns are dropped before the QR transform like the reference does (:362-376); the returned
+    coefficients then belong to the kept columns.  The random marker order of the variance-ratio step mirrors R's
+    `set.seed(seed, sample.kind = "Rounding")`, the setting the reference's golden fixtures were produced with -- under R >= 3.6's
+    default sample.kind ("Rejection") an R session draws a different marker order.
     """
     if trait_type not in ("binary", "quantitative"):
         raise ValueError("Invalid 'trait.type'.")
@@ -458,6 +462,13 @@ def seqFitNullGLMM_SPA(formula: str, data: dict, packed_geno: np.ndarray, trait_
         X_transform = False
     X_qrr = None
     if X_transform:
+        keep = rsetup.independent_columns(X)                               # :362-376: covariates with NA coefficients are dropped
+        if len(keep) < X.shape[1]:
+            if verbose:                                                     # same text as :369-373
+                names = (["(Intercept)"] if intercept else []) + list(terms)
+                drop = [names[j] for j in range(X.shape[1]) if j not in set(keep.tolist())]
+                print("    exclude %d covariates (%s) to avoid multi collinearity." % (len(drop), ", ".join(drop)))
+            X = X[:, keep]
         X, X_qrr = rsetup.qr_transform(X)                                   # :378-380
     if isinstance(packed_geno, np.ndarray) and packed_geno.ndim == 2:
         ctx.saige_store_2b_geno(packed_geno, n)                             # :437

@@ -152,9 +152,11 @@ int sgb_store_2b_geno_device(sgb_context *ctx, uint8_t *packed_device, int take_
                              int64_t variant_offset, double *buf_std_geno, double *buf_diag_grm) {
     return guarded(ctx, [&] {
         if (!packed_device) throw sgb::Error(SGB_ERR_INVALID, "packed_device is NULL");
+        // with take_ownership the buffer is released on every path, also when the shard description is rejected or the store fails
+        struct Guard { uint8_t *p; ~Guard() { if (p) cudaFree(p); } } guard{take_ownership ? packed_device : nullptr};
         store_common(*ctx, n_samp, n_bytes_per_variant, n_variant_local, n_variant_total, variant_offset);
         sgb::store_device_layout(*ctx, packed_device, (size_t)n_bytes_per_variant);
-        if (take_ownership) SGB_CUDA(cudaFree(packed_device));
+        if (take_ownership) { guard.p = nullptr; SGB_CUDA(cudaFree(packed_device)); }
         store_outputs(*ctx, buf_std_geno, buf_diag_grm);
     });
 }
@@ -331,6 +333,7 @@ int sgb_grm_mv(sgb_context *ctx, const double *b, double *out, int k) {
 
 int sgb_diag_sigma(sgb_context *ctx, const double *w, const double tau[2], double *out) {
     return guarded(ctx, [&] {
+        if (!w || !tau || !out) throw sgb::Error(SGB_ERR_INVALID, "w, tau or out is NULL");
         ctx->require_stored();
         sgb::DevBuf<double> dw, dout;
         dw.ensure(ctx->N); dout.ensure(ctx->N);
@@ -405,14 +408,23 @@ int sgb_r_set_seed(sgb_context *ctx, uint32_t seed) {
     return guarded(ctx, [&] { ctx->rng.set_seed(seed); });
 }
 int sgb_r_unif_rand(sgb_context *ctx, int64_t n, double *out) {
-    return guarded(ctx, [&] { for (int64_t i = 0; i < n; i++) out[i] = ctx->rng.unif_rand(); });
+    return guarded(ctx, [&] {
+        if (!out || n < 0) throw sgb::Error(SGB_ERR_INVALID, "out is NULL or n < 0");
+        for (int64_t i = 0; i < n; i++) out[i] = ctx->rng.unif_rand();
+    });
 }
 int sgb_r_sample_int(sgb_context *ctx, int32_t n, int32_t *out) {
-    return guarded(ctx, [&] { ctx->rng.sample_int(n, out); });
+    return guarded(ctx, [&] {
+        if (!out || n < 0) throw sgb::Error(SGB_ERR_INVALID, "out is NULL or n < 0");
+        ctx->rng.sample_int(n, out);
+    });
 }
 
 int sgb_get_stats(sgb_context *ctx, sgb_stats *out) {
-    return guarded(ctx, [&] { *out = ctx->stats; });
+    return guarded(ctx, [&] {
+        if (!out) throw sgb::Error(SGB_ERR_INVALID, "out is NULL");
+        *out = ctx->stats;
+    });
 }
 int sgb_reset_stats(sgb_context *ctx) {
     return guarded(ctx, [&] { ctx->stats = sgb_stats{}; });

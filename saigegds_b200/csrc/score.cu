@@ -499,7 +499,9 @@ void score_init(Context &c, const sgb_score_model *m, double maf, double mac, do
     const char *env_path = getenv("SGB_SCORE_PATH");
     s->path = (env_path && std::string(env_path) == "per_variant") ? SGB_SCORE_PER_VARIANT : SGB_SCORE_TILED;
     s->grid = c.sm_count * 4;
-    s->spa.ensure((size_t)s->grid * 2 * n);
+    // saddle-point scratch (2 n doubles per block of the candidate kernel): binary traits only -- a quantitative trait never
+    // takes the saddle-point branch (saige_main.cpp:322-350)
+    if (m->trait == 0) s->spa.ensure((size_t)s->grid * 2 * n);
     s->counter.ensure(1);
     score::Model &M = s->M;
     M.trait = m->trait; M.n = m->n; M.K = m->K; M.tau0 = m->tau[0];

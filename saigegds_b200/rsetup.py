@@ -122,6 +122,24 @@ def glm_gaussian(X: np.ndarray, y: np.ndarray) -> Fit0:
                 X=X, residuals=y - eta)
 
 
+def independent_columns(X: np.ndarray, tol: float = 1e-7) -> np.ndarray:
+    """Indices of the design-matrix columns R's `lm(y ~ X - 1)` would keep: a column that is linearly dependent on the columns
+    before it gets an NA coefficient (pivoted Householder QR of `lm.fit`, tolerance 1e-7) and is dropped before the QR
+    transform (R/saige_main.r:362-376: `X <- X[, !is.na(fit$coefficients)]`)."""
+    X = np.asarray(X, dtype=np.float64)
+    keep, basis = [], []
+    for j in range(X.shape[1]):
+        v = X[:, j].copy()
+        nrm0 = np.linalg.norm(v)
+        for q in basis:                      # modified Gram-Schmidt against the kept columns
+            v -= (q @ v) * q
+        nrm = np.linalg.norm(v)
+        if nrm0 > 0 and nrm > tol * nrm0:
+            keep.append(j)
+            basis.append(v / nrm)
+    return np.asarray(keep, dtype=np.int64)
+
+
 def qr_transform(X: np.ndarray):
     """R/saige_main.r:378-380: X_new = qr.Q(qr(X)) * sqrt(n), X_qrr = qr.R(qr(X))."""
     Q, R = np.linalg.qr(X)

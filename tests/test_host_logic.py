@@ -153,3 +153,13 @@ def test_oracle_synthetic_generator_is_shard_invariant_and_calibrated():
     c = np.stack([(big >> s) & 3 for s in (0, 2, 4, 6)], axis=2).reshape(200, -1)[:, :20000]
     af = np.where(c == 3, 0, c).sum(1) / (2.0 * (c != 3).sum(1))
     assert 0.004 < af.min() < 0.05 and 0.4 < af.max() < 0.51
+
+
+def test_collinear_covariates_are_dropped_like_lm_does():
+    """R/saige_main.r:362-376: columns with NA coefficients in lm(y ~ X - 1) (dependent on earlier columns) are excluded."""
+    from saigegds_b200 import rsetup
+    rng = np.random.default_rng(0)
+    X = np.column_stack([np.ones(50), rng.standard_normal(50), rng.standard_normal(50)])
+    X = np.column_stack([X, 2 * X[:, 1] - X[:, 0], rng.standard_normal(50), np.zeros(50), X[:, 2] * (1 + 1e-12)])
+    assert rsetup.independent_columns(X).tolist() == [0, 1, 2, 4]
+    assert rsetup.independent_columns(X[:, :3]).tolist() == [0, 1, 2]
