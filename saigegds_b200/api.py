@@ -108,6 +108,15 @@ class Context:
             pass
 
     # ---- configuration ----
+    def set_print(self, fn):
+        """Route the library's verbose output (Rprintf in the reference) to `fn(str)`; None restores stdout."""
+        if fn is None:
+            self._print_cb = None
+            L.check(L.lib().sgb_set_callbacks(self._h, None, None, None))
+            return
+        self._print_cb = C.CFUNCTYPE(None, C.c_char_p)(lambda s: fn(s.decode("utf-8", "replace")))
+        L.check(L.lib().sgb_set_callbacks(self._h, self._print_cb, None, None))
+
     def set_kernel(self, name: str):
         L.check(L.lib().sgb_set_kernel(self._h, C.c_int(L.KERNEL[name])))
 

@@ -378,3 +378,25 @@ def test_multi_gpu_sharding_matches_single_gpu():
            "--master-port", "29517", os.path.join(root, "tests", "multi_gpu_check.py")]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
     assert r.returncode == 0, r.stdout.decode()[-3000:]
+
+
+def test_verbose_log_has_the_reference_format(gpu, fx, setup_binary):
+    """verbose=TRUE output: the text Rprintf produces in saige_fit_AI_PCG_binary (saige_fitnull.cpp:1027-1032,
+    print_vec :934-945, "%0.7g") with the tau trajectory of the reference's fit of its own fixture."""
+    import saigegds_b200 as sg
+    gpu.saige_store_2b_geno(fx.packed, fx.n_samp)
+    lines = []
+    gpu.set_print(lines.append)
+    try:
+        gpu.saige_fit_AI_PCG_binary(setup_binary["fit0"], setup_binary["X"], setup_binary["tau"], sg.make_param(verbose=True))
+    finally:
+        gpu.set_print(None)
+    text = "".join(lines)
+    want_tau = ["0.4994116", "0.3287896", "0.2817812", "0.3211452", "0.3361534"]
+    for it, tv in enumerate(want_tau, start=1):
+        assert ("Iteration %d:\n    tau: (1, %s)\n    fixed coeff: (" % (it, tv)) in text, (it, text[:2000])
+    assert "Final tau: (1, 0.3322063)\n    fixed coeff: (" in text
+    import re
+    assert re.search(r"Initial variance component estimates, tau:\n    Sigma_E: 1, Sigma_G: 0\.5\n", text)
+    coef = re.findall(r"fixed coeff: \(([^)]*)\)", text)
+    assert all(len(c.split(", ")) == 3 for c in coef)
