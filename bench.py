@@ -335,7 +335,7 @@ def run_gpu(args):
         reps = 5
         msb = max_over_ranks(ctx.time_products_device(d_B, d_O, kb, reps)) / reps
         barrier()
-        col0 = ctx.get_crossprod_b_grm(Bh[:, :2])[:, 0]            # k = 2: batched path, through the host entry point
+        col0 = ctx.get_crossprod_b_grm(Bh[:, :3])[:, 0]            # k = 3: batched path, through the host entry point
         batched = {"k": kb, "ms_per_call": msb, "products_per_s": kb * 1e3 / msb,
                    "col0_vs_single_rhs_relinf": float(np.max(np.abs(col0 - out_host)) / np.max(np.abs(out_host))),
                    "note": "tcgen05.mma kind::i8, accumulators in TMEM; one pass over both orientations of the packed matrix "

@@ -69,7 +69,8 @@ struct ImmaPlan {
     int um_fork = 0;         // batched path: sparse corrections on the side stream beside the GEMMs (env SGB_UMMA_FORK)
     int um_gather_w = 16;    // columns per pass of the row-gather kernel: 8, 16 or 32 (env SGB_UMMA_GATHER_W)
     int um_gather_cols = 8;  // batched path: more columns than this take the row-gather sparse kernel (env SGB_UMMA_GATHER_COLS)
-    int um_min_cols = 2;     // AUTO: batched tcgen05 path from this many columns (env SGB_UMMA_MIN_COLS; 0 disables)
+    int um_min_cols = 3;     // AUTO: batched tcgen05 path from this many columns (two columns: 8.3 ms against 2 x 3.4 ms for the fused
+                             // single-RHS kernel at N = 430K; env SGB_UMMA_MIN_COLS; 0 disables)
     bool use_csr = false;    // env SGB_SPARSE_CSR: the older row-per-thread kernel (comparison only)
     int n_stiles = 0, n_vtiles = 0;
     int opt_fork = 1, opt_fork_fused = -1, opt_grid_mult = 2, opt_stages = 3;   // tuning knobs (env: SGB_SPARSE_FORK, SGB_SPARSE_GRID_MULT, SGB_DOTS_STAGES)
