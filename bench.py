@@ -537,8 +537,7 @@ def cpu_fit_times(n, m, traits, cores):
             tau0 = rsetup.initial_tau_quant(fit0)
         t0 = time.perf_counter()
         r = o.fit_AI_PCG(trait if trait == "binary" else "quantitative", fit0, X, tau0)
-        out[trait] = {"fit_s": time.perf_counter() - t0, "tau": [float(x) for x in r["tau"]], "products": int(o.num_products())
-                      if hasattr(o, "num_products") else None}
+        out[trait] = {"fit_s": time.perf_counter() - t0, "tau": [float(x) for x in r["tau"]], "products": int(o.num_products)}
     return out
 
 
