@@ -43,21 +43,23 @@ constexpr int kURows = 256;             // rows per CTA: two M = 128 tiles
 constexpr int kUBoxBytes = 128;         // packed bytes per row and TMA box = 512 contraction elements
 constexpr int kUBoxElems = kUBoxBytes * 4;
 constexpr int kUStage = 128;            // contraction elements per digit tile (128 B per MMA column = 4 k-steps of 32)
-constexpr int kUNP = 2;                 // packed-box ring
+constexpr int kUNP = 3;                 // packed-box ring (its loads are issued by their own lane, up to three boxes = 12 stages ahead)
 constexpr int kUNB = 4;                 // digit-tile ring (= number of mma_done barriers per M-tile)
 constexpr int kUPackBytes = kURows * kUBoxBytes;    // 32 KB
-constexpr int kUWarps = 20;             // 0: TMA producer, 1 / 2: MMA issuers of M-tile 0 / 1, 3: TMEM allocator, 4..19: expanders
+constexpr int kUWarps = 20;             // 0: TMA producer (packed boxes), 1 / 2: MMA issuers of M-tile 0 / 1, 3: TMEM allocator + TMA producer (digit tiles), 4..19: expanders
 constexpr int kUThreads = kUWarps * 32;
 constexpr int kUExpWarps = 16;          // two sets of 8 (256 rows); set s serves the stages with st % 2 == s and owns A slot s
-constexpr unsigned kUAccCols = 192;     // accumulator of M-tile mt: tensor-memory columns [192 mt, 192 mt + 6K)
-constexpr unsigned kUStageCol = 384;    // A-operand slots: column 384 + 64 mt + 32 slot (32 columns = one stage of 128 elements per row)
+// Tensor memory (512 columns).  Up to 32 right-hand sides (N <= 192): accumulators at 192 mt, two A-operand slots of 32 columns per M-tile at
+// 384 + 64 mt + 32 slot.  Up to 21 right-hand sides (N <= 128): accumulators at 128 mt, FOUR A slots per M-tile at 256 + 128 mt + 32 slot --
+// the hand-over loop issuer <-> expanders is ~1,600 clk long, and with few columns a stage's MMAs are far shorter than that.
+__host__ __device__ inline int umma_ns(int ng) { return ng <= 128 ? 4 : 2; }
 // Measured on the B200 (SGB_UMMA_PROF, tools/umma_prof.py): for the single issuing thread an mbarrier try_wait costs ~190 clk, a
 // tcgen05.mma ~65 clk and a tcgen05.commit ~130 clk of issue latency.  Hence one wait, four MMAs and one commit per stage and
 // issuer (~580 clk) against the 768 clk the eight MMAs of a stage keep the tensor pipe busy at K = 32 columns; one issuer per
 // M-tile; the digit-tile dependency is checked by the expanders before they hand the A slot over.
 
 struct UmmaSmem {
-    unsigned long long p_full[kUNP], p_empty[kUNP], b_full[kUNB], a_full[2][2], mma_done[2][kUNB], acc_full[2];
+    unsigned long long p_full[kUNP], p_empty[kUNP], b_full[kUNB], a_full[2][4], mma_done[2][kUNB], acc_full[2];
     unsigned long long deadline;        // %globaltimer value after which every wait of this CTA gives up
     unsigned tmem_base;
 };
@@ -129,7 +131,8 @@ __global__ void __launch_bounds__(kUThreads, 1) umma_gemm_kernel(const __grid_co
         S.deadline = global_ns() + g_wait_timeout_ns;
         for (int i = 0; i < kUNP; i++) { mbar_init(&S.p_full[i], 1); mbar_init(&S.p_empty[i], kUExpWarps); }
         for (int i = 0; i < kUNB; i++) { mbar_init(&S.b_full[i], 1); mbar_init(&S.mma_done[0][i], 1); mbar_init(&S.mma_done[1][i], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&S.a_full[0][i], 4); mbar_init(&S.a_full[1][i], 4); mbar_init(&S.acc_full[i], 1); }
+        for (int i = 0; i < 4; i++) { mbar_init(&S.a_full[0][i], 4); mbar_init(&S.a_full[1][i], 4); }
+        for (int i = 0; i < 2; i++) mbar_init(&S.acc_full[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 3) {
@@ -140,30 +143,36 @@ __global__ void __launch_bounds__(kUThreads, 1) umma_gemm_kernel(const __grid_co
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tb = S.tmem_base;
+    const int ns = umma_ns(A.ng);                          // A slots per M-tile
+    const unsigned acc_stride = ns == 4 ? 128u : 192u, stage_col = ns == 4 ? 256u : 384u, stage_mt = (unsigned)ns * 32u;
 
     if (n_st > 0) {
     if (warp == 0) {
         // ------------------------------------------------------------------ producer
+        // packed boxes: they depend on the expanders only.  (Issued from one loop together with the digit tiles, the box of the next
+        // four stages would be requested just four stages ahead and arrive late; two lanes of ONE warp do not work either -- a lane
+        // spinning in try_wait starves the other, 6.2 instead of 4.2 ms per phase -- so the digit tiles have their own warp, 3.)
         if (lane == 0) {
             unsigned long long policy;
             asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-            bool ok = true;
-            for (int bx = 0; bx < n_box && ok; bx++) {
+            for (int bx = 0; bx < n_box; bx++) {
                 const int ps = bx % kUNP;
-                if (bx >= kUNP) ok = mbar_wait(&S.p_empty[ps], (unsigned)(((bx / kUNP) - 1) & 1), err, dl);
-                if (!ok) break;
+                if (bx >= kUNP && !mbar_wait(&S.p_empty[ps], (unsigned)(((bx / kUNP) - 1) & 1), err, dl)) break;
                 mbar_expect_tx(&S.p_full[ps], kUPackBytes);
                 tma_load_2d(pack + (size_t)ps * kUPackBytes, &tmap_p, (box0 + bx) * kUBoxBytes, row0, &S.p_full[ps], policy);
-                for (int s4 = 0; s4 < 4 && ok; s4++) {
-                    const int st = bx * 4 + s4, bs = st % kUNB;
-                    if (st >= kUNB) {     // the tile's previous user (stage st - 4) must be through both M-tiles
-                        const unsigned par = (unsigned)(((st / kUNB) - 1) & 1);
-                        ok = mbar_wait(&S.mma_done[0][bs], par, err, dl) && mbar_wait(&S.mma_done[1][bs], par, err, dl);
-                    }
-                    if (!ok) break;
-                    mbar_expect_tx(&S.b_full[bs], btile_bytes);
-                    tma_load_2d_nohint(btile + (size_t)bs * btile_bytes, &tmap_d, (box0 * 4 + st) * kUStage, 0, &S.b_full[bs]);
+            }
+        }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------------ digit tiles: they depend on the MMAs only
+        if (lane == 0) {
+            for (int st = 0; st < n_st; st++) {
+                const int bs = st % kUNB;
+                if (st >= kUNB) {     // the tile's previous user (stage st - 4) must be through both M-tiles
+                    const unsigned par = (unsigned)(((st / kUNB) - 1) & 1);
+                    if (!(mbar_wait(&S.mma_done[0][bs], par, err, dl) && mbar_wait(&S.mma_done[1][bs], par, err, dl))) break;
                 }
+                mbar_expect_tx(&S.b_full[bs], btile_bytes);
+                tma_load_2d_nohint(btile + (size_t)bs * btile_bytes, &tmap_d, (box0 * 4 + st) * kUStage, 0, &S.b_full[bs]);
             }
         }
     } else if (warp == 1 || warp == 2) {
@@ -172,14 +181,14 @@ __global__ void __launch_bounds__(kUThreads, 1) umma_gemm_kernel(const __grid_co
             const int mt = warp - 1;
             const unsigned idesc = umma_idesc_i8(128, A.ng);
             const unsigned bt0 = smem_u32(btile);
-            const unsigned acc = tb + mt * kUAccCols, a0 = tb + kUStageCol + mt * 64;
+            const unsigned acc = tb + mt * acc_stride, a0 = tb + stage_col + mt * stage_mt;
             bool ok = true;
             long long c_wa = 0, c_mma = 0, c_cm = 0, t0 = 0, t1 = 0;
             const long long t_begin = PROF ? clock64() : 0;
             for (int st = 0; st < n_st && ok; st++) {
-                const int bs = st % kUNB, as = st & 1;
+                const int bs = st % kUNB, as = st % ns;
                 if (PROF) t0 = clock64();
-                ok = mbar_wait(&S.a_full[mt][as], (unsigned)((st >> 1) & 1), err, dl);
+                ok = mbar_wait(&S.a_full[mt][as], (unsigned)((st / ns) & 1), err, dl);
                 if (!ok) break;
                 if (PROF) { t1 = clock64(); c_wa += t1 - t0; }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -223,11 +232,11 @@ __global__ void __launch_bounds__(kUThreads, 1) umma_gemm_kernel(const __grid_co
 #pragma unroll
                 for (int t = 0; t < 4; t++) x[4 * i + t] = (ws[i] >> (2 * t)) & 0x03030303u;
             if (PROF) { t0 = clock64(); c_ld += t0 - t1; }
-            // A slot `es` is free when the MMAs of stage st - 2 (this M-tile) are done
-            if (st >= 2) ok = mbar_wait(&S.mma_done[mt][(st - 2) % kUNB], (unsigned)(((st - 2) / kUNB) & 1), err, dl);
+            // A slot st % ns is free when the MMAs of stage st - ns (this M-tile) are done
+            if (st >= ns) ok = mbar_wait(&S.mma_done[mt][(st - ns) % kUNB], (unsigned)(((st - ns) / kUNB) & 1), err, dl);
             if (!ok) break;
             if (PROF) { t1 = clock64(); c_we += t1 - t0; }
-            tmem_st32(tb + lane_base + kUStageCol + mt * 64 + es * 32, x);
+            tmem_st32(tb + lane_base + stage_col + mt * stage_mt + (unsigned)(st % ns) * 32u, x);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             if (PROF) { t0 = clock64(); c_st += t0 - t1; }
@@ -236,7 +245,7 @@ __global__ void __launch_bounds__(kUThreads, 1) umma_gemm_kernel(const __grid_co
             if (!ok) break;
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive(&S.a_full[mt][es]);
+                mbar_arrive(&S.a_full[mt][st % ns]);
                 if ((st & 3) >= 2 || st + 2 >= n_st) mbar_arrive(&S.p_empty[ps]);       // this set's last stage in the box
             }
             if (PROF) { t1 = clock64(); c_ar += t1 - t0; }
@@ -253,7 +262,7 @@ __global__ void __launch_bounds__(kUThreads, 1) umma_gemm_kernel(const __grid_co
             for (int g = es; g * 8 < A.ncols; g += 2) {
                 int v[8 * kUND];
 #pragma unroll
-                for (int i = 0; i < kUND; i++) tmem_ld8_nowait(tb + lane_base + mt * kUAccCols + g * (8 * kUND) + i * 8, v + 8 * i);
+                for (int i = 0; i < kUND; i++) tmem_ld8_nowait(tb + lane_base + mt * acc_stride + g * (8 * kUND) + i * 8, v + 8 * i);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int cc = 0; cc < 8; cc++) {
