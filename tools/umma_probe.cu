@@ -239,11 +239,13 @@ static int run_layout(const char *name, int N, int ksteps, int a_layout, int b_l
     return bad == 0;
 }
 
+int pair_main();
 int main(int argc, char **argv) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
     printf("device: %s, %d SMs, clock %d kHz\n", prop.name, prop.multiProcessorCount, prop.clockRate);
     const bool rate_only = argc > 1 && !strcmp(argv[1], "rate");
+    if (argc > 1 && !strcmp(argv[1], "pair")) return pair_main();
     if (!rate_only) {
         for (int N : {16, 240}) {
             for (int swap = 0; swap < 2; swap++) {
@@ -290,5 +292,140 @@ int main(int argc, char **argv) {
                        mac * G / (ms * 1e-3) / 1e12, ms);
             }
         }
+    return 0;
+}
+
+// ---- cta_group::2: one tcgen05.mma drives the tensor cores of both SMs of a CTA pair (M = 256: 128 rows per CTA) ---------------------
+// Layout check (A from tensor memory, each CTA its own 128 rows; B split by rows, N / 2 per CTA, at the same shared-memory offset) and
+// MAC/clk/SM of back-to-back pair MMAs: is the ~124 clk per instruction a per-instruction dispatch cost that a pair MMA halves per SM?
+__device__ __forceinline__ void umma_i8_ts_2cta(unsigned d_tmem, unsigned a_tmem, uint64_t bdesc, unsigned idesc, unsigned accum) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, p;\n}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(unsigned long long *b) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(b)), "h"((unsigned short)3) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+struct Pair2Args { int N, ksteps, iters; const uint8_t *A; const int8_t *B; int *D; long long *cycles; };
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) probe_pair_kernel(Pair2Args P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ unsigned long long bar;
+    __shared__ unsigned tmem_base;
+    unsigned rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int K = 32 * P.ksteps, NH = P.N / 2;
+    // this CTA's half of B: rows [NH rank, NH rank + NH), SW128 K-major
+    for (int i = tid; i < NH * K; i += 128) {
+        const int r = i / K, k = i % K;
+        smem[elem_off(L_K_SW128, P.ksteps, r, k)] = P.B ? (uint8_t)P.B[(size_t)(NH * rank + r) * K + k] : (uint8_t)1;
+    }
+    if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tb = tmem_base;
+    // this CTA's 128 rows of A into its own tensor memory, columns 256.. (8 per k-step)
+    for (int s = 0; s < P.ksteps; s++) {
+        uint32_t r[8];
+        for (int q = 0; q < 8; q++) {
+            uint32_t v = 0x01010101u;
+            if (P.A) { v = 0; for (int by = 0; by < 4; by++) v |= (uint32_t)P.A[(size_t)(128 * rank + tid) * K + s * 32 + q * 4 + by] << (8 * by); }
+            r[q] = v;
+        }
+        tmem_st8(tb + 256 + ((unsigned)(warp * 32) << 16) + s * 8, r);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    long long t0 = 0;
+    if (rank == 0 && tid == 0) {
+        const unsigned idesc = make_idesc(256, P.N, 0, 0);
+        t0 = clock64();
+        for (int it = 0; it < P.iters; it++)
+            for (int s = 0; s < P.ksteps; s++)
+                umma_i8_ts_2cta(tb, tb + 256 + s * 8, make_desc(smem_u32(smem) + s * 32, 16, 1024, 2), idesc, (it > 0 || s > 0) ? 1u : 0u);
+        umma_commit_2cta(&bar);
+    }
+    mbar_wait(&bar, 0);
+    if (rank == 0 && tid == 0 && P.cycles) P.cycles[blockIdx.x / 2] = clock64() - t0;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (P.D)
+        for (int c0 = 0; c0 < P.N; c0 += 8) {
+            uint32_t r[8];
+            tmem_ld8(tb + ((unsigned)(warp * 32) << 16) + c0, r);
+            for (int q = 0; q < 8; q++) P.D[(size_t)(128 * rank + tid) * P.N + c0 + q] = (int)r[q];
+        }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
+}
+
+int pair_main() {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    const int G = prop.multiProcessorCount & ~1;
+    CK(cudaFuncSetAttribute(probe_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    for (int N : {32, 192, 256}) {
+        const int ksteps = 4, K = 128;
+        std::vector<uint8_t> A((size_t)256 * K);
+        std::vector<int8_t> B((size_t)N * K);
+        srand(77 + N);
+        for (auto &v : A) v = (uint8_t)(rand() & 0xFF);
+        for (auto &v : B) v = (int8_t)((rand() & 0xFF) - 128);
+        std::vector<int> ref((size_t)256 * N), got((size_t)256 * N, -1);
+        for (int m = 0; m < 256; m++)
+            for (int n = 0; n < N; n++) {
+                int s = 0;
+                for (int k = 0; k < K; k++) s += (int)A[(size_t)m * K + k] * (int)B[(size_t)n * K + k];
+                ref[(size_t)m * N + n] = s;
+            }
+        uint8_t *dA; int8_t *dB; int *dD;
+        CK(cudaMalloc(&dA, A.size())); CK(cudaMalloc(&dB, B.size())); CK(cudaMalloc(&dD, got.size() * 4));
+        CK(cudaMemcpy(dA, A.data(), A.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dB, B.data(), B.size(), cudaMemcpyHostToDevice));
+        Pair2Args P{N, ksteps, 1, dA, dB, dD, nullptr};
+        probe_pair_kernel<<<2, 128, 65536>>>(P);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("pair layout N=%d: CUDA error %s\n", N, cudaGetErrorString(e)); return 2; }
+        CK(cudaMemcpy(got.data(), dD, got.size() * 4, cudaMemcpyDeviceToHost));
+        size_t bad = 0;
+        for (size_t i = 0; i < got.size(); i++) bad += got[i] != ref[i];
+        printf("cta_group::2, A in TMEM (128 rows per CTA), B halves per CTA, M=256 N=%3d K=%d : %zu / %zu mismatches%s\n", N, K, bad, got.size(),
+               bad ? "" : "   <== OK");
+        cudaFree(dA); cudaFree(dB); cudaFree(dD);
+    }
+    long long *dcyc;
+    CK(cudaMalloc(&dcyc, sizeof(long long) * G));
+    printf("\ncta_group::2 throughput (%d SMs = %d pairs, M = 256, 4 k-steps per iteration, 2000 iterations):\n", G, G / 2);
+    for (int N : {32, 64, 128, 192, 256}) {
+        Pair2Args P{N, 4, 2000, nullptr, nullptr, nullptr, dcyc};
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        probe_pair_kernel<<<G, 128, 65536>>>(P);
+        CK(cudaEventRecord(e0));
+        probe_pair_kernel<<<G, 128, 65536>>>(P);
+        CK(cudaEventRecord(e1));
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("pair rate kernel: CUDA error %s\n", cudaGetErrorString(e)); return 2; }
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        std::vector<long long> cyc(G / 2);
+        CK(cudaMemcpy(cyc.data(), dcyc, sizeof(long long) * (G / 2), cudaMemcpyDeviceToHost));
+        long long mx = 0;
+        for (long long v : cyc) mx = v > mx ? v : mx;
+        const double mac = 8000.0 * 256.0 * N * 32;
+        printf("  pair TS N=%3d : %8lld clk -> %6.1f clk per pair MMA, %7.1f MAC/clk/SM, chip %6.1f TMAC/s (event %.3f ms)\n", N, mx, (double)mx / 8000.0,
+               mac / (double)mx / 2.0, mac * (G / 2) / (ms * 1e-3) / 1e12, ms);
+    }
     return 0;
 }
