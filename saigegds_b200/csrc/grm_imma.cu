@@ -66,6 +66,8 @@ struct ImmaPlan {
     // [k][lane] of 16-bit offsets padded to the longest row of the group with kSpTile (a zero slot of the vector tile)
     DevBuf<int64_t> mv_gstart, ms_gstart;   // [n_tiles * n_groups + 1] block starts (entries, multiples of 32)
     DevBuf<uint16_t> mv_ell, ms_ell;
+    int um_pair = 0;         // batched path: cta_group::2 MMAs in clusters of two CTAs (env SGB_UMMA_PAIR=1).  Correct, but with this
+                             // kernel's two A slots per M-tile the cross-CTA hand-over loop is too long: 7.6 vs 5.0 ms per phase
     int um_fork = 0;         // batched path: sparse corrections on the side stream beside the GEMMs (env SGB_UMMA_FORK)
     int um_gather_w = 16;    // columns per pass of the row-gather kernel: 8, 16 or 32 (env SGB_UMMA_GATHER_W)
     int um_gather_cols = 8;  // batched path: more columns than this take the row-gather sparse kernel (env SGB_UMMA_GATHER_COLS)
@@ -1121,8 +1123,10 @@ void umma_prepare(Context &c, ImmaPlan *p) {
         if (r == CUDA_SUCCESS)
             r = encode_tmap_2d(&u.tmap_pt, u.pt.get(), u.pitch_t, (uint64_t)N, u.pitch_t, kUBoxBytes, kURows, CU_TENSOR_MAP_SWIZZLE_128B);
         if (r != CUDA_SUCCESS) throw Error(SGB_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
-        SGB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmemBytes));
-        SGB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmemBytes));
+        SGB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmemBytes));
+        SGB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmemBytes));
+        SGB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmemBytes));
+        SGB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmemBytes));
         SGB_CUDA(cudaFuncSetAttribute(sparse_ell_multi_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, em_smem<4>()));
         SGB_CUDA(cudaFuncSetAttribute(sparse_ell_multi_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, em_smem<2>()));
         u.split_a = umma_pick_split((M + kURows - 1) / kURows, u.boxes_a, c.sm_count);
@@ -1197,25 +1201,51 @@ void launch_sparse_multi(Context &c, ImmaPlan *p, bool by_variant, const double 
     }
 }
 
-const CUtensorMap *umma_digit_map(ImmaPlan::Umma &u, bool phase_b, int ng) {
-    const int i = ng / 16;
+// digit-tile maps by box height (ng rows for the single-CTA kernel, ng / 2 for the pair kernel: a multiple of 16 either way)
+const CUtensorMap *umma_digit_map(ImmaPlan::Umma &u, bool phase_b, int box_rows) {
+    const int i = box_rows / 16;
     CUtensorMap *tm = phase_b ? &u.tmap_de[i] : &u.tmap_db[i];
     bool &have = u.have_d[i];
     if (!have) {
-        CUresult r = encode_tmap_2d(&u.tmap_db[i], u.db.get(), (uint64_t)u.cpad_a, kUMaxN, (uint64_t)u.cpad_a, 128, (uint32_t)ng, CU_TENSOR_MAP_SWIZZLE_128B);
+        CUresult r = encode_tmap_2d(&u.tmap_db[i], u.db.get(), (uint64_t)u.cpad_a, kUMaxN, (uint64_t)u.cpad_a, 128, (uint32_t)box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
         if (r == CUDA_SUCCESS)
-            r = encode_tmap_2d(&u.tmap_de[i], u.de.get(), (uint64_t)u.cpad_b, kUMaxN, (uint64_t)u.cpad_b, 128, (uint32_t)ng, CU_TENSOR_MAP_SWIZZLE_128B);
+            r = encode_tmap_2d(&u.tmap_de[i], u.de.get(), (uint64_t)u.cpad_b, kUMaxN, (uint64_t)u.cpad_b, 128, (uint32_t)box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
         if (r != CUDA_SUCCESS) throw Error(SGB_ERR_CUDA, "cuTensorMapEncodeTiled (digit tiles) failed (" + std::to_string((int)r) + ")");
         have = true;
     }
     return tm;
 }
 
+// launch of one GEMM phase: clusters of two CTAs along x (cta_group::2 MMAs) or plain CTAs
+void umma_launch(Context &c, ImmaPlan *p, bool pair, bool prof, int64_t rows, int splits, const CUtensorMap &tp, const CUtensorMap &td, const UmmaArgs &a) {
+    unsigned gx = (unsigned)((rows + kURows - 1) / kURows);
+    if (pair) gx = (gx + 1) & ~1u;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(gx, (unsigned)splits);
+    cfg.blockDim = dim3(kUThreads);
+    cfg.dynamicSmemBytes = kUSmemBytes;
+    cfg.stream = c.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (pair) {
+        if (prof) SGB_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<true, true>, tp, td, a));
+        else SGB_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<false, true>, tp, td, a));
+    } else {
+        if (prof) SGB_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<true, false>, tp, td, a));
+        else SGB_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<false, false>, tp, td, a));
+    }
+    (void)p;
+}
+
 // one pass: ncols <= 32 columns
 void umma_grm_mv_pass(Context &c, ImmaPlan *p, const double *b, double *out, int ncols) {
     ImmaPlan::Umma &u = p->um;
     const int64_t M = c.M, N = c.N;
-    const int ng = ((kUND * ncols + 15) / 16) * 16;
+    const bool pair = p->um_pair != 0;
+    const int ng = pair ? ((kUND * ncols + 31) / 32) * 32 : ((kUND * ncols + 15) / 16) * 16;     // pair: each CTA holds ng / 2 rows of a digit tile
     // The sparse corrections can run on the side stream beside the tensor-core GEMMs (env SGB_UMMA_FORK=1): U beside phase A, corr
     // beside phase B.  Measured on the B200: no gain (19.6 vs 19.2 ms at K = 30) -- next to a GEMM CTA (640 threads, 46 K registers)
     // only one 8-warp gather block fits per SM, and the gather lives on having ~64 warps x 16 loads in flight -- so the default is
@@ -1252,13 +1282,10 @@ void umma_grm_mv_pass(Context &c, ImmaPlan *p, const double *b, double *out, int
         SGB_CUDA(cudaMemsetAsync(u.prof.get(), 0, sizeof(long long) * 16 * 65536, c.stream));
         a.prof = u.prof.get();
     }
-    if (prof)
-        umma_gemm_kernel<true><<<dim3((unsigned)((M + kURows - 1) / kURows), ns_a), kUThreads, kUSmemBytes, c.stream>>>(u.tmap_p, *umma_digit_map(u, false, ng), a);
-    else
-        umma_gemm_kernel<false><<<dim3((unsigned)((M + kURows - 1) / kURows), ns_a), kUThreads, kUSmemBytes, c.stream>>>(u.tmap_p, *umma_digit_map(u, false, ng), a);
+    umma_launch(c, p, pair, prof, M, ns_a, u.tmap_p, *umma_digit_map(u, false, pair ? ng / 2 : ng), a);
     if (prof) {
         // debugging aid: cycle counters of the issuer thread and of one expander warp, averaged over the CTAs of phase A
-        const size_t ncta = (size_t)((M + kURows - 1) / kURows) * ns_a;
+        const size_t ncta = (size_t)((((M + kURows - 1) / kURows + (pair ? 1 : 0)) & (pair ? ~(int64_t)1 : ~(int64_t)0))) * ns_a;
         std::vector<long long> h(ncta * 16);
         c.d2h(h.data(), u.prof.get(), sizeof(long long) * ncta * 16);
         c.sync();
@@ -1291,7 +1318,7 @@ void umma_grm_mv_pass(Context &c, ImmaPlan *p, const double *b, double *out, int
     a.out_lo = u.r_lo.get(); a.out_hi = u.r_hi.get(); a.ldo = N;
     const int ns_b = (u.boxes_b + a.boxes_per_split - 1) / a.boxes_per_split;
     c.prof_begin();
-    umma_gemm_kernel<false><<<dim3((unsigned)((N + kURows - 1) / kURows), ns_b), kUThreads, kUSmemBytes, c.stream>>>(u.tmap_pt, *umma_digit_map(u, true, ng), a);
+    umma_launch(c, p, pair, false, N, ns_b, u.tmap_pt, *umma_digit_map(u, true, pair ? ng / 2 : ng), a);
     SGB_CHECK_LAUNCH();
     c.prof_end("umma_gemm_kernel (phase B)");
     if (fork) SGB_CUDA(cudaStreamWaitEvent(c.stream, p->ev_corr, 0));
@@ -1490,6 +1517,7 @@ void imma_prepare(Context &c) {
         }
         if (const char *e = getenv("SGB_UMMA_MIN_COLS")) { p->um_min_cols = atoi(e); if (p->um_min_cols <= 0) p->um_min_cols = INT_MAX; }
         if (const char *e = getenv("SGB_UMMA_FORK")) p->um_fork = atoi(e);
+        if (const char *e = getenv("SGB_UMMA_PAIR")) p->um_pair = atoi(e);
         if (const char *e = getenv("SGB_UMMA_GATHER_COLS")) p->um_gather_cols = atoi(e);
         if (const char *e = getenv("SGB_UMMA_GATHER_W")) { const int w = atoi(e); if (w == 8 || w == 16 || w == 32) p->um_gather_w = w; }
         if (const char *e = getenv("SGB_SPARSE_FORK")) p->opt_fork = atoi(e);

@@ -78,6 +78,26 @@ __device__ __forceinline__ void umma_i8_ts(unsigned d_tmem, unsigned a_tmem, uin
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n}"
                  ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+// cta_group::2: one instruction drives the tensor cores of both SMs of a CTA pair (M = 256: 128 rows per CTA, each CTA's A rows in its
+// own tensor memory, B split by rows over the two CTAs' shared memory at the same offset); issued by the leader CTA only
+__device__ __forceinline__ void umma_i8_ts_pair(unsigned d_tmem, unsigned a_tmem, uint64_t bdesc, unsigned idesc, unsigned accum) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, p;\n}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// the arrival lands on the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_arrive_pair(unsigned long long *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((unsigned short)3) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(unsigned long long *bar, unsigned rank) {
+    unsigned ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // K-major, 128-byte-swizzled operand tile (rows of 128 B, 8-row atoms of 1 KB): start >> 4 | LBO | SBO = 1024 >> 4 | version 1 | SWIZZLE_128B
 __device__ __forceinline__ uint64_t umma_desc_sw128(unsigned addr) {
     return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
@@ -110,14 +130,17 @@ struct UmmaArgs {
     long long *prof;           // PROF build only: per CTA 16 cycle counters (tools/umma_prof.py)
 };
 
-template <bool PROF>
+template <bool PROF, bool PAIR>
 __global__ void __launch_bounds__(kUThreads, 1) umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_p,
                                                                  const __grid_constant__ CUtensorMap tmap_d, UmmaArgs A) {
     extern __shared__ uint8_t smem_dyn[];
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     uint8_t *pack = base;                                   // kUNP x 32 KB
     uint8_t *btile = base + kUNP * kUPackBytes;             // kUNB x (ng x 128 B)
-    const unsigned btile_bytes = (unsigned)A.ng * 128u;
+    // PAIR: the kernel runs in clusters of two CTAs along x; CTA `crank` holds rows [ng / 2 crank, + ng / 2) of every digit tile
+    unsigned crank = 0;
+    if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const unsigned btile_bytes = (unsigned)(PAIR ? A.ng / 2 : A.ng) * 128u;
     UmmaSmem &S = *reinterpret_cast<UmmaSmem *>(btile + kUNB * kUMaxN * 128);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     volatile int *err = A.err;
@@ -131,16 +154,21 @@ __global__ void __launch_bounds__(kUThreads, 1) umma_gemm_kernel(const __grid_co
         S.deadline = global_ns() + g_wait_timeout_ns;
         for (int i = 0; i < kUNP; i++) { mbar_init(&S.p_full[i], 1); mbar_init(&S.p_empty[i], kUExpWarps); }
         for (int i = 0; i < kUNB; i++) { mbar_init(&S.b_full[i], 1); mbar_init(&S.mma_done[0][i], 1); mbar_init(&S.mma_done[1][i], 1); }
-        for (int i = 0; i < 4; i++) { mbar_init(&S.a_full[0][i], 4); mbar_init(&S.a_full[1][i], 4); }
+        for (int i = 0; i < 4; i++) { mbar_init(&S.a_full[0][i], PAIR ? 8 : 4); mbar_init(&S.a_full[1][i], PAIR ? 8 : 4); }   // leader: both CTAs' expanders
         for (int i = 0; i < 2; i++) mbar_init(&S.acc_full[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 3) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();     // barriers initialised and tensor memory allocated in both CTAs
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tb = S.tmem_base;
     const int ns = umma_ns(A.ng);                          // A slots per M-tile
@@ -172,14 +200,15 @@ __global__ void __launch_bounds__(kUThreads, 1) umma_gemm_kernel(const __grid_co
                     if (!(mbar_wait(&S.mma_done[0][bs], par, err, dl) && mbar_wait(&S.mma_done[1][bs], par, err, dl))) break;
                 }
                 mbar_expect_tx(&S.b_full[bs], btile_bytes);
-                tma_load_2d_nohint(btile + (size_t)bs * btile_bytes, &tmap_d, (box0 * 4 + st) * kUStage, 0, &S.b_full[bs]);
+                tma_load_2d_nohint(btile + (size_t)bs * btile_bytes, &tmap_d, (box0 * 4 + st) * kUStage, PAIR ? (int)crank * (A.ng / 2) : 0,
+                                   &S.b_full[bs]);
             }
         }
     } else if (warp == 1 || warp == 2) {
         // ------------------------------------------------------------------ MMA issuer of M-tile mt: one wait, four MMAs, one commit per stage
-        if (lane == 0) {
+        if (lane == 0 && crank == 0) {
             const int mt = warp - 1;
-            const unsigned idesc = umma_idesc_i8(128, A.ng);
+            const unsigned idesc = umma_idesc_i8(PAIR ? 256 : 128, A.ng);
             const unsigned bt0 = smem_u32(btile);
             const unsigned acc = tb + mt * acc_stride, a0 = tb + stage_col + mt * stage_mt;
             bool ok = true;
@@ -195,12 +224,13 @@ __global__ void __launch_bounds__(kUThreads, 1) umma_gemm_kernel(const __grid_co
                 const unsigned bb = bt0 + (unsigned)bs * btile_bytes;
 #pragma unroll
                 for (int ks = 0; ks < 4; ks++)
-                    umma_i8_ts(acc, a0 + as * 32 + ks * 8, umma_desc_sw128(bb + ks * 32), idesc, (st > 0 || ks > 0) ? 1u : 0u);
+                    if (PAIR) umma_i8_ts_pair(acc, a0 + as * 32 + ks * 8, umma_desc_sw128(bb + ks * 32), idesc, (st > 0 || ks > 0) ? 1u : 0u);
+                    else umma_i8_ts(acc, a0 + as * 32 + ks * 8, umma_desc_sw128(bb + ks * 32), idesc, (st > 0 || ks > 0) ? 1u : 0u);
                 if (PROF) { t0 = clock64(); c_mma += t0 - t1; }
-                umma_commit_arrive(&S.mma_done[mt][bs]);
+                if (PAIR) umma_commit_arrive_pair(&S.mma_done[mt][bs]); else umma_commit_arrive(&S.mma_done[mt][bs]);
                 if (PROF) { t1 = clock64(); c_cm += t1 - t0; }
             }
-            umma_commit_arrive(&S.acc_full[mt]);
+            if (PAIR) umma_commit_arrive_pair(&S.acc_full[mt]); else umma_commit_arrive(&S.acc_full[mt]);
             if (PROF && mt == 0) {
                 long long *o = A.prof + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
                 o[0] = clock64() - t_begin; o[1] = 0; o[2] = c_wa; o[3] = c_mma; o[4] = c_cm; o[5] = n_st;
@@ -245,7 +275,7 @@ __global__ void __launch_bounds__(kUThreads, 1) umma_gemm_kernel(const __grid_co
             if (!ok) break;
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive(&S.a_full[mt][st % ns]);
+                if (PAIR) mbar_arrive_cluster(&S.a_full[mt][st % ns], 0u); else mbar_arrive(&S.a_full[mt][st % ns]);
                 if ((st & 3) >= 2 || st + 2 >= n_st) mbar_arrive(&S.p_empty[ps]);       // this set's last stage in the box
             }
             if (PROF) { t1 = clock64(); c_ar += t1 - t0; }
@@ -282,10 +312,11 @@ __global__ void __launch_bounds__(kUThreads, 1) umma_gemm_kernel(const __grid_co
     }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();     // the peer may still read this CTA's shared / tensor memory until here
     if (warp == 3) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
     }
 }
 
