@@ -510,6 +510,7 @@ def fit_on_stored(ctx, n, m_total, var_offset, m_local, rank, world, dist, trait
                       "host_setup_s": t_setup, "tau": [float(x) for x in glmm["tau"]], "converged": bool(glmm["converged"]),
                       "products_fit": int(st_fit["n_products"]), "products_total": int(st["n_products"]),
                       "pcg_solves": int(st["n_pcg_solves"]), "pcg_iterations": int(st["n_pcg_iterations"]),
+                      "host_syncs_fit": int(st_fit["n_host_syncs"]), "host_wait_s_fit": float(st_fit["host_wait_s"]),
                       "var_ratio_mean": float(np.mean(vr["ratio"])), "n_markers": int(len(vr["ratio"])),
                       "workload": "synthetic N=%d M=%d %s trait, y ~ x1 + x2 + g, var(g) = %.2g from 1,000 causal variants, intercept %.1f; "
                                   "seqFitNullGLMM_SPA defaults (nrun 30, tol 0.02, tolPCG 1e-5)" % (n, m_total, trait, ph["h2"], ph["intercept"]),

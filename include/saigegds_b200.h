@@ -270,6 +270,9 @@ typedef struct {
     int64_t n_pcg_solves;
     int64_t n_pcg_iterations;
     double last_product_ms;    /* CUDA-event time of the most recent sgb_grm_mv*_ call, device part only */
+    int64_t n_host_syncs;      /* cudaStreamSynchronize calls on the library's stream */
+    double host_wait_s;        /* wall-clock seconds the host spent blocked in them (GPU busy); entry-point wall time minus this
+                                  is host-side work with the GPU idle or running ahead */
 } sgb_stats;
 int sgb_get_stats(sgb_context *ctx, sgb_stats *out);
 int sgb_reset_stats(sgb_context *ctx);

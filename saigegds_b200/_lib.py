@@ -77,7 +77,8 @@ class GxG(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("n_products", C.c_int64), ("n_product_launches", C.c_int64), ("n_kernel_launches", C.c_int64),
-                ("n_pcg_solves", C.c_int64), ("n_pcg_iterations", C.c_int64), ("last_product_ms", C.c_double)]
+                ("n_pcg_solves", C.c_int64), ("n_pcg_iterations", C.c_int64), ("last_product_ms", C.c_double),
+                ("n_host_syncs", C.c_int64), ("host_wait_s", C.c_double)]
 
 
 # every symbol declared in include/saigegds_b200.h

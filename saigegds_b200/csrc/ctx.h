@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <chrono>
 #include <cstdarg>
 #include <map>
 #include <cstdio>
@@ -159,7 +160,10 @@ struct Context {
     volatile int *async_err = nullptr;   // pinned flag copied back after every fused-kernel launch
     int *async_err_dev = nullptr;        // its device-side source (cleared after an error was reported)
     void sync() {
+        const auto t_sync0 = std::chrono::steady_clock::now();
         SGB_CUDA(cudaStreamSynchronize(stream));
+        stats.n_host_syncs++;
+        stats.host_wait_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_sync0).count();
         if (async_err && *async_err) {
             const int code = *async_err;
             *async_err = 0;

@@ -66,8 +66,9 @@ struct ImmaPlan {
     // [k][lane] of 16-bit offsets padded to the longest row of the group with kSpTile (a zero slot of the vector tile)
     DevBuf<int64_t> mv_gstart, ms_gstart;   // [n_tiles * n_groups + 1] block starts (entries, multiples of 32)
     DevBuf<uint16_t> mv_ell, ms_ell;
-    int um_pair = 0;         // batched path: cta_group::2 MMAs in clusters of two CTAs (env SGB_UMMA_PAIR=1).  Correct, but with this
-                             // kernel's two A slots per M-tile the cross-CTA hand-over loop is too long: 7.6 vs 5.0 ms per phase
+    int um_pair = 2;         // batched GEMM kernel: 2 = pair kernel (clusters of two CTAs, cta_group::2 MMAs, one M-tile per CTA, eight A slots,
+                             // four issuer threads: 4.6 ms per phase at K = 30, 3.5 ms for few columns), 0 = one CTA per MMA (5.0 / 4.0 ms),
+                             // 1 = the single-CTA kernel's structure with pair MMAs (7.6 ms: hand-over loop too long); env SGB_UMMA_PAIR
     int um_fork = 0;         // batched path: sparse corrections on the side stream beside the GEMMs (env SGB_UMMA_FORK)
     int um_gather_w = 16;    // columns per pass of the row-gather kernel: 8, 16 or 32 (env SGB_UMMA_GATHER_W)
     int um_gather_cols = 8;  // batched path: more columns than this take the row-gather sparse kernel (env SGB_UMMA_GATHER_COLS)
@@ -119,7 +120,8 @@ struct ImmaPlan {
         DevBuf<int> err;
         DevBuf<long long> prof;
         PinBuf<int> herr;
-        CUtensorMap tmap_p, tmap_pt, tmap_db[15], tmap_de[15];
+        CUtensorMap tmap_p, tmap_pt, tmap_p128, tmap_pt128, tmap_db[15], tmap_de[15];
+        int split_a2 = 1, split_b2 = 1;   // splits of the pair kernel (a cluster = 256 rows on two SMs)
         bool have_d[15] = {false};
     } um;
 };
@@ -1122,7 +1124,10 @@ void umma_prepare(Context &c, ImmaPlan *p) {
         CUresult r = encode_tmap_2d(&u.tmap_p, c.packed.get(), c.pitch, (uint64_t)M, c.pitch, kUBoxBytes, kURows, CU_TENSOR_MAP_SWIZZLE_128B);
         if (r == CUDA_SUCCESS)
             r = encode_tmap_2d(&u.tmap_pt, u.pt.get(), u.pitch_t, (uint64_t)N, u.pitch_t, kUBoxBytes, kURows, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (r == CUDA_SUCCESS) r = encode_tmap_2d(&u.tmap_p128, c.packed.get(), c.pitch, (uint64_t)M, c.pitch, kUBoxBytes, kPRows, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (r == CUDA_SUCCESS) r = encode_tmap_2d(&u.tmap_pt128, u.pt.get(), u.pitch_t, (uint64_t)N, u.pitch_t, kUBoxBytes, kPRows, CU_TENSOR_MAP_SWIZZLE_128B);
         if (r != CUDA_SUCCESS) throw Error(SGB_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+        SGB_CUDA(cudaFuncSetAttribute(umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes));
         SGB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmemBytes));
         SGB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmemBytes));
         SGB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmemBytes));
@@ -1131,8 +1136,10 @@ void umma_prepare(Context &c, ImmaPlan *p) {
         SGB_CUDA(cudaFuncSetAttribute(sparse_ell_multi_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, em_smem<2>()));
         u.split_a = umma_pick_split((M + kURows - 1) / kURows, u.boxes_a, c.sm_count);
         u.split_b = umma_pick_split((N + kURows - 1) / kURows, u.boxes_b, c.sm_count);
-        if (const char *e = getenv("SGB_UMMA_SPLIT_A")) u.split_a = std::max(1, atoi(e));
-        if (const char *e = getenv("SGB_UMMA_SPLIT_B")) u.split_b = std::max(1, atoi(e));
+        u.split_a2 = umma_pick_split((M + kURows - 1) / kURows, u.boxes_a, c.sm_count / 2);
+        u.split_b2 = umma_pick_split((N + kURows - 1) / kURows, u.boxes_b, c.sm_count / 2);
+        if (const char *e = getenv("SGB_UMMA_SPLIT_A")) u.split_a = u.split_a2 = std::max(1, atoi(e));
+        if (const char *e = getenv("SGB_UMMA_SPLIT_B")) u.split_b = u.split_b2 = std::max(1, atoi(e));
         c.sync();
         u.ready = true;
     } catch (const Error &e) {
@@ -1218,6 +1225,12 @@ const CUtensorMap *umma_digit_map(ImmaPlan::Umma &u, bool phase_b, int box_rows)
 
 // launch of one GEMM phase: clusters of two CTAs along x (cta_group::2 MMAs) or plain CTAs
 void umma_launch(Context &c, ImmaPlan *p, bool pair, bool prof, int64_t rows, int splits, const CUtensorMap &tp, const CUtensorMap &td, const UmmaArgs &a) {
+    if (p->um_pair == 2) {          // pair kernel: 128 rows per CTA, clusters of two (static __cluster_dims__)
+        const unsigned gx2 = ((unsigned)((rows + kPRows - 1) / kPRows) + 1) & ~1u;
+        umma_pair_kernel<<<dim3(gx2, (unsigned)splits), kPThreads, kPSmemBytes, c.stream>>>(tp, td, a);
+        SGB_CHECK_LAUNCH();
+        return;
+    }
     unsigned gx = (unsigned)((rows + kURows - 1) / kURows);
     if (pair) gx = (gx + 1) & ~1u;
     cudaLaunchConfig_t cfg = {};
@@ -1271,7 +1284,8 @@ void umma_grm_mv_pass(Context &c, ImmaPlan *p, const double *b, double *out, int
     UmmaArgs a;
     a.ncols = ncols; a.ng = ng; a.err = u.err.get();
     // phase A: rows = variants, contraction over samples
-    a.R = M; a.boxes_total = u.boxes_a; a.boxes_per_split = (u.boxes_a + u.split_a - 1) / u.split_a;
+    const int sa = p->um_pair == 2 ? u.split_a2 : u.split_a, sb = p->um_pair == 2 ? u.split_b2 : u.split_b;
+    a.R = M; a.boxes_total = u.boxes_a; a.boxes_per_split = (u.boxes_a + sa - 1) / sa;
     a.out_lo = u.t_lo.get(); a.out_hi = u.t_hi.get(); a.ldo = M;
     const int ns_a = (u.boxes_a + a.boxes_per_split - 1) / a.boxes_per_split;
     c.prof_begin();
@@ -1282,19 +1296,18 @@ void umma_grm_mv_pass(Context &c, ImmaPlan *p, const double *b, double *out, int
         SGB_CUDA(cudaMemsetAsync(u.prof.get(), 0, sizeof(long long) * 16 * 65536, c.stream));
         a.prof = u.prof.get();
     }
-    umma_launch(c, p, pair, prof, M, ns_a, u.tmap_p, *umma_digit_map(u, false, pair ? ng / 2 : ng), a);
+    umma_launch(c, p, pair, prof, M, ns_a, p->um_pair == 2 ? u.tmap_p128 : u.tmap_p, *umma_digit_map(u, false, pair ? ng / 2 : ng), a);
     if (prof) {
-        // debugging aid: cycle counters of the issuer thread and of one expander warp, averaged over the CTAs of phase A
-        const size_t ncta = (size_t)((((M + kURows - 1) / kURows + (pair ? 1 : 0)) & (pair ? ~(int64_t)1 : ~(int64_t)0))) * ns_a;
-        std::vector<long long> h(ncta * 16);
-        c.d2h(h.data(), u.prof.get(), sizeof(long long) * ncta * 16);
+        // debugging aid: cycle counters of one issuer thread and of one expander warp of the leader CTAs, per OWN stage
+        std::vector<long long> h((size_t)16 * 65536);
+        c.d2h(h.data(), u.prof.get(), sizeof(long long) * h.size());
         c.sync();
         double s[16] = {0};
-        for (size_t i = 0; i < ncta; i++) for (int k = 0; k < 16; k++) s[k] += (double)h[i * 16 + k];
-        const double ks = s[5] > 0 ? s[5] : 1;
-        c.printf("umma prof (clk per stage, %zu CTAs): issuer total %.0f = wait_a %.0f + mma %.0f + commit %.0f | expander (per own stage) total %.0f = "
-                 "wait_p %.0f + load/expand %.0f + wait_empty %.0f + st/wait::st %.0f + wait_b/arrive %.0f\n", ncta, s[0] / ks, s[2] / ks, s[3] / ks,
-                 s[4] / ks, 2 * s[8] / ks, 2 * s[9] / ks, 2 * s[10] / ks, 2 * s[11] / ks, 2 * s[12] / ks, 2 * s[13] / ks);
+        for (size_t i = 0; i < 65536; i++) for (int k = 0; k < 16; k++) s[k] += (double)h[i * 16 + k];
+        const double ks = s[5] > 0 ? s[5] : 1, es = s[14] > 0 ? s[14] : ks;
+        c.printf("umma prof (clk per own stage): issuer total %.0f = wait_a %.0f + mma %.0f + commit %.0f | expander total %.0f = "
+                 "wait_p %.0f + load/expand %.0f + wait_done %.0f + st/wait::st %.0f + wait_b/arrive %.0f\n", s[0] / ks, s[2] / ks, s[3] / ks,
+                 s[4] / ks, s[8] / es, s[9] / es, s[10] / es, s[11] / es, s[12] / es, s[13] / es);
     }
     SGB_CHECK_LAUNCH();
     c.prof_end("umma_gemm_kernel (phase A)");
@@ -1314,11 +1327,11 @@ void umma_grm_mv_pass(Context &c, ImmaPlan *p, const double *b, double *out, int
     launch_sparse_multi(c, p, false, u.hm.get(), M, ncols, u.corr.get(), N, side);
     if (fork) SGB_CUDA(cudaEventRecord(p->ev_corr, side));
     // phase B: rows = samples, contraction over variants (sample-major copy)
-    a.R = N; a.boxes_total = u.boxes_b; a.boxes_per_split = (u.boxes_b + u.split_b - 1) / u.split_b;
+    a.R = N; a.boxes_total = u.boxes_b; a.boxes_per_split = (u.boxes_b + sb - 1) / sb;
     a.out_lo = u.r_lo.get(); a.out_hi = u.r_hi.get(); a.ldo = N;
     const int ns_b = (u.boxes_b + a.boxes_per_split - 1) / a.boxes_per_split;
     c.prof_begin();
-    umma_launch(c, p, pair, false, N, ns_b, u.tmap_pt, *umma_digit_map(u, true, pair ? ng / 2 : ng), a);
+    umma_launch(c, p, pair, false, N, ns_b, p->um_pair == 2 ? u.tmap_pt128 : u.tmap_pt, *umma_digit_map(u, true, pair ? ng / 2 : ng), a);
     SGB_CHECK_LAUNCH();
     c.prof_end("umma_gemm_kernel (phase B)");
     if (fork) SGB_CUDA(cudaStreamWaitEvent(c.stream, p->ev_corr, 0));

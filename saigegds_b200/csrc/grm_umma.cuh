@@ -93,10 +93,17 @@ __device__ __forceinline__ void umma_commit_arrive_pair(unsigned long long *bar)
 __device__ __forceinline__ void mbar_arrive_cluster(unsigned long long *bar, unsigned rank) {
     unsigned ra;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");     // (the form CUTLASS' ClusterBarrier::arrive uses)
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 2-D TMA load of a CTA pair: the bytes land in this CTA's shared memory, the transaction count on the barrier of CTA `bar_rank`
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *tmap, int x, int y, unsigned long long *bar, unsigned bar_rank) {
+    unsigned ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(bar_rank));
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(ra) : "memory");
 }
 // K-major, 128-byte-swizzled operand tile (rows of 128 B, 8-row atoms of 1 KB): start >> 4 | LBO | SBO = 1024 >> 4 | version 1 | SWIZZLE_128B
 __device__ __forceinline__ uint64_t umma_desc_sw128(unsigned addr) {
@@ -647,4 +654,202 @@ __global__ void transpose_cols_kernel(const double *__restrict__ src, int64_t ld
     double2 *d = reinterpret_cast<double2 *>(dst + (size_t)i * W);
 #pragma unroll
     for (int c = 0; c < W; c += 2) d[c >> 1] = make_double2(v[c], v[c + 1]);
+}
+
+// ---- pair kernel: cta_group::2 MMAs, one M = 128 tile per CTA, eight A slots ------------------------------------------------------------
+// tools/umma_probe.cu (profiles/r02_umma_probe_pair_b200.txt): a tcgen05.mma of one CTA costs ~124 clk whatever N <= 240, a pair MMA
+// (M = 256 over two SMs) 96.3 clk for N <= 192 = 8,167 MAC/clk/SM at N = 192, 99.7 % of the int8 peak.  The kernel above is therefore
+// bound by MMA dispatch (8 x 124 clk per stage and SM).  Here a cluster of two CTAs shares every MMA: each CTA owns 128 rows (one
+// M-tile, accumulator of 192 columns), which leaves 256 tensor-memory columns = EIGHT A-operand slots, so the cross-CTA hand-over loop
+// (remote a_full arrivals, multicast commits) is hidden; each CTA loads half of every digit tile (rows [ng/2 rank, +ng/2)), which
+// also halves the L2 -> SM traffic of the digit matrix.
+//   warp 0: packed boxes [128 rows x 128 B] (4 stages each, ring of 4)     warp 2: digit half tiles (ring of 8)
+//   warp 1: issuer (leader CTA only): per stage one wait, four pair MMAs, one multicast commit
+//   warp 3: tensor-memory allocation (cta_group::2)                        warps 4..19: four expander sets, set s serves st % 4 == s
+constexpr int kPRows = 128, kPNP = 4, kPNB = 8, kPNA = 8;
+constexpr int kPIssuers = 4;            // issuing threads (leader CTA), stages round-robin: for ONE thread a tcgen05.mma costs ~100 clk of issue
+                                        // latency and a multicast commit ~240 clk (tools/umma_probe.cu), a pair MMA of N = 192 keeps the pipe 96 clk
+constexpr int kPThreads = (20 + kPIssuers) * 32;    // warp 0: packed boxes, 1 / 3: digit tiles, 2: tensor-memory allocation, 4..19: expanders, 20..: issuers
+constexpr int kPPackBytes = kPRows * kUBoxBytes;      // 16 KB
+constexpr int kPBMax = (kUMaxN / 2) * 128;            // 12 KB
+struct PairSmem {
+    unsigned long long p_full[kPNP], p_empty[kPNP], b_full[kPNB], a_full[kPNA], mma_done[kPNB], acc_full, first_issued;
+    unsigned long long deadline;
+    unsigned tmem_base;
+};
+constexpr int kPSmemBytes = kPNP * kPPackBytes + kPNB * kPBMax + 1024 + (int)sizeof(PairSmem);
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, 1) umma_pair_kernel(const __grid_constant__ CUtensorMap tmap_p,
+                                                                                          const __grid_constant__ CUtensorMap tmap_d, UmmaArgs A) {
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    uint8_t *pack = base;
+    uint8_t *btile = base + kPNP * kPPackBytes;
+    PairSmem &S = *reinterpret_cast<PairSmem *>(btile + kPNB * kPBMax);
+    unsigned crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const unsigned bhalf_rows = (unsigned)A.ng / 2, btile_bytes = bhalf_rows * 128u;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    volatile int *err = A.err;
+    const int box0 = blockIdx.y * A.boxes_per_split;
+    const int n_box = min(A.boxes_per_split, A.boxes_total - box0);
+    const int n_st = n_box * 4;
+    const int row0 = blockIdx.x * kPRows;
+    const volatile unsigned long long *dl = &S.deadline;
+    if (tid == 0) {
+        S.deadline = global_ns() + g_wait_timeout_ns;
+        for (int i = 0; i < kPNP; i++) { mbar_init(&S.p_full[i], 1); mbar_init(&S.p_empty[i], 16); }
+        for (int i = 0; i < kPNB; i++) { mbar_init(&S.b_full[i], 1); mbar_init(&S.mma_done[i], 1); }
+        for (int i = 0; i < kPNA; i++) mbar_init(&S.a_full[i], 8);          // four expander warps of each CTA of the pair
+        mbar_init(&S.acc_full, kPIssuers);                                   // one commit per issuer
+        mbar_init(&S.first_issued, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tb = S.tmem_base;
+    constexpr unsigned kStage0 = 256;                       // A slots: columns 256 + 32 slot; accumulator: columns [0, ng)
+
+    if (n_st > 0) {
+    if (warp == 0) {
+        if (lane == 0) {
+            unsigned long long policy;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+            for (int bx = 0; bx < n_box; bx++) {
+                const int ps = bx % kPNP;
+                if (bx >= kPNP && !mbar_wait(&S.p_empty[ps], (unsigned)(((bx / kPNP) - 1) & 1), err, dl)) break;
+                mbar_expect_tx(&S.p_full[ps], kPPackBytes);
+                tma_load_2d(pack + (size_t)ps * kPPackBytes, &tmap_p, (box0 + bx) * kUBoxBytes, row0, &S.p_full[ps], policy);
+            }
+        }
+    } else if (warp == 1 || warp == 3) {
+        // digit half tiles, two producer threads on alternating stages (one thread's wait + expect_tx + TMA issue is ~500 clk per stage)
+        if (lane == 0) {
+            for (int st = (warp == 1 ? 0 : 1); st < n_st; st += 2) {
+                const int bs = st % kPNB;
+                if (st >= kPNB && !mbar_wait(&S.mma_done[bs], (unsigned)(((st / kPNB) - 1) & 1), err, dl)) break;
+                // both halves of the tile are counted on the LEADER's barrier (the issuers wait there); the leader expects all the bytes
+                if (crank == 0) mbar_expect_tx(&S.b_full[bs], 2 * btile_bytes);
+                tma_load_2d_pair(btile + (size_t)bs * kPBMax, &tmap_d, (box0 * 4 + st) * kUStage, (int)(crank * bhalf_rows), &S.b_full[bs], 0u);
+            }
+        }
+    } else if (warp >= 20) {
+        // two issuers (leader CTA), stages alternating: for the issuing thread a stage is a serial wait (~200-350 clk) + four pair MMAs
+        // (~385 clk, the thread is held while the queue is full) + multicast commit; one thread alone leaves the tensor pipe idle half
+        // of the time.  Integer accumulation commutes, so the interleaving of the two MMA streams on the one accumulator does not
+        // matter -- except that the zero-initialising MMA (stage 0, k-step 0) must be first: issuer 1 waits for it to be issued.
+        if (lane == 0 && crank == 0) {
+            const int me = warp - 20;
+            const unsigned idesc = umma_idesc_i8(256, A.ng);
+            const unsigned bt0 = smem_u32(btile);
+            long long c_wa = 0, c_mma = 0, c_cm = 0, t0 = 0, t1 = 0;
+            const bool PROF = A.prof != nullptr;
+            const long long t_begin = PROF ? clock64() : 0;
+            for (int st = me; st < n_st; st += kPIssuers) {
+                const int sl = st % kPNA;
+                if (PROF) t0 = clock64();
+                if (!mbar_wait(&S.a_full[sl], (unsigned)((st / kPNA) & 1), err, dl)) break;
+                if (!mbar_wait(&S.b_full[st % kPNB], (unsigned)((st / kPNB) & 1), err, dl)) break;
+                if (PROF) { t1 = clock64(); c_wa += t1 - t0; }
+                if (st == me && me != 0 && !mbar_wait(&S.first_issued, 0u, err, dl)) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned bb = bt0 + (unsigned)(st % kPNB) * kPBMax;
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++)
+                    umma_i8_ts_pair(tb, tb + kStage0 + sl * 32 + ks * 8, umma_desc_sw128(bb + ks * 32), idesc, (st > 0 || ks > 0) ? 1u : 0u);
+                if (st == 0) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&S.first_issued);
+                }
+                if (PROF) { t0 = clock64(); c_mma += t0 - t1; }
+                umma_commit_arrive_pair(&S.mma_done[st % kPNB]);
+                if (PROF) { t1 = clock64(); c_cm += t1 - t0; }
+            }
+            umma_commit_arrive_pair(&S.acc_full);
+            if (PROF && me == 0) {
+                long long *o = A.prof + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
+                o[0] = clock64() - t_begin; o[1] = 0; o[2] = c_wa; o[3] = c_mma; o[4] = c_cm; o[5] = (n_st + kPIssuers - 1) / kPIssuers;
+            }
+        }
+    } else if (warp >= 4 && warp < 20) {
+        const int e = warp - 4, set = e >> 2, quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const unsigned lane_base = (unsigned)(quarter * 32) << 16;
+        const unsigned prow = (unsigned)r * kUBoxBytes, psw = (unsigned)(r & 7);
+        bool ok = true;
+        long long c_wp = 0, c_ld = 0, c_we = 0, c_st = 0, c_ar = 0, t0 = 0, t1 = 0;
+        const bool PROF = A.prof != nullptr;
+        const long long t_begin = PROF ? clock64() : 0;
+        for (int st = set; st < n_st && ok; st += 4) {
+            const int bx = st >> 2, ps = bx % kPNP, sl = st % kPNA;
+            if (PROF) t0 = clock64();
+            ok = mbar_wait(&S.p_full[ps], (unsigned)((bx / kPNP) & 1), err, dl);
+            if (!ok) break;
+            if (PROF) { t1 = clock64(); c_wp += t1 - t0; }
+            const uint8_t *src = pack + (size_t)ps * kPPackBytes + prow;
+            const unsigned c0 = (unsigned)(st & 3) * 2;
+            const uint4 wa = *reinterpret_cast<const uint4 *>(src + ((c0 ^ psw) << 4));
+            const uint4 wb = *reinterpret_cast<const uint4 *>(src + (((c0 + 1) ^ psw) << 4));
+            const uint32_t ws[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            uint32_t x[32];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int t = 0; t < 4; t++) x[4 * i + t] = (ws[i] >> (2 * t)) & 0x03030303u;
+            if (PROF) { t0 = clock64(); c_ld += t0 - t1; }
+            if (st >= kPNA) ok = mbar_wait(&S.mma_done[(st - kPNA) % kPNB], (unsigned)(((st - kPNA) / kPNB) & 1), err, dl);
+            if (!ok) break;
+            if (PROF) { t1 = clock64(); c_we += t1 - t0; }
+            tmem_st32(tb + lane_base + kStage0 + (unsigned)sl * 32u, x);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (PROF) { t0 = clock64(); c_st += t0 - t1; }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_cluster(&S.a_full[sl], 0u);
+                mbar_arrive(&S.p_empty[ps]);
+            }
+            if (PROF) { t1 = clock64(); c_ar += t1 - t0; }
+        }
+        if (PROF && warp == 4 && lane == 0 && crank == 0) {
+            long long *o = A.prof + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
+            o[8] = clock64() - t_begin; o[9] = c_wp; o[10] = c_ld; o[11] = c_we; o[12] = c_st; o[13] = c_ar; o[14] = (n_st + 3) / 4;
+        }
+        if (ok) ok = mbar_wait(&S.acc_full, 0u, err, dl);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (ok) {
+            const int64_t row = (int64_t)row0 + r;
+            for (int g = set; g * 8 < A.ncols; g += 4) {
+                int v[8 * kUND];
+#pragma unroll
+                for (int i = 0; i < kUND; i++) tmem_ld8_nowait(tb + lane_base + g * (8 * kUND) + i * 8, v + 8 * i);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int cc = 0; cc < 8; cc++) {
+                    const int col = g * 8 + cc;
+                    long long lo = 0, hi = 0;
+#pragma unroll
+                    for (int l = 2; l >= 0; l--) lo = lo * 256 + v[cc * kUND + l];
+#pragma unroll
+                    for (int l = 5; l >= 3; l--) hi = hi * 256 + v[cc * kUND + l];
+                    if (col < A.ncols && row < A.R) {
+                        red_add_u64(A.out_lo + (size_t)col * A.ldo + row, (unsigned long long)lo);
+                        red_add_u64(A.out_hi + (size_t)col * A.ldo + row, (unsigned long long)hi);
+                    }
+                }
+            }
+        }
+    }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
+    }
 }

@@ -8,6 +8,8 @@
 //     multi-right-hand-side PCG batches; every column keeps its own alpha/beta/stop test;
 //   * the Rademacher vectors u_i are identical in every get_trace call because the reference re-seeds
 //     R's RNG each time (:631, :676), so u_i and GRM*u_i (:652) are generated once per fit and cached.
+#include <chrono>
+#include <map>
 #include <algorithm>
 #include <cmath>
 
@@ -37,6 +39,19 @@ void grm_mv_device(Context &c, const double *b, double *out, int k) {
 namespace {
 
 typedef std::vector<double> hvec;
+
+// wall-clock phase timer of a fit (env SGB_FIT_TIMING: printed once at the end; a debugging aid for host-side overheads)
+struct PhaseTimer {
+    std::map<std::string, double> t;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char *name) {
+        const auto now = std::chrono::steady_clock::now();
+        t[name] += std::chrono::duration<double>(now - t0).count();
+        t0 = now;
+    }
+};
+PhaseTimer *g_phase = nullptr;
+inline void lap(const char *name) { if (g_phase) g_phase->lap(name); }
 
 struct hmat {  // column-major host matrix
     int nr = 0, nc = 0;
@@ -251,14 +266,18 @@ struct Solver {
             cap_u = new_cap;
         }
         const int cnt = upto - n_u;
+        lap("other");
         std::vector<int8_t> h((size_t)N * cnt);
         if (c.rademacher_fn) c.rademacher_fn(c.cb_user, n_u == 0 ? 1 : 0, P.seed, (int64_t)N * cnt, h.data());
         else for (size_t i = 0; i < h.size(); i++) h[i] = (int8_t)trace_rng.bernoulli_half();
+        lap("rademacher draws on the host (R's RNG)");
         bits.ensure(h.size());
         c.h2d(bits.get(), h.data(), h.size());
         expand_rademacher(c, bits.get(), U.get() + (size_t)N * n_u, (int64_t)N * cnt);
         c.sync();  // h goes out of scope
         grm_mv_device(c, U.get() + (size_t)N * n_u, AU.get() + (size_t)N * n_u, cnt);   // :652 / :698
+        c.sync();
+        lap("GRM u_i (cached once per fit)");
         n_u = upto;
     }
 
@@ -396,6 +415,8 @@ void fit_AI_PCG(Context &c, bool quant, const sgb_fit0 *f, const double *hX, con
     const int64_t N = c.N;
     const int p = f->p;
     const double tol = P.tol, tol_inv_2 = 1 / (tol * tol);
+    PhaseTimer timer;
+    g_phase = getenv("SGB_FIT_TIMING") ? &timer : nullptr;
     Solver S(c, N, p, f->family, P);
     S.init(hX, f->y, f->offset);
     // eta, mu of the glm fit; Y at :983/:1138 is recomputed inside get_coeff, so only eta is needed here
@@ -412,7 +433,11 @@ void fit_AI_PCG(Context &c, bool quant, const sgb_fit0 *f, const double *hX, con
     DevBuf<double> eta0;
     eta0.ensure(N);
     S.copy(eta0.get(), S.eta_acc.get(), N);
+    c.sync();
+    lap("set-up and uploads");
     S.get_coeff(tau, alpha0, eta0.get());
+    c.sync();
+    lap("get_coeff");
     int iter = 1;
     bool converged;
     if (no_iteration) {   // :1004-1014
@@ -424,6 +449,8 @@ void fit_AI_PCG(Context &c, bool quant, const sgb_fit0 *f, const double *hX, con
         if (!quant) {
             double YPAPY, Trace, AI;
             S.get_AI_score(tau, YPAPY, Trace, AI);
+            c.sync();
+            lap("AI score + trace");
             tau[1] = std::max(0.0, tau0[1] + tau0[1] * tau0[1] * (YPAPY - Trace) / (double)N);   // :1024
         } else {
             double YPAPY[2], Trace[2], AI[4];
@@ -442,7 +469,9 @@ void fit_AI_PCG(Context &c, bool quant, const sgb_fit0 *f, const double *hX, con
             S.copy(eta0.get(), S.eta_acc.get(), N);   // eta0 = eta  (:1036)
             for (int itry = 1; itry <= 11; itry++) {
                 S.get_coeff(tau0, alpha0, eta0.get());
+                if (g_phase) { c.sync(); lap("get_coeff"); }
                 if (!quant) S.fit_tau_binary(tau0, tau); else S.fit_tau_quant(tau0, tau);
+                if (g_phase) { c.sync(); lap("AI score + trace"); }
                 if (std::max(tau[0], tau[1]) > tol_inv_2) {
                     if (itry <= 10) {
                         if (quant && P.verbose) print_vec(c, indent, "tau: ", tau, 2, false);
@@ -490,6 +519,13 @@ void fit_AI_PCG(Context &c, bool quant, const sgb_fit0 *f, const double *hX, con
     for (int64_t i = 0; i < N; i++) out->residuals[i] = f->y[i] - out->fitted_values[i];
     for (int i = 0; i < p * p; i++) out->cov[i] = cov.a[i];
     out->converged = converged ? 1 : 0;
+    if (g_phase) {
+        lap("download");
+        std::string line = "fit timing (wall s):";
+        for (auto &kv : timer.t) { char b[96]; snprintf(b, sizeof(b), " %s %.3f;", kv.first.c_str(), kv.second); line += b; }
+        c.printf("%s\n", line.c_str());
+        g_phase = nullptr;
+    }
 }
 
 // saige_calc_var_ratio_binary (:1255-1362) / _quant (:1366-1474)

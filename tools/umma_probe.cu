@@ -309,10 +309,10 @@ __device__ __forceinline__ void umma_commit_2cta(unsigned long long *b) {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-struct Pair2Args { int N, ksteps, iters; const uint8_t *A; const int8_t *B; int *D; long long *cycles; };
+struct Pair2Args { int N, ksteps, iters; const uint8_t *A; const int8_t *B; int *D; long long *cycles; int commit_every; int st_during; };
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) probe_pair_kernel(Pair2Args P) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ unsigned long long bar;
+    __shared__ unsigned long long bar, bar2;
     __shared__ unsigned tmem_base;
     unsigned rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -323,7 +323,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) probe_pair_k
         const int r = i / K, k = i % K;
         smem[elem_off(L_K_SW128, P.ksteps, r, k)] = P.B ? (uint8_t)P.B[(size_t)(NH * rank + r) * K + k] : (uint8_t)1;
     }
-    if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1 << 20); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -351,10 +351,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) probe_pair_k
     if (rank == 0 && tid == 0) {
         const unsigned idesc = make_idesc(256, P.N, 0, 0);
         t0 = clock64();
-        for (int it = 0; it < P.iters; it++)
+        for (int it = 0; it < P.iters; it++) {
             for (int s = 0; s < P.ksteps; s++)
                 umma_i8_ts_2cta(tb, tb + 256 + s * 8, make_desc(smem_u32(smem) + s * 32, 16, 1024, 2), idesc, (it > 0 || s > 0) ? 1u : 0u);
+            if (P.commit_every && (it % P.commit_every) == P.commit_every - 1) {
+                asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                             ::"r"(smem_u32(&bar2)), "h"((unsigned short)3) : "memory");
+            }
+        }
         umma_commit_2cta(&bar);
+    } else if (P.st_during && warp >= 1 && P.cycles) {
+        // the other warps keep writing A-operand-sized blocks into unrelated tensor-memory columns while the MMAs run
+        uint32_t r[8] = {1, 2, 3, 4, 5, 6, 7, 8};
+        for (int it = 0; it < P.iters * 2; it++) {
+            tmem_st8(tb + 384 + ((unsigned)(warp * 32) << 16) + (it & 7) * 8, r);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
     }
     mbar_wait(&bar, 0);
     if (rank == 0 && tid == 0 && P.cycles) P.cycles[blockIdx.x / 2] = clock64() - t0;
@@ -393,7 +405,7 @@ int pair_main() {
         CK(cudaMalloc(&dA, A.size())); CK(cudaMalloc(&dB, B.size())); CK(cudaMalloc(&dD, got.size() * 4));
         CK(cudaMemcpy(dA, A.data(), A.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(dB, B.data(), B.size(), cudaMemcpyHostToDevice));
-        Pair2Args P{N, ksteps, 1, dA, dB, dD, nullptr};
+        Pair2Args P{N, ksteps, 1, dA, dB, dD, nullptr, 0, 0};
         probe_pair_kernel<<<2, 128, 65536>>>(P);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("pair layout N=%d: CUDA error %s\n", N, cudaGetErrorString(e)); return 2; }
@@ -407,8 +419,12 @@ int pair_main() {
     long long *dcyc;
     CK(cudaMalloc(&dcyc, sizeof(long long) * G));
     printf("\ncta_group::2 throughput (%d SMs = %d pairs, M = 256, 4 k-steps per iteration, 2000 iterations):\n", G, G / 2);
+    for (int variant = 0; variant < 3; variant++)
     for (int N : {32, 64, 128, 192, 256}) {
-        Pair2Args P{N, 4, 2000, nullptr, nullptr, nullptr, dcyc};
+        if (variant && N != 192) continue;
+        Pair2Args P{N, 4, 2000, nullptr, nullptr, nullptr, dcyc, variant == 1 ? 1 : 0, variant == 2 ? 1 : 0};
+        if (variant == 1) printf("  (a multicast commit after every 4 MMAs)\n");
+        if (variant == 2) printf("  (three warps keep issuing tcgen05.st + wait::st into other columns)\n");
         cudaEvent_t e0, e1;
         CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
         probe_pair_kernel<<<G, 128, 65536>>>(P);
