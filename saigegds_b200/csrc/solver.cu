@@ -9,6 +9,7 @@
 //   * the Rademacher vectors u_i are identical in every get_trace call because the reference re-seeds
 //     R's RNG each time (:631, :676), so u_i and GRM*u_i (:652) are generated once per fit and cached.
 #include <chrono>
+#include <future>
 #include <map>
 #include <algorithm>
 #include <cmath>
@@ -42,11 +43,15 @@ typedef std::vector<double> hvec;
 
 // wall-clock phase timer of a fit (env SGB_FIT_TIMING: printed once at the end; a debugging aid for host-side overheads)
 struct PhaseTimer {
-    std::map<std::string, double> t;
+    std::map<std::string, std::pair<double, double>> t;   // wall seconds, of which waiting for the GPU
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    const sgb_stats *st = nullptr;
+    double w0 = 0;
     void lap(const char *name) {
         const auto now = std::chrono::steady_clock::now();
-        t[name] += std::chrono::duration<double>(now - t0).count();
+        auto &e = t[name];
+        e.first += std::chrono::duration<double>(now - t0).count();
+        if (st) { e.second += st->host_wait_s - w0; w0 = st->host_wait_s; }
         t0 = now;
     }
 };
@@ -164,6 +169,7 @@ struct Solver {
     DevBuf<int8_t> bits;
     int n_u = 0, cap_u = 0;
     RRng trace_rng;
+    std::future<std::vector<int8_t>> pre_draws;   // the first nrun Rademacher vectors, drawn beside get_coeff (prefetch_draws)
     bool has_offset = false;
     PcgWork pcg;
     hmat cov;
@@ -186,6 +192,7 @@ struct Solver {
 
     void init(const double *hX, const double *hy, const double *hoff) {
         upload(X, hX, (size_t)N * p);
+        lap("set-up: upload X");
         upload(y, hy, N);
         has_offset = hoff != nullptr;
         if (has_offset) upload(offset, hoff, N);
@@ -194,6 +201,18 @@ struct Solver {
         sol.ensure((size_t)N * (1 + p));
         copy(rhs.get() + N, X.get(), (size_t)N * p);
         trace_rng.set_seed((uint32_t)P.seed);
+    }
+
+    // R's RNG is serial (3.8 ns per draw, 50 ms for 30 vectors of 430K): take the first nrun vectors on a host thread while the
+    // GPU runs the first get_coeff.  Same stream of draws as drawing them in ensure_u (trace_rng is not touched until the join).
+    void prefetch_draws() {
+        if (c.rademacher_fn || n_u != 0 || pre_draws.valid()) return;
+        const size_t cnt = (size_t)N * P.nrun;
+        pre_draws = std::async(std::launch::async, [this, cnt] {
+            std::vector<int8_t> h(cnt);
+            for (size_t i = 0; i < cnt; i++) h[i] = (int8_t)trace_rng.bernoulli_half();
+            return h;
+        });
     }
 
     // t(A) %*% v for the p columns of A (ld N)
@@ -219,7 +238,9 @@ struct Solver {
     // get_coeff_w, :739-758
     void get_coeff_w(const double tau[2]) {
         copy(rhs.get(), Y.get(), N);
+        lap("other");
         pcg_solve(c, pcg, W.get(), tau[0], tau[1], rhs.get(), 1 + p, P.maxiterPCG, P.tolPCG, sol.get(), nullptr);
+        lap("get_coeff_w: PCG of the 1+p columns");
         std::vector<const double *> a, b;
         for (int j = 0; j < p; j++) for (int i = 0; i < p; i++) { a.push_back(X.get() + (size_t)i * N); b.push_back(SiX() + (size_t)j * N); }
         for (int i = 0; i < p; i++) { a.push_back(SiX() + (size_t)i * N); b.push_back(Y.get()); }
@@ -267,9 +288,19 @@ struct Solver {
         }
         const int cnt = upto - n_u;
         lap("other");
-        std::vector<int8_t> h((size_t)N * cnt);
-        if (c.rademacher_fn) c.rademacher_fn(c.cb_user, n_u == 0 ? 1 : 0, P.seed, (int64_t)N * cnt, h.data());
-        else for (size_t i = 0; i < h.size(); i++) h[i] = (int8_t)trace_rng.bernoulli_half();
+        std::vector<int8_t> h;
+        if (pre_draws.valid()) {
+            h = pre_draws.get();
+            if (n_u != 0 || h.size() != (size_t)N * cnt) {   // not the request the prefetch was made for: redo it in order
+                trace_rng.set_seed((uint32_t)P.seed);
+                h.clear();
+            }
+        }
+        if (h.empty()) {
+            h.resize((size_t)N * cnt);
+            if (c.rademacher_fn) c.rademacher_fn(c.cb_user, n_u == 0 ? 1 : 0, P.seed, (int64_t)N * cnt, h.data());
+            else for (size_t i = 0; i < h.size(); i++) h[i] = (int8_t)trace_rng.bernoulli_half();
+        }
         lap("rademacher draws on the host (R's RNG)");
         bits.ensure(h.size());
         c.h2d(bits.get(), h.data(), h.size());
@@ -291,7 +322,9 @@ struct Solver {
             ensure_u(nrunEnd);
             SiU.ensure((size_t)N * K); PU.ensure((size_t)N * K);
             const double *u = U.get() + (size_t)N * nrunStart, *au = AU.get() + (size_t)N * nrunStart;
+            lap("other");
             pcg_solve(c, pcg, W.get(), tau[0], tau[1], u, K, P.maxiterPCG, P.tolPCG, SiU.get(), nullptr);
+            lap("trace: PCG of the nrun columns");
             std::vector<const double *> a, b;
             for (int i = 0; i < K; i++) for (int j = 0; j < p; j++) { a.push_back(SiX() + (size_t)j * N); b.push_back(u + (size_t)i * N); }
             hvec d(a.size());
@@ -416,9 +449,13 @@ void fit_AI_PCG(Context &c, bool quant, const sgb_fit0 *f, const double *hX, con
     const int p = f->p;
     const double tol = P.tol, tol_inv_2 = 1 / (tol * tol);
     PhaseTimer timer;
+    timer.st = &c.stats;
+    timer.w0 = c.stats.host_wait_s;
     g_phase = getenv("SGB_FIT_TIMING") ? &timer : nullptr;
     Solver S(c, N, p, f->family, P);
+    lap("set-up: construct");
     S.init(hX, f->y, f->offset);
+    lap("set-up: init (uploads of X, y; workspaces)");
     // eta, mu of the glm fit; Y at :983/:1138 is recomputed inside get_coeff, so only eta is needed here
     c.h2d(S.eta_acc.get(), f->linear_predictors, sizeof(double) * N);
     c.h2d(S.mu_acc.get(), f->fitted_values, sizeof(double) * N);
@@ -435,6 +472,7 @@ void fit_AI_PCG(Context &c, bool quant, const sgb_fit0 *f, const double *hX, con
     S.copy(eta0.get(), S.eta_acc.get(), N);
     c.sync();
     lap("set-up and uploads");
+    if (!no_iteration) S.prefetch_draws();
     S.get_coeff(tau, alpha0, eta0.get());
     c.sync();
     lap("get_coeff");
@@ -521,8 +559,12 @@ void fit_AI_PCG(Context &c, bool quant, const sgb_fit0 *f, const double *hX, con
     out->converged = converged ? 1 : 0;
     if (g_phase) {
         lap("download");
-        std::string line = "fit timing (wall s):";
-        for (auto &kv : timer.t) { char b[96]; snprintf(b, sizeof(b), " %s %.3f;", kv.first.c_str(), kv.second); line += b; }
+        std::string line = "fit timing (wall s, of which waiting for the GPU):";
+        for (auto &kv : timer.t) {
+            char b[128];
+            snprintf(b, sizeof(b), " %s %.3f (%.3f);", kv.first.c_str(), kv.second.first, kv.second.second);
+            line += b;
+        }
         c.printf("%s\n", line.c_str());
         g_phase = nullptr;
     }

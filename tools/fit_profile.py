@@ -24,6 +24,7 @@ def run():
     else:
         g = ctx.saige_fit_AI_PCG_quant(fit0, X, rsetup.initial_tau_quant(fit0), param)
     return time.perf_counter() - t0, g
+t_first, g = run()
 t_plain, g = run()
 ctx.set_profiling(True)
 t_prof, _ = run()
@@ -31,5 +32,5 @@ kt = ctx.kernel_times()
 ctx.set_profiling(False)
 tot = sum(v[0] for v in kt.values())
 rows = sorted(kt.items(), key=lambda kv: -kv[1][0])
-print(json.dumps({"n": n, "m": m, "trait": trait, "fit_s": t_plain, "fit_profiled_s": t_prof, "kernel_ms_total": tot, "tau": list(map(float, g["tau"])),
+print(json.dumps({"n": n, "m": m, "trait": trait, "first_fit_s": t_first, "fit_s": t_plain, "fit_profiled_s": t_prof, "kernel_ms_total": tot, "tau": list(map(float, g["tau"])),
                   "kernels": {k: {"ms": round(v[0], 2), "launches": v[1]} for k, v in rows}}, indent=1))
