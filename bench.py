@@ -803,23 +803,44 @@ def run_assoc(args):
     kt = ctx.kernel_times()
     ctx.set_profiling(False)
     ms = float(np.mean(times))
-    # the kernel that bounds the scan reads n (2K + 2) doubles of model values per variant from shared memory
-    smem_bytes = float(n) * (2 * ASSOC_K + 2) * 8 * m
-    smem_peak = 148 * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9          # GB/s: 128 B/clk/SM
-    tiled_ms = kt.get("score_tiled_kernel", (ms, 1))[0]
+    # dense part of the scan: three integer GEMMs (bit planes of the codes x digit planes of the 2K + 3 model columns) on tcgen05
+    ncols = 2 * ASSOC_K + 3
+    gemm_key = next((k for k in kt if k.startswith("umma_pair_kernel")), None)
+    shares = {k: v[0] / max(1e-9, sum(x[0] for x in kt.values())) for k, v in kt.items()}
+    if gemm_key is not None:
+        gemm_ms = kt[gemm_key][0] / max(1, kt[gemm_key][1])
+        macs = 3.0 * float(n) * m * 6 * ncols
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        peak_tops = max(2.0 * float(pk.get("bf16_tflops", 1590.0)), 4179.0)
+        ach = 2.0 * macs / (gemm_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "umma_pair_kernel (class sums: low / high / low & high bit planes of the 2-bit codes x "
+                                             "6 digit planes of %d model columns)" % ncols,
+                "achieved": ach, "peak": peak_tops, "unit": "TOP/s", "frac": ach / peak_tops, "traffic": None,
+                "peak_source": "int8 tcgen05 rate measured with tools/umma_probe.cu on this pool's B200 (4,179 TOP/s), or 2 x bf16 of "
+                               "MEASURED_PEAKS.json if larger",
+                "note": "algorithmic MACs = 3 planes x n x variants x 6 digits x (2K + 3) columns; a pair MMA costs ~96 clk whatever "
+                        "N <= 192, so %d digit columns of 192 leave the pipe under-used by construction. The scan as a whole is bound by "
+                        "score_test_kernel (saddle-point candidates, FP64 transcendentals): see `shares`" % (6 * ncols)}
+    else:
+        # CUDA-core tiled kernel: reads n (2K + 2) doubles of model values per variant from shared memory
+        smem_bytes = float(n) * (2 * ASSOC_K + 2) * 8 * m
+        smem_peak = 148 * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9          # GB/s: 128 B/clk/SM
+        tiled_ms = kt.get("score_tiled_kernel", (ms, 1))[0]
+        roof = {"bound": "shared-memory", "kernel": "score_tiled_kernel", "achieved": smem_bytes / (tiled_ms * 1e-3) / 1e9,
+                "peak": smem_peak, "unit": "GB/s", "frac": smem_bytes / (tiled_ms * 1e-3) / 1e9 / smem_peak, "traffic": None,
+                "peak_source": "148 SMs x 128 B/clk x SM clock under load",
+                "note": "algorithmic shared-memory bytes = n (2K+2) 8 B per variant; the packed genotypes (n/4 B per variant from "
+                        "HBM) are 0.1 % of that"}
+    roof["kernels"] = {k: {"ms": v[0], "launches": v[1]} for k, v in kt.items()}
+    roof["shares"] = shares
     line = {"metric": "association_variants_per_s", "value": m / (ms * 1e-3), "unit": "variants/s", "n_gpus": 1,
             "steps": len(times), "warmup": max(1, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": m / e2e_s, "unit": "variants/s", "h2d_bytes_per_step": int(host.nbytes),
                     "d2h_bytes_per_step": int(m * 8 * 8 + m * 4),
-                    "note": "ScoreTest.test on packed host batches (sgb_score_test_packed): copy in, both kernels, copy out"},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "shared-memory", "kernel": "score_tiled_kernel", "achieved": smem_bytes / (tiled_ms * 1e-3) / 1e9,
-                         "peak": smem_peak, "unit": "GB/s", "frac": smem_bytes / (tiled_ms * 1e-3) / 1e9 / smem_peak,
-                         "traffic": None, "peak_source": "148 SMs x 128 B/clk x SM clock under load",
-                         "note": "algorithmic shared-memory bytes = n (2K+2) 8 B per variant; the packed genotypes "
-                                 "(n/4 B per variant from HBM) are 0.1 % of that",
-                         "kernels": {k: {"ms": v[0], "launches": v[1]} for k, v in kt.items()}},
+                    "note": "ScoreTest.test on packed host batches (sgb_score_test_packed): copy in, all kernels, copy out"},
+            "gpu_launches": int(launches), "score_path": os.environ.get("SGB_SCORE_PATH", "tensor"),
+            "roofline": roof,
             "spa_adjusted": int(np.sum(res["pval"][res["valid"]] != res["p.norm"][res["valid"]])),
             "valid": int(res["valid"].sum())}
     if not args.no_cpu:

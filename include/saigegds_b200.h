@@ -247,11 +247,14 @@ int sgb_score_test_init(sgb_context *ctx, const sgb_score_model *model, double m
  *            *kernel_ms (may be NULL) receives the CUDA-event time of the kernel. */
 int sgb_score_test_packed(sgb_context *ctx, const uint8_t *packed, int64_t n_bytes_per_variant, int64_t n_variant,
                           double *out, int32_t *valid);
-/* Kernel choice (after sgb_score_test_init): SGB_SCORE_TILED (default) computes the score statistics of all variants
- * with the shared-memory-tiled kernel and sends only the saddle-point candidates through the per-variant kernel;
- * SGB_SCORE_PER_VARIANT runs every variant through the latter.  Same results to rounding. */
+/* Kernel choice (after sgb_score_test_init).  SGB_SCORE_TENSOR (default for 2-bit packed genotypes): the score statistics of a
+ * block of variants are three integer GEMMs on the tcgen05 tensor cores (class sums of the model columns, exact fixed point) and a
+ * per-variant finishing kernel; SGB_SCORE_TILED: the shared-memory-tiled CUDA-core kernel (always used for dosages);
+ * either way only the saddle-point candidates go through the per-variant kernel.  SGB_SCORE_PER_VARIANT runs every variant
+ * through the latter.  Same results to rounding. */
 #define SGB_SCORE_TILED 0
 #define SGB_SCORE_PER_VARIANT 1
+#define SGB_SCORE_TENSOR 2
 int sgb_score_test_set_path(sgb_context *ctx, int path);
 int sgb_score_test_dosage(sgb_context *ctx, const double *dosage, int64_t n_variant, double *out, int32_t *valid);
 int sgb_score_test_stored(sgb_context *ctx, int64_t first, int64_t n_variant, double *out, int32_t *valid,

@@ -71,9 +71,10 @@ class ScoreTest:
                                             C.c_double(mobj["missing"]), C.c_double(mobj["spa_pval"])))
 
     def set_path(self, name: str):
-        """'tiled' (default: shared-memory-tiled kernel for every variant + per-variant kernel for the saddle-point
-        candidates) or 'per_variant' (every variant through the per-variant kernel)."""
-        L.check(L.lib().sgb_score_test_set_path(self.ctx._h, C.c_int({"tiled": 0, "per_variant": 1}[name])))
+        """'tensor' (default for packed genotypes: class sums on the tcgen05 tensor cores + a per-variant finishing kernel),
+        'tiled' (shared-memory-tiled CUDA-core kernel for every variant; always used for dosages) -- either way the saddle-point
+        candidates go through the per-variant kernel -- or 'per_variant' (every variant through the per-variant kernel)."""
+        L.check(L.lib().sgb_score_test_set_path(self.ctx._h, C.c_int({"tiled": 0, "per_variant": 1, "tensor": 2}[name])))
 
     @staticmethod
     def _result(out, valid):

@@ -199,6 +199,12 @@ void imma_prepare(Context &c);
 void imma_release(Context &c);
 bool imma_available(const Context &c);
 void imma_grm_mv(Context &c, const double *b_device, double *out_device, int k);
+// class sums of a packed block against fixed model columns on the tcgen05 pair kernel (the dense part of the score scan)
+constexpr int kClassMaxCols = 32, kClassDigitRows = 192, kClassScal = 8;   // columns per group, rows of a digit matrix, scalars per column
+void umma_class_digits(Context &c, const double *cols_device, int64_t n, int ncols, int64_t cpad, int8_t *digits_device,
+                       double *scal_device, long long *tot_device);
+void umma_class_sums(Context &c, const uint8_t *packed_device, size_t pitch, int64_t rows, int64_t n, const int8_t *digits_device,
+                     int64_t cpad, int ncols, int amode, unsigned long long *out_lo, unsigned long long *out_hi, int *err_device);
 // ---- product dispatch (solver.cu) ----
 void grm_mv_device(Context &c, const double *b_device, double *out_device, int k);
 // ---- score.cu: single-variant score test + SPA (saige_main.cpp:101-407, SPATest.cpp) ----

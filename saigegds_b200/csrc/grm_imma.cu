@@ -1345,6 +1345,52 @@ void umma_grm_mv_pass(Context &c, ImmaPlan *p, const double *b, double *out, int
 
 }  // namespace
 
+// ---- class sums of a packed genotype block against fixed model columns: the dense part of the score scan (score.cu) -----------------
+// The score statistics of a variant are sums of model columns over the samples of each genotype class, so the scan over a block of
+// variants is three integer GEMMs on the pair kernel above -- A = low bit, high bit and (low & high) of the 2-bit codes, B = the digit
+// planes of the model columns, quantised once per model.
+static_assert(kClassMaxCols == kUMaxCols && kClassDigitRows == kUMaxN && kClassScal == kUScal, "ctx.h mirrors grm_umma.cuh");
+void umma_class_digits(Context &c, const double *cols, int64_t n, int ncols, int64_t cpad, int8_t *digits, double *scal, long long *tot) {
+    if (ncols < 1 || ncols > kUMaxCols) throw Error(SGB_ERR_INVALID, "umma_class_digits: 1..32 columns per group");
+    umma_colstats_kernel<<<ncols, 1024, 0, c.stream>>>(cols, n, scal);
+    SGB_CHECK_LAUNCH();
+    SGB_CUDA(cudaMemsetAsync(digits, 0, (size_t)kUMaxN * cpad, c.stream));
+    umma_digits_kernel<<<dim3((unsigned)((cpad + 255) / 256), ncols), 256, 0, c.stream>>>(cols, n, n, cpad, scal, 0, digits);
+    SGB_CHECK_LAUNCH();
+    umma_digit_totals_kernel<<<ncols, 1024, 0, c.stream>>>(cols, n, n, scal, tot);
+    SGB_CHECK_LAUNCH();
+    c.stats.n_kernel_launches += 3;
+}
+
+// out_lo / out_hi [ncols][rows] (zeroed here) += limbs of sum_i A(code(row, i)) * digits(col, i); amode as in UmmaArgs
+void umma_class_sums(Context &c, const uint8_t *packed, size_t pitch, int64_t rows, int64_t n, const int8_t *digits, int64_t cpad, int ncols,
+                     int amode, unsigned long long *out_lo, unsigned long long *out_hi, int *err_dev) {
+    if (pitch % 128 != 0 || (int64_t)pitch * 4 > cpad || ((uintptr_t)packed & 127) != 0)
+        throw Error(SGB_ERR_INVALID, "umma_class_sums: the packed block needs a 128-byte aligned base and pitch");
+    static bool attr_set = false;
+    if (!attr_set) {
+        SGB_CUDA(cudaFuncSetAttribute(umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes));
+        attr_set = true;
+    }
+    const int ng = ((kUND * ncols + 31) / 32) * 32;
+    CUtensorMap tp, td;
+    CUresult r = encode_tmap_2d(&tp, packed, pitch, (uint64_t)rows, pitch, kUBoxBytes, kPRows, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r == CUDA_SUCCESS) r = encode_tmap_2d(&td, digits, (uint64_t)cpad, kUMaxN, (uint64_t)cpad, 128, (uint32_t)(ng / 2), CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r != CUDA_SUCCESS) throw Error(SGB_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    const int boxes = (int)((n + kUBoxElems - 1) / kUBoxElems);
+    const int splits = umma_pick_split((rows + kURows - 1) / kURows, boxes, c.sm_count / 2);
+    UmmaArgs a;
+    a.ncols = ncols; a.ng = ng; a.R = rows; a.boxes_total = boxes; a.boxes_per_split = (boxes + splits - 1) / splits;
+    a.out_lo = out_lo; a.out_hi = out_hi; a.ldo = rows; a.err = err_dev; a.prof = nullptr; a.amode = amode;
+    const int ns = (boxes + a.boxes_per_split - 1) / a.boxes_per_split;
+    SGB_CUDA(cudaMemsetAsync(out_lo, 0, sizeof(unsigned long long) * (size_t)ncols * rows, c.stream));
+    SGB_CUDA(cudaMemsetAsync(out_hi, 0, sizeof(unsigned long long) * (size_t)ncols * rows, c.stream));
+    const unsigned gx2 = ((unsigned)((rows + kPRows - 1) / kPRows) + 1) & ~1u;
+    umma_pair_kernel<<<dim3(gx2, (unsigned)ns), kPThreads, kPSmemBytes, c.stream>>>(tp, td, a);
+    SGB_CHECK_LAUNCH();
+    c.stats.n_kernel_launches++;
+}
+
 bool imma_available(const Context &c) { return c.imma != nullptr; }
 
 void imma_release(Context &c) {

@@ -135,6 +135,8 @@ struct UmmaArgs {
     int64_t ldo;
     int *err;
     long long *prof;           // PROF build only: per CTA 16 cycle counters (tools/umma_prof.py)
+    int amode = 0;             // pair kernel: value of the A operand per 2-bit code -- 0: the code itself (0, 1, 2, 3), the GRM product;
+                               // 1: its low bit, 2: its high bit, 3: low & high (code 3 = missing): the class sums of the score scan (score.cu)
 };
 
 template <bool PROF, bool PAIR>
@@ -410,6 +412,32 @@ __global__ void umma_digits_kernel(const double *__restrict__ v, int64_t n_valid
     const int64_t p = (i & ~(int64_t)15) + 4 * (i & 3) + ((i & 15) >> 2);
 #pragma unroll
     for (int l = 0; l < kUND; l++) D[(size_t)(c * kUND + l) * cpad + p] = d[l];
+}
+
+// exact column totals of the quantised values in limb form (what a GEMM against an all-ones operand would return): tot[c] = {sum of
+// d0 + 256 d1 + 65536 d2, sum of d3 + 256 d4 + 65536 d5} over i < n.  One block of 1024 threads per column, integer arithmetic.
+__global__ void __launch_bounds__(1024) umma_digit_totals_kernel(const double *__restrict__ v, int64_t n, int64_t ldv, const double *__restrict__ scal,
+                                                                 long long *__restrict__ tot) {
+    __shared__ long long sm[2][32];
+    const int c = blockIdx.x;
+    const double unit = scal[(size_t)c * kUScal + 2];
+    const int sh = (int)scal[(size_t)c * kUScal + 3];
+    long long lo = 0, hi = 0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) {
+        int8_t d[kUND];
+        to_digits6(unit > 0 ? v[(size_t)c * ldv + i] : 0.0, sh, d);
+        lo += (long long)d[0] + 256ll * d[1] + 65536ll * d[2];
+        hi += (long long)d[3] + 256ll * d[4] + 65536ll * d[5];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { lo += __shfl_xor_sync(0xffffffffu, lo, o); hi += __shfl_xor_sync(0xffffffffu, hi, o); }
+    if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = lo; sm[1][threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long a = 0, b = 0;
+        for (int w = 0; w < 32; w++) { a += sm[0][w]; b += sm[1][w]; }
+        tot[2 * c] = a; tot[2 * c + 1] = b;
+    }
 }
 
 // after phase A: T' limbs -> dot, e, hm per (variant, column); per-column max|e| and H = sum h (deterministic).  grid (G, K)
@@ -795,7 +823,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, 1) umma_p
             const unsigned c0 = (unsigned)(st & 3) * 2;
             const uint4 wa = *reinterpret_cast<const uint4 *>(src + ((c0 ^ psw) << 4));
             const uint4 wb = *reinterpret_cast<const uint4 *>(src + (((c0 + 1) ^ psw) << 4));
-            const uint32_t ws[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            uint32_t ws[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            if (A.amode != 0) {          // indicator operands: one bit per code, in the low bit of its 2-bit field
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const uint32_t w = ws[i];
+                    ws[i] = (A.amode == 1 ? w : (A.amode == 2 ? (w >> 1) : (w & (w >> 1)))) & 0x55555555u;
+                }
+            }
             uint32_t x[32];
 #pragma unroll
             for (int i = 0; i < 8; i++)
