@@ -5,7 +5,7 @@
 // Three paths for the score statistics of all variants of a block, then one kernel for the saddle-point candidates.
 //  * tensor (default for 2-bit packed genotypes): the statistics are sums of model columns over the samples of each genotype class,
 //    so a block of variants is three integer GEMMs on the tcgen05 pair kernel of the batched GRM product (grm_umma.cuh) -- A = low
-//    bit / high bit / low & high of the 2-bit codes, B = the digit planes of the 2K + 3 model columns (a, w x, y - mu, w, 1),
+//    bit / high bit / low & high of the 2-bit codes, B = the digit planes of the 2K + 4 model columns (a, w x, y - mu, w, mu, 1),
 //    quantised once per model -- followed by score_finish_kernel (one thread per variant: exact class sums -> allele counts,
 //    filters, score_stats).  9,472 variants x 430K samples: 3 x 0.33 ms instead of 32 ms for the tiled kernel.
 //  * score_tiled_kernel (dosages, and SGB_SCORE_TILED): the score statistic of every variant.  A block owns 16 variants (8 warps x 2) and walks the
@@ -33,14 +33,15 @@ struct ScoreState {
     DevBuf<double> out;                  // [n_var][8]
     DevBuf<int32_t> valid;
     DevBuf<uint8_t> geno;                // staged batch (packed bytes or dosages)
-    int grid = 0;
+    int grid = 0, grid_spa = 0;
     // tiled kernel: model values in tile order [tile][row][32 * spl], rows = a(K), w*x(K), y-mu, w, mu
     DevBuf<double> mt;
     int rows = 0, spl = 8;
     int path = SGB_SCORE_TILED;
     // tensor path: digit planes of the model columns in groups of <= 32, per-column scalars and exact totals, class-sum limbs
     bool tensor_ok = false;
-    int ncols = 0;                       // 2K + 3: a (K), w x (K), y - mu, w, 1
+    int ncols = 0;                       // 2K + 4: a (K), w x (K), y - mu, w, mu, 1
+    DevBuf<double> cand;                 // [n_var][kCandCols + K]: what the saddle-point kernel needs of a candidate
     int64_t cpad = 0;                    // contraction length of a digit row = 4 * pitch of a packed block
     DevBuf<int8_t> cdig;                 // [groups][192][cpad]
     DevBuf<double> cscal;                // [ncols][8]
@@ -56,6 +57,8 @@ struct ScoreState {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kSpaThreads = 512;   // saddle-point candidates of the tensor scan: one block per candidate
+constexpr int kCandCols = 8;       // AC, Num, AF, S, var2, coef_xmu, G'mu, (spare), then coef[K]
 
 struct BlockEnv {
     double *red;   // shared, one slot per warp
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(64) score_finish_kernel(score::Model M, int64_
                                                           const unsigned long long *__restrict__ hi, const long long *__restrict__ tot,
                                                           const double *__restrict__ scal, double *__restrict__ out,
                                                           int32_t *__restrict__ valid, int32_t *__restrict__ spa_list,
-                                                          unsigned int *__restrict__ spa_count) {
+                                                          unsigned int *__restrict__ spa_count, double *__restrict__ cand) {
     const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_var) return;
     const int K = M.K;
@@ -367,7 +370,7 @@ __global__ void __launch_bounds__(64) score_finish_kernel(score::Model M, int64_
         S[0] = val(tot[2 * c] - Ll - Hl + Ml, tot[2 * c + 1] - Lh - Hh + Mh);
     };
     double S[4];
-    classes(2 * K + 2, S);                                   // the column of ones: class counts (exact integers)
+    classes(2 * K + 3, S);                                   // the column of ones: class counts (exact integers)
     const double AC = S[1] + 2 * S[2];
     const int Num = (int)(M.n - (int64_t)S[3]);
     double AF, mac;
@@ -402,7 +405,57 @@ __global__ void __launch_bounds__(64) score_finish_kernel(score::Model M, int64_
     o[4] = fabs(beta / score::qnorm_as241(pval_noadj / 2));
     o[5] = pval_noadj; o[6] = pval_noadj; o[7] = fin ? 1.0 : 0.0;
     valid[v] = 1;
-    if (M.trait == 0 && fin && pval_noadj <= M.thr_pval_spa) spa_list[atomicAdd(spa_count, 1u)] = (int32_t)v;
+    if (M.trait == 0 && fin && pval_noadj <= M.thr_pval_spa) {
+        // saddle-point candidate: hand the sums over so that spa_candidate_kernel does not repeat the passes that produced them
+        spa_list[atomicAdd(spa_count, 1u)] = (int32_t)v;
+        double *r = cand + (size_t)v * (kCandCols + K);
+        r[0] = AC; r[1] = (double)Num; r[2] = AF; r[3] = Sc; r[4] = var2; r[5] = coef_xmu; r[6] = gsum(2 * K + 2);
+        for (int c = 0; c < K; c++) r[kCandCols + c] = coef[c];
+    }
+}
+
+// One block per saddle-point candidate of the tensor scan (atomic work counter): the count of its samples with G != 0, then
+// score::spa_adjust with both Newton iterations advanced by the same passes.  Fills beta, SE, pval, converged of the variant's row.
+template <int KMAX>
+__global__ void __launch_bounds__(kSpaThreads) spa_candidate_kernel(score::Model M, PackedSrc src, int64_t n_cand,
+                                                                     const int32_t *__restrict__ list, const double *__restrict__ cand,
+                                                                     double *spa, unsigned long long *__restrict__ counter,
+                                                                     double *__restrict__ out) {
+    __shared__ double red[kSpaThreads / 32];
+    __shared__ int wsum[kSpaThreads / 32];
+    __shared__ unsigned long long next;
+    BlockEnv env{red, wsum};
+    const int K = M.K;
+    double *spa_g = spa + (size_t)blockIdx.x * 2 * (size_t)M.n, *spa_mu = spa_g + M.n;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) next = atomicAdd(counter, 1ULL);
+        __syncthreads();
+        if ((int64_t)next >= n_cand) break;
+        const int64_t v = list[next];
+        const double *r = cand + (size_t)v * (kCandCols + K);
+        const double AC = r[0], AF = r[2], S = r[3], var2 = r[4], coef_xmu = r[5], gmu = r[6];
+        const int Num = (int)r[1];
+        const bool minus = AF > 0.5;
+        double coef[KMAX];
+#pragma unroll
+        for (int c = 0; c < KMAX; c++) coef[c] = (c < K) ? r[kCandCols + c] : 0.0;
+        const score::Coded<score::PackedRow> G{src.row(v), AF * 2, minus};
+        int my_nnz = 0;
+        SGB_SCORE_FOR_SAMPLES(env, M.n, i) my_nnz += (G(i) != 0);
+        double *o = out + v * score::kOutCols;
+        double pval = o[6], beta = 0;
+        bool converged = true;
+        score::spa_adjust<KMAX, true>(env, M, G, coef, my_nnz, AC, Num, minus, S, var2, coef_xmu, gmu, o[6], spa_g, spa_mu, pval, beta,
+                                      converged);
+        if (minus) beta = -beta;
+        if (threadIdx.x == 0) {
+            o[3] = beta;
+            o[4] = fabs(beta / score::qnorm_as241(pval / 2));
+            o[5] = pval;
+            o[7] = converged ? 1.0 : 0.0;
+        }
+    }
 }
 
 // statistics of n_var variants of a packed block (128-byte aligned base and pitch) through the tensor path
@@ -420,9 +473,10 @@ void launch_tensor(Context &c, ScoreState &s, const uint8_t *packed, size_t pitc
     c.prof_begin();
     const unsigned grid = (unsigned)((n_var + 63) / 64);
     const int K = s.M.K;
+    s.cand.ensure((size_t)n_var * (kCandCols + K));
 #define SGB_FINISH(KMAX)                                                                                                              \
     score_finish_kernel<KMAX><<<grid, 64, 0, c.stream>>>(s.M, n_var, s.ncols, s.c_lo.get(), s.c_hi.get(), s.ctot.get(), s.cscal.get(), \
-                                                         s.out.get(), s.valid.get(), s.spa_list.get(), s.spa_count.get())
+                                                         s.out.get(), s.valid.get(), s.spa_list.get(), s.spa_count.get(), s.cand.get())
     if (K <= 4) SGB_FINISH(4);
     else if (K <= 8) SGB_FINISH(8);
     else if (K <= 16) SGB_FINISH(16);
@@ -432,6 +486,24 @@ void launch_tensor(Context &c, ScoreState &s, const uint8_t *packed, size_t pitc
     c.prof_end("score_finish_kernel");
     c.stats.n_kernel_launches++;
     SGB_CUDA(cudaMemcpyAsync(s.h_cerr.p, s.cerr.get(), sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+}
+
+void launch_candidates(Context &c, ScoreState &s, const PackedSrc &src, int64_t n_cand) {
+    const int grid = (int)std::min<int64_t>(n_cand, s.grid_spa);
+    SGB_CUDA(cudaMemsetAsync(s.counter.get(), 0, sizeof(unsigned long long), c.stream));
+    c.prof_begin();
+    const int K = s.M.K;
+#define SGB_SPA_LAUNCH(KMAX)                                                                                                          \
+    spa_candidate_kernel<KMAX><<<grid, kSpaThreads, 0, c.stream>>>(s.M, src, n_cand, s.spa_list.get(), s.cand.get(), s.spa.get(),     \
+                                                                   s.counter.get(), s.out.get())
+    if (K <= 4) SGB_SPA_LAUNCH(4);
+    else if (K <= 8) SGB_SPA_LAUNCH(8);
+    else if (K <= 16) SGB_SPA_LAUNCH(16);
+    else SGB_SPA_LAUNCH(32);
+#undef SGB_SPA_LAUNCH
+    SGB_CHECK_LAUNCH();
+    c.prof_end("spa_candidate_kernel");
+    c.stats.n_kernel_launches++;
 }
 
 template <class Src>
@@ -501,7 +573,8 @@ void launch(Context &c, ScoreState &s, const Tiles &tiles, const Src &src, int64
                                   "sgb_score_test_set_path(ctx, SGB_SCORE_TILED) selects the kernel without such waits");
     }
     const int64_t n_spa = *s.h_count.p;
-    if (n_spa > 0) launch_per_variant(c, s, src, n_spa, s.spa_list.get());
+    if (n_spa > 0 && tensor) launch_candidates(c, s, PackedSrc{tensor_base, tensor_pitch}, n_spa);
+    else if (n_spa > 0) launch_per_variant(c, s, src, n_spa, s.spa_list.get());
 }
 
 void fetch(Context &c, ScoreState &s, int64_t n_var, double *out, int32_t *valid) {
@@ -617,10 +690,10 @@ void score_init(Context &c, const sgb_score_model *m, double maf, double mac, do
     }
     s->spa_count.ensure(1);
     s->h_count.ensure(1);
-    // tensor path: the 2K + 3 model columns [a | w x | y - mu | w | 1], column-major, cut into digit planes once
+    // tensor path: the 2K + 4 model columns [a | w x | y - mu | w | mu | 1], column-major, cut into digit planes once
     try {
         const bool bin = (m->trait == 0);
-        s->ncols = (int)(2 * K + 3);
+        s->ncols = (int)(2 * K + 4);
         const size_t nb = (n + 3) / 4, pitch = ((nb + 255) / 256) * 256;
         s->cpad = (int64_t)pitch * 4;
         const int groups = (s->ncols + kClassMaxCols - 1) / kClassMaxCols;
@@ -633,7 +706,8 @@ void score_init(Context &c, const sgb_score_model *m, double maf, double mac, do
             }
             W[2 * K * n + i] = m->y_mu[i];
             W[(2 * K + 1) * n + i] = w;
-            W[(2 * K + 2) * n + i] = 1.0;
+            W[(2 * K + 2) * n + i] = m->mu[i];
+            W[(2 * K + 3) * n + i] = 1.0;
         }
         DevBuf<double> wdev;
         up(wdev, W.data(), W.size());
@@ -660,6 +734,7 @@ void score_init(Context &c, const sgb_score_model *m, double maf, double mac, do
     const std::string ep = env_path ? env_path : "";
     s->path = ep == "per_variant" ? SGB_SCORE_PER_VARIANT : (ep == "tiled" || !s->tensor_ok) ? SGB_SCORE_TILED : SGB_SCORE_TENSOR;
     s->grid = c.sm_count * 4;
+    s->grid_spa = c.sm_count * 2;   // blocks of spa_candidate_kernel (512 threads), scratch rows [0, grid_spa) of `spa`
     // saddle-point scratch (2 n doubles per block of the candidate kernel): binary traits only -- a quantitative trait never
     // takes the saddle-point branch (saige_main.cpp:322-350)
     if (m->trait == 0) s->spa.ensure((size_t)s->grid * 2 * n);

@@ -264,6 +264,191 @@ SGB_HD double saddle_prob(Env &env, double q, double m1, double var1, double g_p
     return pval;
 }
 
+// ---- the same, both roots at once ------------------------------------------------------------------------------------------------------
+// Saddle_Prob_Fast solves K1(t) = q and K1(t) = qinv by two independent Newton iterations; each step is a pass over the (g, mu) pairs.
+// The sums of a pass depend on t only, so one pass serves the current step of both iterations (and the first pass, at t = 0, is the
+// same for both): the pairs are read half as often.  Every root follows exactly the sequence of getroot_K1_fast.
+struct RootIter {
+    double q, t, root, K1_eval, k2, prevJump, tnew, t_eval;
+    int it, phase;          // phase 0: wants the sums at t = 0; 1: at the Newton step tnew; 2: at the halved jump; 3: finished
+    bool converged;
+    SGB_HD void start(double q_, double g_pos, double g_neg) {
+        q = q_; t = root = 0; K1_eval = k2 = tnew = t_eval = 0; prevJump = INFINITY; it = 0; converged = false; phase = 0;
+        if (q >= g_pos || q <= g_neg) { root = INFINITY; converged = true; phase = 3; }
+    }
+    SGB_HD bool active() const { return phase != 3; }
+    // top of an iteration of the loop at SPATest.cpp:143
+    SGB_HD void advance(double NAsigma) {
+        const double root_tol = 1.220703125e-4;
+        if (++it > 1000) { phase = 3; return; }
+        const double K2_eval = k2 + NAsigma;
+        tnew = t - K1_eval / K2_eval;
+        if (!isfinite(tnew)) { phase = 3; return; }
+        if (fabs(tnew - t) < root_tol) { converged = true; phase = 3; return; }
+        phase = 1;
+        t_eval = tnew;
+    }
+    // s1, s2: the raw sums of K1_K2 at t_eval
+    SGB_HD void consume(double s1, double s2, double NAmu, double NAsigma) {
+        const double root_tol = 1.220703125e-4;
+        const double k1 = s1 - q;
+        if (phase == 0) {
+            K1_eval = k1 + NAmu + NAsigma * t;
+            k2 = s2;
+            advance(NAsigma);
+            return;
+        }
+        const double newK1 = k1 + NAmu + NAsigma * tnew;
+        k2 = s2;
+        if (phase == 1) {
+            if (sign(K1_eval) != sign(newK1)) {
+                if (fabs(tnew - t) > prevJump - root_tol) {
+                    tnew = t + sign(newK1 - K1_eval) * prevJump * 0.5;
+                    phase = 2;
+                    t_eval = tnew;
+                    return;
+                }
+                prevJump = fabs(tnew - t);
+            }
+        } else {
+            prevJump *= 0.5;
+        }
+        root = t = tnew;
+        K1_eval = newK1;
+        advance(NAsigma);
+    }
+};
+
+template <class Env>
+SGB_HD void K1_K2_dual(Env &env, double ta, bool on_a, double tb, bool on_b, int64_t nnz, const double *g, const double *mu,
+                       double &s1a, double &s2a, double &s1b, double &s2b) {
+    double a1 = 0, a2 = 0, b1 = 0, b2 = 0;
+    if (on_a && on_b && ta == tb) {          // the first pass (t = 0): one evaluation serves both
+#pragma unroll 4
+        for (int64_t k = env.tid(); k < nnz; k += env.nthr()) {
+            const double m = mu[k], om = 1 - m, gi = g[k], e = exp(-gi * ta);
+            const double inv = 1 / (om * e + m), mg = m * gi * inv;
+            a1 += mg;
+            const double v = om * e * gi * inv * mg;
+            if (isfinite(v)) a2 += v;
+        }
+        s1a = s1b = env.sum(a1);
+        s2a = s2b = env.sum(a2);
+        return;
+    }
+#pragma unroll 4
+    for (int64_t k = env.tid(); k < nnz; k += env.nthr()) {
+        const double m = mu[k], om = 1 - m, gi = g[k];
+        if (on_a) {
+            const double e = exp(-gi * ta), inv = 1 / (om * e + m), mg = m * gi * inv;
+            a1 += mg;
+            const double v = om * e * gi * inv * mg;
+            if (isfinite(v)) a2 += v;
+        }
+        if (on_b) {
+            const double e = exp(-gi * tb), inv = 1 / (om * e + m), mg = m * gi * inv;
+            b1 += mg;
+            const double v = om * e * gi * inv * mg;
+            if (isfinite(v)) b2 += v;
+        }
+    }
+    if (on_a) { s1a = env.sum(a1); s2a = env.sum(a2); }
+    if (on_b) { s1b = env.sum(b1); s2b = env.sum(b2); }
+}
+
+// Korg and K2 of get_saddle_prob_fast at both roots from one pass
+template <class Env>
+SGB_HD void saddle_sums_dual(Env &env, double ta, bool on_a, double tb, bool on_b, int64_t nnz, const double *g, const double *mu,
+                             double &Ka, double &k2a, double &Kb, double &k2b) {
+    double a0 = 0, a2 = 0, b0 = 0, b2 = 0;
+#pragma unroll 2
+    for (int64_t k = env.tid(); k < nnz; k += env.nthr()) {
+        const double m = mu[k], om = 1 - m, gi = g[k];
+        if (on_a) {
+            a0 += log(1 - m + m * exp(gi * ta));
+            const double e = exp(-gi * ta);
+            const double v = (om * m * gi * gi * e) / sq(om * e + m);
+            if (isfinite(v)) a2 += v;
+        }
+        if (on_b) {
+            b0 += log(1 - m + m * exp(gi * tb));
+            const double e = exp(-gi * tb);
+            const double v = (om * m * gi * gi * e) / sq(om * e + m);
+            if (isfinite(v)) b2 += v;
+        }
+    }
+    if (on_a) { Ka = env.sum(a0); k2a = env.sum(a2); }
+    if (on_b) { Kb = env.sum(b0); k2b = env.sum(b2); }
+}
+
+SGB_HD double saddle_pval_from_sums(double t, double Korg_t, double K2_t, double q, double NAmu, double NAsigma) {
+    if (!isfinite(t)) return 0;
+    const double K = Korg_t + NAmu * t + 0.5 * NAsigma * t * t;
+    const double k2 = K2_t + NAsigma;
+    double pval = 0;
+    if (isfinite(K) && isfinite(k2)) {
+        const double w = sign(t) * sqrt(2 * (t * q - K));
+        const double v = t * sqrt(k2);
+        const double z = w + log(v / w) / w;
+        pval = (z > 0) ? pnorm_upper(z) : -pnorm_lower(z);
+    }
+    return pval;
+}
+
+// saddle_prob with the two roots advanced together.  The roots do not depend on the cutoff, so the cutoff-doubling loop of
+// SPATest.cpp:298-374 is replayed on the values computed once.  Same result as saddle_prob (bit-identical for a one-thread Env).
+template <class Env>
+SGB_HD double saddle_prob_dual(Env &env, double q, double m1, double var1, double g_pos, double g_neg, int64_t nnz, const double *g,
+                               const double *mu, double NAmu, double NAsigma, double cutoff, bool &converged, double &p_noadj) {
+    const double sdiff = q - m1, qinv = -sdiff + m1;
+    p_noadj = pchisq1_upper(sdiff * sdiff / var1);
+    bool have = false, conv = false;
+    double pval_roots = 0;
+    double pval;
+    while (true) {
+        converged = true;
+        if (cutoff < 0.1) cutoff = 0.1;
+        if (fabs(q - m1) / sqrt(var1) < cutoff) {
+            pval = p_noadj;
+        } else {
+            if (!have) {
+                RootIter A, B;
+                A.start(q, g_pos, g_neg);
+                B.start(qinv, g_pos, g_neg);
+                while (A.active() || B.active()) {
+                    double s1a = 0, s2a = 0, s1b = 0, s2b = 0;
+                    const bool on_a = A.active(), on_b = B.active();
+                    K1_K2_dual(env, A.t_eval, on_a, B.t_eval, on_b, nnz, g, mu, s1a, s2a, s1b, s2b);
+                    if (on_a) A.consume(s1a, s2a, NAmu, NAsigma);
+                    if (on_b) B.consume(s1b, s2b, NAmu, NAsigma);
+                }
+                conv = A.converged && B.converged;
+                if (conv) {
+                    const bool fa = isfinite(A.root), fb = isfinite(B.root);
+                    double Ka = 0, k2a = 0, Kb = 0, k2b = 0;
+                    if (fa || fb) saddle_sums_dual(env, A.root, fa, B.root, fb, nnz, g, mu, Ka, k2a, Kb, k2b);
+                    const double p1 = saddle_pval_from_sums(A.root, Ka, k2a, q, NAmu, NAsigma);
+                    const double p2 = saddle_pval_from_sums(B.root, Kb, k2b, qinv, NAmu, NAsigma);
+                    pval_roots = fabs(p1) + fabs(p2);
+                }
+                have = true;
+            }
+            if (conv) {
+                pval = pval_roots;
+            } else {
+                pval = p_noadj;
+                converged = false;
+                break;
+            }
+        }
+        if (pval != 0 && p_noadj / pval > 1000)
+            cutoff *= 2;
+        else
+            break;
+    }
+    return pval;
+}
+
 // Filters of saige_main.cpp:197-205 / :297-305 from the allele count AC over Num called samples.
 SGB_HD bool variant_passes(const Model &M, double AC, int Num, double &AF, double &mac) {
     AF = (Num > 0) ? (AC / (2 * Num)) : nan_value();
@@ -312,9 +497,66 @@ SGB_HD void score_stats(const Model &M, const double (&coef)[KMAX], const double
     }
 }
 
+// The saddle-point step of one variant whose normal-approximation p-value calls for it (saige_main.cpp:353-394): G = the coded
+// genotypes, coef = (X'VX)^-1 X'V G, my_nnz = this thread's number of samples with G != 0 under SGB_SCORE_FOR_SAMPLES, the rest
+// as score_stats returned them.  DUAL: saddle_prob_dual.  Replaces pval, beta, converged.
+template <int KMAX, bool DUAL, class Env, class CodedGeno>
+SGB_HD void spa_adjust(Env &env, const Model &M, const CodedGeno &G, const double (&coef)[KMAX], int my_nnz, double AC, int Num, bool minus,
+                       double S, double var2, double coef_xmu, double gmu, double pval_noadj, double *spa_g, double *spa_mu, double &pval,
+                       double &beta, bool &converged) {
+    const int64_t n = M.n;
+    const int K = M.K;
+    const double AC2 = minus ? (2 * Num - AC) : AC;
+    const double sc = 1 / sqrt(AC2);
+    // adjusted genotype g = (G - B) / sqrt(AC2):  q - m1 = sum (y-mu) g,  m1 = sum mu g,  var2 = sum mu(1-mu) g^2
+    const double m1 = (gmu - coef_xmu) * sc;
+    const double svar2 = var2 * sc * sc, svar1 = svar2 * M.varRatio;
+    const double Tstat = S * sc;
+    const double q = Tstat / sqrt(svar1) * sqrt(svar2) + m1;      // "qtilde"
+    // one pass over all samples: one-sided sums, and the (g, mu) pairs of the samples with G != 0, compacted in
+    // thread order (offset = exclusive scan of the per-thread counts of pass 1)
+    int64_t nnz = 0;
+    int64_t at = env.excl_scan(my_nnz, nnz);
+    double g_pos = 0, g_neg = 0, sub_mu = 0, sub_sigma = 0;
+    SGB_SCORE_FOR_SAMPLES(env, n, i) {
+        const double v = G(i);
+        const double *x = M.t_X + (size_t)i * K;
+        double B = 0;
+#pragma unroll
+        for (int c = 0; c < KMAX; c++)
+            if (c < K) B += coef[c] * x[c];
+        const double g = (v - B) * sc;
+        if (g > 0) g_pos += g; else g_neg += g;
+        if (v != 0) {
+            const double m = M.mu[i];
+            spa_g[at] = g;
+            spa_mu[at] = m;
+            at++;
+            sub_mu += g * m;
+            sub_sigma += g * g * m * (1 - m);
+        }
+    }
+    g_pos = env.sum(g_pos);
+    g_neg = env.sum(g_neg);
+    const double NAmu = m1 - env.sum(sub_mu);
+    const double NAsigma = svar2 - env.sum(sub_sigma);
+    env.sync();   // the compacted pairs are read by other threads from here on
+
+    // Saddle_Prob_Fast with (q, m1, var1) = (qtilde, m1, svar2) and cutoff 2 (saige_main.cpp:386-388)
+    double p_na;
+    pval = DUAL ? saddle_prob_dual(env, q, m1, svar2, g_pos, g_neg, nnz, spa_g, spa_mu, NAmu, NAsigma, 2.0, converged, p_na)
+                : saddle_prob(env, q, m1, svar2, g_pos, g_neg, nnz, spa_g, spa_mu, NAmu, NAsigma, 2.0, converged, p_na);
+    if (pval == 0 && pval_noadj > 0) {
+        pval = pval_noadj;
+        converged = false;
+    }
+    beta = (Tstat / svar1) / sqrt(AC2);
+    env.sync();   // scratch is reused by the block's next variant
+}
+
 // One variant.  KMAX >= M.K bounds the per-thread coefficient registers.  spa_g / spa_mu: scratch of n doubles each, owned
 // by this block.  out: kOutCols doubles; returns (to every thread) whether the variant passed the filters.
-template <int KMAX, class Env, class Geno>
+template <int KMAX, class Env, class Geno, bool DUAL = false>
 SGB_HD bool test_variant(Env &env, const Model &M, const Geno &geno, double *spa_g, double *spa_mu, double *out) {
     const int64_t n = M.n;
     const int K = M.K;
@@ -370,53 +612,9 @@ SGB_HD bool test_variant(Env &env, const Model &M, const Geno &geno, double *spa
     // ---- saddle-point approximation, saige_main.cpp:353-394 + Saddle_Prob_Fast
     double pval = pval_noadj;
     bool converged = isfinite(pval_noadj);
-    if (bin && converged && (pval_noadj <= M.thr_pval_spa)) {
-        const double AC2 = minus ? (2 * Num - AC) : AC;
-        const double sc = 1 / sqrt(AC2);
-        // adjusted genotype g = (G - B) / sqrt(AC2):  q - m1 = sum (y-mu) g,  m1 = sum mu g,  var2 = sum mu(1-mu) g^2
-        const double m1 = (gmu - coef_xmu) * sc;
-        const double svar2 = var2 * sc * sc, svar1 = svar2 * M.varRatio;
-        const double Tstat = S * sc;
-        const double q = Tstat / sqrt(svar1) * sqrt(svar2) + m1;      // "qtilde"
-        // one pass over all samples: one-sided sums, and the (g, mu) pairs of the samples with G != 0, compacted in
-        // thread order (offset = exclusive scan of the per-thread counts of pass 1)
-        int64_t nnz = 0;
-        int64_t at = env.excl_scan(my_nnz, nnz);
-        double g_pos = 0, g_neg = 0, sub_mu = 0, sub_sigma = 0;
-        SGB_SCORE_FOR_SAMPLES(env, n, i) {
-            const double v = G(i);
-            const double *x = M.t_X + (size_t)i * K;
-            double B = 0;
-#pragma unroll
-            for (int c = 0; c < KMAX; c++)
-                if (c < K) B += coef[c] * x[c];
-            const double g = (v - B) * sc;
-            if (g > 0) g_pos += g; else g_neg += g;
-            if (v != 0) {
-                const double m = M.mu[i];
-                spa_g[at] = g;
-                spa_mu[at] = m;
-                at++;
-                sub_mu += g * m;
-                sub_sigma += g * g * m * (1 - m);
-            }
-        }
-        g_pos = env.sum(g_pos);
-        g_neg = env.sum(g_neg);
-        const double NAmu = m1 - env.sum(sub_mu);
-        const double NAsigma = svar2 - env.sum(sub_sigma);
-        env.sync();   // the compacted pairs are read by other threads from here on
-
-        // Saddle_Prob_Fast with (q, m1, var1) = (qtilde, m1, svar2) and cutoff 2 (saige_main.cpp:386-388)
-        double p_na;
-        pval = saddle_prob(env, q, m1, svar2, g_pos, g_neg, nnz, spa_g, spa_mu, NAmu, NAsigma, 2.0, converged, p_na);
-        if (pval == 0 && pval_noadj > 0) {
-            pval = pval_noadj;
-            converged = false;
-        }
-        beta = (Tstat / svar1) / sqrt(AC2);
-        env.sync();   // scratch is reused by the block's next variant
-    }
+    if (bin && converged && (pval_noadj <= M.thr_pval_spa))
+        spa_adjust<KMAX, DUAL>(env, M, G, coef, my_nnz, AC, Num, minus, S, var2, coef_xmu, gmu, pval_noadj, spa_g, spa_mu, pval, beta,
+                               converged);
     if (minus) beta = -beta;
     if (env.tid() == 0) {
         out[0] = AF; out[1] = mac; out[2] = (double)Num; out[3] = beta;

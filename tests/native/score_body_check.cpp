@@ -16,7 +16,10 @@ struct HostEnv {
     double sum(double v) { return v; }
     int64_t excl_scan(int v, int64_t &total) { total = v; return 0; }
 };
+int g_dual = 0;   // 1: saddle_prob_dual (both Newton iterations advanced by the same passes) instead of saddle_prob
 }  // namespace
+
+extern "C" void score_body_set_dual(int on) { g_dual = on; }
 
 extern "C" int score_body_check(int trait, long n, int K, double tau0, const double *mu, const double *y_mu, const double *mu2,
                                 const double *t_XVX_inv_XV, const double *XVX, const double *t_X, const double *S_a,
@@ -33,8 +36,12 @@ extern "C" int score_body_check(int trait, long n, int K, double tau0, const dou
     HostEnv env;
     for (long v = 0; v < n_var; v++) {
         bool ok;
-        if (packed)
+        if (packed && g_dual)
+            ok = test_variant<32, HostEnv, PackedRow, true>(env, M, PackedRow{packed + (size_t)v * nb}, spa.data(), spa.data() + n, out + v * kOutCols);
+        else if (packed)
             ok = test_variant<32>(env, M, PackedRow{packed + (size_t)v * nb}, spa.data(), spa.data() + n, out + v * kOutCols);
+        else if (g_dual)
+            ok = test_variant<32, HostEnv, DosageRow, true>(env, M, DosageRow{dosage + (size_t)v * n}, spa.data(), spa.data() + n, out + v * kOutCols);
         else
             ok = test_variant<32>(env, M, DosageRow{dosage + (size_t)v * n}, spa.data(), spa.data() + n, out + v * kOutCols);
         valid[v] = ok ? 1 : 0;

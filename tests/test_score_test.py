@@ -101,6 +101,7 @@ def body(tmp_path_factory):
         r = {k: out[:, i].copy() for i, k in enumerate(NAMES)}
         r["valid"] = valid.astype(bool)
         return r
+    run.set_dual = lambda on: lib.score_body_set_dual(C.c_int(int(on)))
     return run
 
 
@@ -123,6 +124,23 @@ def test_device_body_reproduces_golden_pvalues(body, fx, trait, source):
         # rows the saddle-point step really moved (inside the cutoff it returns the normal p-value again, :311-313)
         moved = np.abs(pv["pval"] - pv["p_norm"]) > 1e-9 * pv["p_norm"]
         assert np.array_equal(np.abs(r["pval"][ids] - r["p.norm"][ids]) > 1e-9 * r["p.norm"][ids], moved) and moved.sum() > 300
+
+
+def test_both_roots_in_one_pass_equals_two_newton_iterations_bit_for_bit(body, fx):
+    """saddle_prob_dual (the candidate kernel of the tensor scan: one pass over the (g, mu) pairs serves the current Newton step of
+    both roots) against saddle_prob (SPATest.cpp's order) on one host thread: every root takes the same sequence of steps, so all
+    10,000 golden rows -- 434 of them saddle-point adjusted -- and a low-threshold run with many more candidates agree bit for bit."""
+    for kw in (dict(mac=4.0), dict(mac=2.0, spa_pval=0.5, missing=0.3)):
+        body.set_dual(False)
+        a = body(oracle_model(fx, "binary")[0], oracle_model(fx, "binary")[1], fx.packed_all[:4000], **kw)
+        body.set_dual(True)
+        try:
+            b = body(oracle_model(fx, "binary")[0], oracle_model(fx, "binary")[1], fx.packed_all[:4000], **kw)
+        finally:
+            body.set_dual(False)
+        assert np.array_equal(a["valid"], b["valid"])
+        assert all(np.array_equal(a[k], b[k], equal_nan=True) for k in NAMES)
+        assert np.sum(a["pval"][a["valid"]] != a["p.norm"][a["valid"]]) > 100
 
 
 @pytest.mark.parametrize("trait", ["binary", "quantitative"])
