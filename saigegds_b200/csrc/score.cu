@@ -42,6 +42,8 @@ struct ScoreState {
     bool tensor_ok = false;
     int ncols = 0;                       // 2K + 4: a (K), w x (K), y - mu, w, mu, 1
     DevBuf<double> cand;                 // [n_var][kCandCols + K]: what the saddle-point kernel needs of a candidate
+    DevBuf<double> xt, mup;              // column-major covariates [K][ldx] and mu [ldx], zero-padded to ldx = 4 ceil(n / 4)
+    int64_t ldx = 0;
     int64_t cpad = 0;                    // contraction length of a digit row = 4 * pitch of a packed block
     DevBuf<int8_t> cdig;                 // [groups][192][cpad]
     DevBuf<double> cscal;                // [ncols][8]
@@ -414,19 +416,25 @@ __global__ void __launch_bounds__(64) score_finish_kernel(score::Model M, int64_
     }
 }
 
-// One block per saddle-point candidate of the tensor scan (atomic work counter): the count of its samples with G != 0, then
-// score::spa_adjust with both Newton iterations advanced by the same passes.  Fills beta, SE, pval, converged of the variant's row.
+// One block per saddle-point candidate of the tensor scan (atomic work counter).  The sums that called for the saddle-point step come
+// from the finishing kernel; what is left of score::test_variant is the pass over all samples that forms the adjusted genotype
+// g = (G - x'coef) / sqrt(AC) -- one-sided sums, and the (g, mu) pairs of the samples with G != 0 compacted in thread order -- and
+// the root finding on those pairs (score::saddle_prob_dual: both Newton iterations advanced by the same passes).  Same arithmetic
+// per sample as score::spa_adjust; the covariates are read from a column-major copy (xt: [K][ldx], 32 bytes per thread and column for
+// its four samples) so that ten 32-byte loads per thread are in flight instead of one row.  Fills beta, SE, pval, converged.
 template <int KMAX>
 __global__ void __launch_bounds__(kSpaThreads) spa_candidate_kernel(score::Model M, PackedSrc src, int64_t n_cand,
                                                                      const int32_t *__restrict__ list, const double *__restrict__ cand,
-                                                                     double *spa, unsigned long long *__restrict__ counter,
+                                                                     const double *__restrict__ xt, const double *__restrict__ mup,
+                                                                     int64_t ldx, double *spa, unsigned long long *__restrict__ counter,
                                                                      double *__restrict__ out) {
     __shared__ double red[kSpaThreads / 32];
     __shared__ int wsum[kSpaThreads / 32];
     __shared__ unsigned long long next;
     BlockEnv env{red, wsum};
     const int K = M.K;
-    double *spa_g = spa + (size_t)blockIdx.x * 2 * (size_t)M.n, *spa_mu = spa_g + M.n;
+    const int64_t n = M.n, ngrp = (n + 3) >> 2;
+    double *spa_g = spa + (size_t)blockIdx.x * 2 * (size_t)n, *spa_mu = spa_g + n;
     while (true) {
         __syncthreads();
         if (threadIdx.x == 0) next = atomicAdd(counter, 1ULL);
@@ -440,14 +448,73 @@ __global__ void __launch_bounds__(kSpaThreads) spa_candidate_kernel(score::Model
         double coef[KMAX];
 #pragma unroll
         for (int c = 0; c < KMAX; c++) coef[c] = (c < K) ? r[kCandCols + c] : 0.0;
-        const score::Coded<score::PackedRow> G{src.row(v), AF * 2, minus};
+        // value of a code after mean imputation and the flip to the minor allele (score::Coded)
+        const double imp = AF * 2;
+        const double t0 = minus ? 2.0 : 0.0, t2 = minus ? 0.0 : 2.0, t3 = minus ? 2 - imp : imp;
+        auto value = [&](unsigned code) { return code == 0 ? t0 : (code == 1 ? 1.0 : (code == 2 ? t2 : t3)); };
+        const uint8_t *row = src.base + (size_t)v * src.pitch;
         int my_nnz = 0;
-        SGB_SCORE_FOR_SAMPLES(env, M.n, i) my_nnz += (G(i) != 0);
+        for (int64_t g = threadIdx.x; g < ngrp; g += kSpaThreads) {
+            const unsigned b = row[g];
+            const int lim = (int)min((int64_t)4, n - 4 * g);
+#pragma unroll
+            for (int j = 0; j < 4; j++) my_nnz += (j < lim && value((b >> (2 * j)) & 3u) != 0);
+        }
         double *o = out + v * score::kOutCols;
-        double pval = o[6], beta = 0;
+        const double pval_noadj = o[6];
+        // ---- score::spa_adjust, with the pass over the samples restated for 32-byte loads
+        const double AC2 = minus ? (2 * Num - AC) : AC;
+        const double sc = 1 / sqrt(AC2);
+        const double m1 = (gmu - coef_xmu) * sc;
+        const double svar2 = var2 * sc * sc, svar1 = svar2 * M.varRatio;
+        const double Tstat = S * sc;
+        const double q = Tstat / sqrt(svar1) * sqrt(svar2) + m1;
+        int64_t nnz = 0;
+        int64_t at = env.excl_scan(my_nnz, nnz);
+        double g_pos = 0, g_neg = 0, sub_mu = 0, sub_sigma = 0;
+        for (int64_t g = threadIdx.x; g < ngrp; g += kSpaThreads) {
+            const unsigned b = row[g];
+            const int64_t i0 = 4 * g;
+            const int lim = (int)min((int64_t)4, n - i0);
+            double B[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int c = 0; c < KMAX; c++)
+                if (c < K) {
+                    const double2 xa = __ldg(reinterpret_cast<const double2 *>(xt + (size_t)c * ldx + i0));
+                    const double2 xb = __ldg(reinterpret_cast<const double2 *>(xt + (size_t)c * ldx + i0 + 2));
+                    B[0] += coef[c] * xa.x; B[1] += coef[c] * xa.y; B[2] += coef[c] * xb.x; B[3] += coef[c] * xb.y;
+                }
+            const double2 ma = __ldg(reinterpret_cast<const double2 *>(mup + i0)), mb = __ldg(reinterpret_cast<const double2 *>(mup + i0 + 2));
+            const double mm[4] = {ma.x, ma.y, mb.x, mb.y};
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (j < lim) {
+                    const double gv = value((b >> (2 * j)) & 3u);
+                    const double gg = (gv - B[j]) * sc;
+                    if (gg > 0) g_pos += gg; else g_neg += gg;
+                    if (gv != 0) {
+                        const double m = mm[j];
+                        spa_g[at] = gg;
+                        spa_mu[at] = m;
+                        at++;
+                        sub_mu += gg * m;
+                        sub_sigma += gg * gg * m * (1 - m);
+                    }
+                }
+        }
+        g_pos = env.sum(g_pos);
+        g_neg = env.sum(g_neg);
+        const double NAmu = m1 - env.sum(sub_mu);
+        const double NAsigma = svar2 - env.sum(sub_sigma);
+        env.sync();
+        double p_na;
         bool converged = true;
-        score::spa_adjust<KMAX, true>(env, M, G, coef, my_nnz, AC, Num, minus, S, var2, coef_xmu, gmu, o[6], spa_g, spa_mu, pval, beta,
-                                      converged);
+        double pval = score::saddle_prob_dual(env, q, m1, svar2, g_pos, g_neg, nnz, spa_g, spa_mu, NAmu, NAsigma, 2.0, converged, p_na);
+        if (pval == 0 && pval_noadj > 0) {
+            pval = pval_noadj;
+            converged = false;
+        }
+        double beta = (Tstat / svar1) / sqrt(AC2);
         if (minus) beta = -beta;
         if (threadIdx.x == 0) {
             o[3] = beta;
@@ -494,8 +561,8 @@ void launch_candidates(Context &c, ScoreState &s, const PackedSrc &src, int64_t 
     c.prof_begin();
     const int K = s.M.K;
 #define SGB_SPA_LAUNCH(KMAX)                                                                                                          \
-    spa_candidate_kernel<KMAX><<<grid, kSpaThreads, 0, c.stream>>>(s.M, src, n_cand, s.spa_list.get(), s.cand.get(), s.spa.get(),     \
-                                                                   s.counter.get(), s.out.get())
+    spa_candidate_kernel<KMAX><<<grid, kSpaThreads, 0, c.stream>>>(s.M, src, n_cand, s.spa_list.get(), s.cand.get(), s.xt.get(),      \
+                                                                   s.mup.get(), s.ldx, s.spa.get(), s.counter.get(), s.out.get())
     if (K <= 4) SGB_SPA_LAUNCH(4);
     else if (K <= 8) SGB_SPA_LAUNCH(8);
     else if (K <= 16) SGB_SPA_LAUNCH(16);
@@ -711,6 +778,14 @@ void score_init(Context &c, const sgb_score_model *m, double maf, double mac, do
         }
         DevBuf<double> wdev;
         up(wdev, W.data(), W.size());
+        s->ldx = (int64_t)((n + 3) / 4 * 4);
+        std::vector<double> xt((size_t)K * s->ldx, 0.0), mup((size_t)s->ldx, 0.0);
+        for (size_t i = 0; i < n; i++) {
+            for (size_t k = 0; k < K; k++) xt[k * s->ldx + i] = m->t_X[i * K + k];
+            mup[i] = m->mu[i];
+        }
+        up(s->xt, xt.data(), xt.size());
+        up(s->mup, mup.data(), mup.size());
         s->cdig.ensure((size_t)groups * kClassDigitRows * s->cpad);
         s->cscal.ensure((size_t)s->ncols * kClassScal);
         s->ctot.ensure((size_t)s->ncols * 2);
