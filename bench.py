@@ -784,6 +784,7 @@ def run_assoc(args):
     st = sg.ScoreTest(sg.init_nullmod(assoc_null_model(n)), ctx)
     for _ in range(max(1, args.warmup)):
         st.test_stored(0, min(m, 512))
+    st.test_stored(0, m)          # the workspaces grow to the batch size here, not inside the timed steps
     mon = ClockSampler(0)
     mon.start()
     ctx.reset_stats()

@@ -60,6 +60,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kSpaThreads = 512;   // saddle-point candidates of the tensor scan: one block per candidate
+constexpr int kSpaBuckets = 8;     // candidate lists by minor-allele frequency: the kernel takes the costliest (most non-zero genotypes) first
 constexpr int kCandCols = 8;       // AC, Num, AF, S, var2, coef_xmu, G'mu, (spare), then coef[K]
 
 struct BlockEnv {
@@ -409,7 +410,9 @@ __global__ void __launch_bounds__(64) score_finish_kernel(score::Model M, int64_
     valid[v] = 1;
     if (M.trait == 0 && fin && pval_noadj <= M.thr_pval_spa) {
         // saddle-point candidate: hand the sums over so that spa_candidate_kernel does not repeat the passes that produced them
-        spa_list[atomicAdd(spa_count, 1u)] = (int32_t)v;
+        const double maf = fmin(AF, 1 - AF);
+        const int bucket = kSpaBuckets - 1 - min(kSpaBuckets - 1, (int)(maf * (2 * kSpaBuckets)));
+        spa_list[(size_t)bucket * n_var + atomicAdd(spa_count + bucket, 1u)] = (int32_t)v;
         double *r = cand + (size_t)v * (kCandCols + K);
         r[0] = AC; r[1] = (double)Num; r[2] = AF; r[3] = Sc; r[4] = var2; r[5] = coef_xmu; r[6] = gsum(2 * K + 2);
         for (int c = 0; c < K; c++) r[kCandCols + c] = coef[c];
@@ -424,7 +427,8 @@ __global__ void __launch_bounds__(64) score_finish_kernel(score::Model M, int64_
 // its four samples) so that ten 32-byte loads per thread are in flight instead of one row.  Fills beta, SE, pval, converged.
 template <int KMAX>
 __global__ void __launch_bounds__(kSpaThreads) spa_candidate_kernel(score::Model M, PackedSrc src, int64_t n_cand,
-                                                                     const int32_t *__restrict__ list, const double *__restrict__ cand,
+                                                                     const int32_t *__restrict__ list, const unsigned int *__restrict__ counts,
+                                                                     int64_t list_stride, const double *__restrict__ cand,
                                                                      const double *__restrict__ xt, const double *__restrict__ mup,
                                                                      int64_t ldx, double *spa, unsigned long long *__restrict__ counter,
                                                                      double *__restrict__ out) {
@@ -440,7 +444,10 @@ __global__ void __launch_bounds__(kSpaThreads) spa_candidate_kernel(score::Model
         if (threadIdx.x == 0) next = atomicAdd(counter, 1ULL);
         __syncthreads();
         if ((int64_t)next >= n_cand) break;
-        const int64_t v = list[next];
+        int64_t pos = (int64_t)next;
+        int bucket = 0;
+        while (bucket < kSpaBuckets - 1 && pos >= (int64_t)counts[bucket]) pos -= counts[bucket++];
+        const int64_t v = list[(size_t)bucket * list_stride + pos];
         const double *r = cand + (size_t)v * (kCandCols + K);
         const double AC = r[0], AF = r[2], S = r[3], var2 = r[4], coef_xmu = r[5], gmu = r[6];
         const int Num = (int)r[1];
@@ -454,6 +461,7 @@ __global__ void __launch_bounds__(kSpaThreads) spa_candidate_kernel(score::Model
         auto value = [&](unsigned code) { return code == 0 ? t0 : (code == 1 ? 1.0 : (code == 2 ? t2 : t3)); };
         const uint8_t *row = src.base + (size_t)v * src.pitch;
         int my_nnz = 0;
+#pragma unroll 4
         for (int64_t g = threadIdx.x; g < ngrp; g += kSpaThreads) {
             const unsigned b = row[g];
             const int lim = (int)min((int64_t)4, n - 4 * g);
@@ -472,8 +480,12 @@ __global__ void __launch_bounds__(kSpaThreads) spa_candidate_kernel(score::Model
         int64_t nnz = 0;
         int64_t at = env.excl_scan(my_nnz, nnz);
         double g_pos = 0, g_neg = 0, sub_mu = 0, sub_sigma = 0;
+        unsigned bnext = (threadIdx.x < ngrp) ? row[threadIdx.x] : 0u;
         for (int64_t g = threadIdx.x; g < ngrp; g += kSpaThreads) {
-            const unsigned b = row[g];
+            // the packed byte of the next iteration is requested before this one's covariates: the warp issues in order, and the
+            // first use of the byte would otherwise hold back the loads behind it for a full memory latency
+            const unsigned b = bnext;
+            if (g + kSpaThreads < ngrp) bnext = row[g + kSpaThreads];
             const int64_t i0 = 4 * g;
             const int lim = (int)min((int64_t)4, n - i0);
             double B[4] = {0, 0, 0, 0};
@@ -555,14 +567,15 @@ void launch_tensor(Context &c, ScoreState &s, const uint8_t *packed, size_t pitc
     SGB_CUDA(cudaMemcpyAsync(s.h_cerr.p, s.cerr.get(), sizeof(int), cudaMemcpyDeviceToHost, c.stream));
 }
 
-void launch_candidates(Context &c, ScoreState &s, const PackedSrc &src, int64_t n_cand) {
+void launch_candidates(Context &c, ScoreState &s, const PackedSrc &src, int64_t n_cand, int64_t n_var) {
     const int grid = (int)std::min<int64_t>(n_cand, s.grid_spa);
     SGB_CUDA(cudaMemsetAsync(s.counter.get(), 0, sizeof(unsigned long long), c.stream));
     c.prof_begin();
     const int K = s.M.K;
 #define SGB_SPA_LAUNCH(KMAX)                                                                                                          \
-    spa_candidate_kernel<KMAX><<<grid, kSpaThreads, 0, c.stream>>>(s.M, src, n_cand, s.spa_list.get(), s.cand.get(), s.xt.get(),      \
-                                                                   s.mup.get(), s.ldx, s.spa.get(), s.counter.get(), s.out.get())
+    spa_candidate_kernel<KMAX><<<grid, kSpaThreads, 0, c.stream>>>(s.M, src, n_cand, s.spa_list.get(), s.spa_count.get(), n_var,      \
+                                                                   s.cand.get(), s.xt.get(), s.mup.get(), s.ldx, s.spa.get(),         \
+                                                                   s.counter.get(), s.out.get())
     if (K <= 4) SGB_SPA_LAUNCH(4);
     else if (K <= 8) SGB_SPA_LAUNCH(8);
     else if (K <= 16) SGB_SPA_LAUNCH(16);
@@ -612,8 +625,8 @@ void launch(Context &c, ScoreState &s, const Tiles &tiles, const Src &src, int64
         return;
     }
     if (n_var > 0x7fffffff) throw Error(SGB_ERR_INVALID, "more than 2^31 - 1 variants in one batch");
-    s.spa_list.ensure((size_t)n_var);
-    SGB_CUDA(cudaMemsetAsync(s.spa_count.get(), 0, sizeof(unsigned int), c.stream));
+    s.spa_list.ensure((size_t)n_var * kSpaBuckets);   // the tiled kernel fills list 0 only
+    SGB_CUDA(cudaMemsetAsync(s.spa_count.get(), 0, sizeof(unsigned int) * kSpaBuckets, c.stream));
     const bool tensor = s.path == SGB_SCORE_TENSOR && s.tensor_ok && tensor_base != nullptr;
     if (tensor) {
         launch_tensor(c, s, tensor_base, tensor_pitch, n_var);
@@ -631,7 +644,7 @@ void launch(Context &c, ScoreState &s, const Tiles &tiles, const Src &src, int64
     c.prof_end("score_tiled_kernel");
     c.stats.n_kernel_launches++;
     }
-    c.d2h(s.h_count.p, s.spa_count.get(), sizeof(unsigned int));
+    c.d2h(s.h_count.p, s.spa_count.get(), sizeof(unsigned int) * kSpaBuckets);
     c.sync();
     if (tensor && *s.h_cerr.p != 0) {
         *s.h_cerr.p = 0;
@@ -639,8 +652,9 @@ void launch(Context &c, ScoreState &s, const Tiles &tiles, const Src &src, int64
         throw Error(SGB_ERR_CUDA, "the tensor-core score scan timed out waiting inside the GEMM kernel (SGB_WAIT_TIMEOUT_MS); "
                                   "sgb_score_test_set_path(ctx, SGB_SCORE_TILED) selects the kernel without such waits");
     }
-    const int64_t n_spa = *s.h_count.p;
-    if (n_spa > 0 && tensor) launch_candidates(c, s, PackedSrc{tensor_base, tensor_pitch}, n_spa);
+    int64_t n_spa = 0;
+    for (int b = 0; b < kSpaBuckets; b++) n_spa += s.h_count.p[b];
+    if (n_spa > 0 && tensor) launch_candidates(c, s, PackedSrc{tensor_base, tensor_pitch}, n_spa, n_var);
     else if (n_spa > 0) launch_per_variant(c, s, src, n_spa, s.spa_list.get());
 }
 
@@ -755,8 +769,8 @@ void score_init(Context &c, const sgb_score_model *m, double maf, double mac, do
         up(s->mt, mt.data(), mt.size());
         c.sync();
     }
-    s->spa_count.ensure(1);
-    s->h_count.ensure(1);
+    s->spa_count.ensure(kSpaBuckets);
+    s->h_count.ensure(kSpaBuckets);
     // tensor path: the 2K + 4 model columns [a | w x | y - mu | w | mu | 1], column-major, cut into digit planes once
     try {
         const bool bin = (m->trait == 0);

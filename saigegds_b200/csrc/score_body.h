@@ -319,14 +319,23 @@ struct RootIter {
     }
 };
 
+// The loops below read the next (g, mu) pair of the thread before they work on the current one: a pair costs two or four
+// exponentials, during which the next load is in flight (the plain loops sat in the latency of these loads with 16 warps per SM).
+// The order of a thread's additions is unchanged.
 template <class Env>
 SGB_HD void K1_K2_dual(Env &env, double ta, bool on_a, double tb, bool on_b, int64_t nnz, const double *g, const double *mu,
                        double &s1a, double &s2a, double &s1b, double &s2b) {
     double a1 = 0, a2 = 0, b1 = 0, b2 = 0;
+    const int64_t step = env.nthr();
+    int64_t k = env.tid();
+    double gn = 0, mn = 0;
+    if (k < nnz) { gn = g[k]; mn = mu[k]; }
     if (on_a && on_b && ta == tb) {          // the first pass (t = 0): one evaluation serves both
-#pragma unroll 4
-        for (int64_t k = env.tid(); k < nnz; k += env.nthr()) {
-            const double m = mu[k], om = 1 - m, gi = g[k], e = exp(-gi * ta);
+        while (k < nnz) {
+            const double m = mn, om = 1 - m, gi = gn;
+            k += step;
+            if (k < nnz) { gn = g[k]; mn = mu[k]; }
+            const double e = exp(-gi * ta);
             const double inv = 1 / (om * e + m), mg = m * gi * inv;
             a1 += mg;
             const double v = om * e * gi * inv * mg;
@@ -336,9 +345,10 @@ SGB_HD void K1_K2_dual(Env &env, double ta, bool on_a, double tb, bool on_b, int
         s2a = s2b = env.sum(a2);
         return;
     }
-#pragma unroll 4
-    for (int64_t k = env.tid(); k < nnz; k += env.nthr()) {
-        const double m = mu[k], om = 1 - m, gi = g[k];
+    while (k < nnz) {
+        const double m = mn, om = 1 - m, gi = gn;
+        k += step;
+        if (k < nnz) { gn = g[k]; mn = mu[k]; }
         if (on_a) {
             const double e = exp(-gi * ta), inv = 1 / (om * e + m), mg = m * gi * inv;
             a1 += mg;
@@ -361,9 +371,14 @@ template <class Env>
 SGB_HD void saddle_sums_dual(Env &env, double ta, bool on_a, double tb, bool on_b, int64_t nnz, const double *g, const double *mu,
                              double &Ka, double &k2a, double &Kb, double &k2b) {
     double a0 = 0, a2 = 0, b0 = 0, b2 = 0;
-#pragma unroll 2
-    for (int64_t k = env.tid(); k < nnz; k += env.nthr()) {
-        const double m = mu[k], om = 1 - m, gi = g[k];
+    const int64_t step = env.nthr();
+    int64_t k = env.tid();
+    double gn = 0, mn = 0;
+    if (k < nnz) { gn = g[k]; mn = mu[k]; }
+    while (k < nnz) {
+        const double m = mn, om = 1 - m, gi = gn;
+        k += step;
+        if (k < nnz) { gn = g[k]; mn = mu[k]; }
         if (on_a) {
             a0 += log(1 - m + m * exp(gi * ta));
             const double e = exp(-gi * ta);
