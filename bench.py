@@ -793,7 +793,13 @@ def run_assoc(args):
         res, ms = st.test_stored(0, m)
         times.append(ms)
     launches = ctx.stats()["n_kernel_launches"]
-    host = ctx.synth_to_host(n, m)
+    host0 = ctx.synth_to_host(n, m)
+    # the batch in page-locked host memory (sgb_malloc_host), as a pipeline that reads genotype blocks for the GPU would hold it
+    pin = ctx.pinned_empty((host0.size + 7) // 8)
+    host = pin.view(np.uint8)[:host0.size].reshape(host0.shape)
+    host[...] = host0
+    del host0
+    st.test(host[:512])
     t0 = time.perf_counter()
     res_h = st.test(host)
     e2e_s = time.perf_counter() - t0
@@ -804,8 +810,8 @@ def run_assoc(args):
     kt = ctx.kernel_times()
     ctx.set_profiling(False)
     ms = float(np.mean(times))
-    # dense part of the scan: three integer GEMMs (bit planes of the codes x digit planes of the 2K + 3 model columns) on tcgen05
-    ncols = 2 * ASSOC_K + 3
+    # dense part of the scan: three integer GEMMs (bit planes of the codes x digit planes of the 2K + 4 model columns) on tcgen05
+    ncols = 2 * ASSOC_K + 4
     gemm_key = next((k for k in kt if k.startswith("umma_pair_kernel")), None)
     shares = {k: v[0] / max(1e-9, sum(x[0] for x in kt.values())) for k, v in kt.items()}
     if gemm_key is not None:
@@ -819,9 +825,9 @@ def run_assoc(args):
                 "achieved": ach, "peak": peak_tops, "unit": "TOP/s", "frac": ach / peak_tops, "traffic": None,
                 "peak_source": "int8 tcgen05 rate measured with tools/umma_probe.cu on this pool's B200 (4,179 TOP/s), or 2 x bf16 of "
                                "MEASURED_PEAKS.json if larger",
-                "note": "algorithmic MACs = 3 planes x n x variants x 6 digits x (2K + 3) columns; a pair MMA costs ~96 clk whatever "
+                "note": "algorithmic MACs = 3 planes x n x variants x 6 digits x (2K + 4) columns; a pair MMA costs ~96 clk whatever "
                         "N <= 192, so %d digit columns of 192 leave the pipe under-used by construction. The scan as a whole is bound by "
-                        "score_test_kernel (saddle-point candidates, FP64 transcendentals): see `shares`" % (6 * ncols)}
+                        "spa_candidate_kernel (saddle-point candidates, FP64 transcendentals): see `shares`" % (6 * ncols)}
     else:
         # CUDA-core tiled kernel: reads n (2K + 2) doubles of model values per variant from shared memory
         smem_bytes = float(n) * (2 * ASSOC_K + 2) * 8 * m
@@ -839,7 +845,7 @@ def run_assoc(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": m / e2e_s, "unit": "variants/s", "h2d_bytes_per_step": int(host.nbytes),
                     "d2h_bytes_per_step": int(m * 8 * 8 + m * 4),
-                    "note": "ScoreTest.test on packed host batches (sgb_score_test_packed): copy in, all kernels, copy out"},
+                    "note": "ScoreTest.test on a packed host batch in page-locked memory (sgb_score_test_packed): copy in, all kernels, copy out"},
             "gpu_launches": int(launches), "score_path": os.environ.get("SGB_SCORE_PATH", "tensor"),
             "roofline": roof,
             "spa_adjusted": int(np.sum(res["pval"][res["valid"]] != res["p.norm"][res["valid"]])),
