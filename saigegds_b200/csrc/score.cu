@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(64) score_finish_kernel(score::Model M, int64_
 // per sample as score::spa_adjust; the covariates are read from a column-major copy (xt: [K][ldx], 32 bytes per thread and column for
 // its four samples) so that ten 32-byte loads per thread are in flight instead of one row.  Fills beta, SE, pval, converged.
 template <int KMAX>
-__global__ void __launch_bounds__(kSpaThreads) spa_candidate_kernel(score::Model M, PackedSrc src, int64_t n_cand,
+__global__ void __launch_bounds__(kSpaThreads, 2) spa_candidate_kernel(score::Model M, PackedSrc src, int64_t n_cand,
                                                                      const int32_t *__restrict__ list, const unsigned int *__restrict__ counts,
                                                                      int64_t list_stride, const double *__restrict__ cand,
                                                                      const double *__restrict__ xt, const double *__restrict__ mup,
