@@ -13,6 +13,7 @@ The reference calls the native test once per variant from seqApply; here a batch
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -114,12 +115,46 @@ class ScoreTest:
         return self._result(out, valid), float(ms.value)
 
 
-def seqAssocGLMM_SPA(geno: np.ndarray, modobj: NullModel, maf=float("nan"), mac=10.0, missing=0.1, spa_pval=0.05,
+def _scan_gds(gdsfile, modobj: NullModel, maf, mac, missing, spa_pval, var_ratio, batch_variants, kernel_path, ctx, threads):
+    """seqAssocGLMM_SPA on a GDS file (R/assoc_single.r:116-155, 233-300): the file is read without SeqArray (gds.py), the samples
+    of the model are selected in file order (`seqSetFilter(sample.id=)`), the model rows are reordered to that order
+    (`ii <- match(sid, modobj$sample.id)`), the genotype node is turned into 2-bit dosage rows on the device (they replace the
+    genotypes the context stores) and scanned from HBM in batches."""
+    from . import gds as G
+    if modobj.sample_id is None:
+        raise ValueError("The model has no sample IDs to match against the GDS file.")
+    g = G.read_gds_genotypes(str(gdsfile), threads=threads)
+    model_ids = np.asarray(modobj.sample_id).astype(g.sample_id.dtype)
+    pos = {sid: i for i, sid in enumerate(model_ids.tolist())}
+    in_model = np.array([s in pos for s in g.sample_id.tolist()])
+    sel = np.flatnonzero(in_model).astype(np.int32)
+    if len(sel) != len(model_ids):
+        raise ValueError("Some of sample IDs are not available in the GDS file.")
+    ii = np.array([pos[s] for s in g.sample_id[sel].tolist()], dtype=np.int64)
+    if g.n_variant <= 0:
+        raise ValueError("No variant in the genotypic data set!")
+    mobj = init_nullmod(modobj, ii, maf, mac, missing, spa_pval, var_ratio)
+    ctx = ctx or default_context()
+    r = ctx.store_gds_geno(g.allele_bits, g.n_sample, g.n_variant, sample_sel=None if len(sel) == g.n_sample else sel)
+    st = ScoreTest(mobj, ctx)
+    if kernel_path is not None:
+        st.set_path(kernel_path)
+    n_stored = int(np.sum(r["variant_sel"]))
+    parts = [st.test_stored(a, min(batch_variants, n_stored - a))[0] for a in range(0, n_stored, batch_variants)]
+    res = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+    return res, np.asarray(g.variant_id)[r["variant_sel"]]
+
+
+def seqAssocGLMM_SPA(geno, modobj: NullModel, maf=float("nan"), mac=10.0, missing=0.1, spa_pval=0.05,
                      var_ratio=float("nan"), variant_id=None, sample_index=None, batch_bytes=1 << 30,
-                     kernel_path: str | None = None, ctx: Context | None = None) -> dict:
-    """Mirror of seqAssocGLMM_SPA (R/assoc_single.r:92-334) for genotypes already in memory: `geno` replaces the GDS
-    node (2-bit packed uint8 [n_var][ceil(n/4)] or float64 dosages [n_var][n]).  Returns the data.frame columns id, AF.alt,
-    mac, num, beta, SE, pval (+ p.norm, converged for binary traits) of the variants that pass the filters."""
+                     kernel_path: str | None = None, ctx: Context | None = None, threads: int = 8) -> dict:
+    """Mirror of seqAssocGLMM_SPA (R/assoc_single.r:92-334).  `geno` is the path of a SeqArray GDS file (read without SeqArray, the
+    model's `sample_id` selects and orders the samples as the reference does) or genotypes already in memory (2-bit packed uint8
+    [n_var][ceil(n/4)] or float64 dosages [n_var][n]; `sample_index` then reorders the model).  Returns the data.frame columns id,
+    AF.alt, mac, num, beta, SE, pval (+ p.norm, converged for binary traits) of the variants that pass the filters."""
+    if isinstance(geno, (str, os.PathLike)):
+        res, ids_all = _scan_gds(geno, modobj, maf, mac, missing, spa_pval, var_ratio, 1 << 16, kernel_path, ctx, threads)
+        return _answer(res, ids_all if variant_id is None else np.asarray(variant_id), modobj)
     if geno.shape[0] <= 0:
         raise ValueError("No variant in the genotypic data set!")
     mobj = init_nullmod(modobj, sample_index, maf, mac, missing, spa_pval, var_ratio)
@@ -129,8 +164,11 @@ def seqAssocGLMM_SPA(geno: np.ndarray, modobj: NullModel, maf=float("nan"), mac=
     step = max(1, int(batch_bytes // max(1, geno.shape[1] * geno.itemsize)))
     parts = [st.test(geno[a:a + step]) for a in range(0, geno.shape[0], step)]
     res = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+    return _answer(res, np.arange(1, geno.shape[0] + 1) if variant_id is None else np.asarray(variant_id), modobj)
+
+
+def _answer(res: dict, ids, modobj: NullModel) -> dict:
     keep = res.pop("valid")
-    ids = np.arange(1, geno.shape[0] + 1) if variant_id is None else np.asarray(variant_id)
     ans = {"id": ids[keep]}
     for k in COLUMNS:
         ans[k] = res[k][keep]

@@ -88,3 +88,42 @@ def test_gds_file_to_stored_genotypes(gpu, fx, oracle):
     sub = [s for s in g.sample_id[::2]]
     g2, r2 = gds.store_from_gds(gpu, REF_GDS, sample_id=sub, maf=0.005)
     assert gpu.n_samp == 500 and np.array_equal(r2["sample_sel"], np.arange(0, 1000, 2))
+
+
+def gds_from_packed(tmp_path, packed, n_sample, name="fixture.gds"):
+    """The fixture's genotypes in the framing the reader relies on (sample ids s1.., variant ids 1.., bit2 allele pairs)."""
+    bits = bits_from_packed(packed, n_sample).tobytes()
+    sid = b"".join(bytes([len(s)]) + s for s in (("s%d" % (i + 1)).encode() for i in range(n_sample)))
+    vid = np.arange(1, packed.shape[0] + 1, dtype="<i4").tobytes()
+    cut = max(65536, (len(bits) // 3 // 4096) * 4096)
+    blob = gds.GDS_MAGIC + b"\x00\x01hdr" + lzma.compress(sid) + b"\x07" + lzma.compress(vid) + b"pad" + \
+        b"".join(lzma.compress(bits[i:i + cut]) for i in range(0, len(bits), cut)) + b"tail"
+    path = tmp_path / name
+    path.write_bytes(blob)
+    return str(path)
+
+
+@pytest.mark.gpu
+def test_association_scan_straight_from_a_gds_file(gpu, fx, tmp_path):
+    """seqAssocGLMM_SPA(gdsfile, modobj) (R/assoc_single.r:92-334) without SeqArray: file -> xz streams -> device dosage rows -> scan.
+    The model's samples are given in another order than the file's (the reference reorders the model rows with
+    `match(sid, modobj$sample.id)`, :141-145) and the golden p-values of all 10,000 variants must come out."""
+    import saigegds_b200 as sg
+    from test_score_test import golden_modobj, relmax
+    path = gds_from_packed(tmp_path, fx.packed_all, fx.n_samp)
+    perm = np.random.default_rng(5).permutation(fx.n_samp)
+    mod = golden_modobj(fx, "binary")
+    ids = np.array(["s%d" % (i + 1) for i in range(fx.n_samp)])
+    noK = mod.obj_noK
+    mod.sample_id = ids[perm]
+    mod.fitted_values, mod.linear_predictors, mod.residuals = mod.fitted_values[perm], mod.linear_predictors[perm], mod.residuals[perm]
+    noK.y, noK.mu, noK.res, noK.V = noK.y[perm], noK.mu[perm], noK.res[perm], noK.V[perm]
+    noK.X1, noK.XXVX_inv, noK.XV = noK.X1[perm], noK.XXVX_inv[perm], noK.XV[:, perm]
+    ans = sg.seqAssocGLMM_SPA(path, mod, mac=4, ctx=gpu)
+    pv = fx.pval
+    assert np.array_equal(ans["id"], pv["id"]) and np.array_equal(ans["mac"], pv["mac"])
+    assert relmax(ans["pval"], pv["pval"]) < 1e-9 and relmax(ans["p.norm"], pv["p_norm"]) < 1e-9
+    assert np.array_equal(ans["converged"].astype(int), pv["converged"])
+    mod.sample_id = np.append(ids[perm][:-1], "nobody")
+    with pytest.raises(ValueError, match="not available in the GDS file"):
+        sg.seqAssocGLMM_SPA(path, mod, mac=4, ctx=gpu)
