@@ -20,6 +20,7 @@ into the C-ABI.  torch is used for plumbing only (device selection, torch.distri
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -445,16 +446,76 @@ class NullModel:
     variant_id: np.ndarray | None = None
 
 
-def seqFitNullGLMM_SPA(formula: str, data: dict, packed_geno: np.ndarray, trait_type="binary", sample_id=None,
+def _gds_front_end(ctx, path, data: dict, used: list, sample_col: str, maf, missing_rate, max_num_snp, variant_id, seed, verbose, threads):
+    """The part of seqFitNullGLMM_SPA that talks to the GDS file (R/saige_main.r:273-333), without SeqArray: rows of `data` with a
+    missing value are dropped, the rest are matched to the file's samples and put in file order, the variants are filtered on the
+    selected samples (maf / missing.rate, or an explicit variant.id list), at most max.num.snp of them are kept (R's
+    `set.seed(seed); sample(which(v), max.num.snp)`), and the genotypes are stored in `ctx`.  Returns (data in file order, variant ids)."""
+    from . import gds as G
+    if sample_col in used:
+        raise ValueError("'%s' should not be in the formula." % sample_col)
+    if sample_col not in data:
+        raise ValueError("'%s' should be one of the columns in 'data'." % sample_col)
+    ids = np.asarray(data[sample_col])
+    if len(set(ids.tolist())) != len(ids):
+        raise ValueError("'%s' in data should be unique." % sample_col)
+    ok = np.ones(len(ids), dtype=bool)
+    for k in used:                                                          # na.omit(data[, c(sample.col, vars)])
+        ok &= ~np.isnan(np.asarray(data[k], dtype=np.float64))
+    g = G.read_gds_genotypes(str(path), threads=threads)
+    row_of = {sid: i for i, sid in enumerate(ids.astype(g.sample_id.dtype).tolist()) if ok[i]}
+    file_sel = np.array([i for i, sid in enumerate(g.sample_id.tolist()) if sid in row_of], dtype=np.int32)
+    if len(file_sel) == 0:
+        raise ValueError("No common sample.id between 'data' and the GDS file.")
+    rows = np.array([row_of[sid] for sid in g.sample_id[file_sel].tolist()], dtype=np.int64)   # data <- data[match(sid, ...), ]
+    sub = {k: np.asarray(v)[rows] for k, v in data.items()}
+    sel = None if len(file_sel) == g.n_sample else file_sel
+
+    def subset_bits(mask):
+        """allele bits of the variants in `mask` (the node is [variant][sample][2] x 2 bits)"""
+        per = g.n_sample * 4
+        if per % 8 == 0:
+            return np.ascontiguousarray(g.allele_bits[:g.n_variant * (per // 8)].reshape(g.n_variant, per // 8)[mask]).reshape(-1)
+        nib = np.stack([g.allele_bits & 15, g.allele_bits >> 4], axis=1).reshape(-1)[:g.n_variant * g.n_sample]
+        nib = nib.reshape(g.n_variant, g.n_sample)[mask].reshape(-1)
+        if nib.size % 2:
+            nib = np.append(nib, np.uint8(0))
+        return (nib[0::2] | (nib[1::2] << 4)).astype(np.uint8)
+
+    vid = np.asarray(g.variant_id)
+    if variant_id is None:
+        if verbose:
+            print("Filtering variants:")
+        r = ctx.store_gds_geno(g.allele_bits, g.n_sample, g.n_variant, sample_sel=sel, maf=maf, missing_rate=missing_rate)
+        keep = r["variant_sel"].copy()
+    else:
+        keep = np.isin(vid, np.asarray(variant_id))
+        ctx.store_gds_geno(subset_bits(keep), g.n_sample, int(keep.sum()), sample_sel=sel)
+    n_kept = int(keep.sum())
+    if max_num_snp > 0 and n_kept > max_num_snp:
+        ctx.set_seed(seed)
+        pick = np.sort(np.flatnonzero(keep)[ctx.sample_int(n_kept)[:int(max_num_snp)] - 1])
+        keep = np.zeros_like(keep)
+        keep[pick] = True
+        ctx.store_gds_geno(subset_bits(keep), g.n_sample, int(keep.sum()), sample_sel=sel)
+    if verbose:
+        print("    # of samples: %d\n    # of variants: %d%s" % (len(file_sel), int(keep.sum()),
+              " (randomly selected from %d)" % n_kept if n_kept > keep.sum() else ""))
+    return sub, vid[keep]
+
+
+def seqFitNullGLMM_SPA(formula: str, data: dict, packed_geno, trait_type="binary", sample_id=None,
                        variant_id=None, inv_norm=True, X_transform=True, tol=0.02, maxiter=20, nrun=30, tolPCG=1e-5,
                        maxiterPCG=500, num_marker=30, tau_init=(0, 0), traceCVcutoff=0.0025, ratioCVcutoff=0.001,
-                       seed=200, verbose=False, ctx: Context | None = None) -> NullModel:
-    """Mirror of seqFitNullGLMM_SPA (R/saige_main.r:223-654) for data already in memory.
+                       seed=200, verbose=False, ctx: Context | None = None, sample_col="sample.id", maf=0.005,
+                       missing_rate=0.01, max_num_snp=1000000, threads: int = 8) -> NullModel:
+    """Mirror of seqFitNullGLMM_SPA (R/saige_main.r:223-654).
 
-    `packed_geno` replaces the GDS file + the genotype loading at R/saige_main.r:388-421: either a uint8 array
+    `packed_geno` is the path of a SeqArray GDS file -- read without SeqArray (gds.py); `data[sample_col]`, `maf`, `missing_rate`,
+    `max_num_snp` and `variant_id` then select samples and variants like the reference (:273-333) and the model carries the
+    file's sample and variant ids -- or genotypes already in memory, replacing the loading at :388-421: a uint8 array
     [n_variant][ceil(n_samp/4)] in the 2-bit format (geno.sparse=FALSE, SeqArray:::.seqGet2bGeno) or a list of
-    `saige_get_sparse` vectors (geno.sparse=TRUE, the reference's default).  Sample/variant filtering, which the
-    reference does through SeqArray (:305-333), is the caller's job (or `saigegds_b200.store_from_gds`).
+    `saige_get_sparse` vectors (geno.sparse=TRUE, the reference's default); sample / variant filtering is then the caller's job.
     Linearly dependent covariate columns are dropped before the QR transform like the reference does (:362-376); the returned
     coefficients then belong to the kept columns.  The random marker order of the variance-ratio step mirrors R's
     `set.seed(seed, sample.kind = "Rounding")`, the setting the reference's golden fixtures were produced with -- under R >= 3.6's
@@ -464,6 +525,11 @@ def seqFitNullGLMM_SPA(formula: str, data: dict, packed_geno: np.ndarray, trait_
         raise ValueError("Invalid 'trait.type'.")
     ctx = ctx or default_context()
     phenovar, terms, intercept = rsetup.parse_formula(formula)
+    from_gds = isinstance(packed_geno, (str, os.PathLike))
+    if from_gds:
+        data, gds_variant_id = _gds_front_end(ctx, packed_geno, data, [phenovar] + list(terms), sample_col, maf, missing_rate,
+                                              max_num_snp, variant_id, seed, verbose, threads)
+        sample_id, variant_id = data[sample_col], gds_variant_id
     y = np.asarray(data[phenovar], dtype=np.float64)
     n = len(y)
     X = rsetup.model_matrix(data, terms, intercept)
@@ -479,7 +545,9 @@ def seqFitNullGLMM_SPA(formula: str, data: dict, packed_geno: np.ndarray, trait_
                 print("    exclude %d covariates (%s) to avoid multi collinearity." % (len(drop), ", ".join(drop)))
             X = X[:, keep]
         X, X_qrr = rsetup.qr_transform(X)                                   # :378-380
-    if isinstance(packed_geno, np.ndarray) and packed_geno.ndim == 2:
+    if from_gds:
+        pass                                                                # stored by _gds_front_end
+    elif isinstance(packed_geno, np.ndarray) and packed_geno.ndim == 2:
         ctx.saige_store_2b_geno(packed_geno, n)                             # :437
     else:
         ctx.saige_store_sp_geno(packed_geno, n)                             # :434

@@ -127,3 +127,39 @@ def test_association_scan_straight_from_a_gds_file(gpu, fx, tmp_path):
     mod.sample_id = np.append(ids[perm][:-1], "nobody")
     with pytest.raises(ValueError, match="not available in the GDS file"):
         sg.seqAssocGLMM_SPA(path, mod, mac=4, ctx=gpu)
+
+
+@pytest.mark.gpu
+def test_null_model_fit_and_scan_from_a_gds_file_like_the_reference_workflow(gpu, fx, tmp_path):
+    """The reference's own workflow (inst/unitTests/test_SAIGE.R: seqFitNullGLMM_SPA(y ~ x1 + x2, pheno, gdsfile) then
+    seqAssocGLMM_SPA(gdsfile, glmm, mac = 4)) on a GDS-framed file of the fixture, through the Python mirror with no SeqArray:
+    the phenotype table is given in another row order with two extra rows (an unknown sample, a missing covariate), the MAF filter
+    runs on the device -> the golden 9,976 variants, tau, variance ratio, and the golden p-values of the scan."""
+    import saigegds_b200 as sg
+    from test_score_test import relmax
+    path = gds_from_packed(tmp_path, fx.packed_all, fx.n_samp)
+    n = fx.n_samp
+    perm = np.random.default_rng(11).permutation(n)
+    ids = np.array(["s%d" % (i + 1) for i in range(n)])
+    data = {"sample.id": np.append(ids[perm], ["ghost", "s0"]),
+            "y": np.append(fx.pheno["y"][perm], [1.0, 0.0]),
+            "x1": np.append(fx.pheno["x1"][perm], [0.3, np.nan]),
+            "x2": np.append(fx.pheno["x2"][perm], [1.0, 0.0])}
+    glmm = sg.seqFitNullGLMM_SPA("y ~ x1 + x2", data, path, trait_type="binary", ctx=gpu)
+    g = fx.model
+    assert gpu.n_samp == n and gpu.n_var == 9976
+    assert np.array_equal(glmm.sample_id, ids) and np.array_equal(glmm.variant_id, fx.variant_id)
+    assert abs(glmm.tau[1] - g["tau"][1]) / g["tau"][1] < 1e-6
+    assert np.max(np.abs(glmm.coefficients - g["coefficients"]) / np.abs(g["coefficients"])) < 1e-6
+    assert np.array_equal(glmm.var_ratio["id"], g["vr_id"]) and np.allclose(glmm.var_ratio["ratio"], g["vr_ratio"], rtol=1e-6)
+    ans = sg.seqAssocGLMM_SPA(path, glmm, mac=4, ctx=gpu)
+    pv = fx.pval
+    assert np.array_equal(ans["id"], pv["id"]) and relmax(ans["pval"], pv["pval"]) < 1e-6
+    # an explicit variant list instead of the filters, and the sample column checks
+    some = fx.variant_id[::7]
+    glmm2 = sg.seqFitNullGLMM_SPA("y ~ x1 + x2", data, path, trait_type="binary", ctx=gpu, variant_id=some, num_marker=5)
+    assert gpu.n_var == len(some) and np.array_equal(glmm2.variant_id, some)
+    with pytest.raises(ValueError, match="should be unique"):
+        sg.seqFitNullGLMM_SPA("y ~ x1 + x2", dict(data, **{"sample.id": np.append(ids[perm], ["s1", "s2"])}), path, ctx=gpu)
+    with pytest.raises(ValueError, match="No common sample.id"):
+        sg.seqFitNullGLMM_SPA("y ~ x1 + x2", dict(data, **{"sample.id": np.array(["q%d" % i for i in range(n + 2)])}), path, ctx=gpu)
