@@ -28,7 +28,11 @@ void grm_mv_device(Context &c, const double *b, double *out, int k) {
         for (int i = 0; i < k; i++) simt_grm_mv(c, b + (size_t)i * c.N, out + (size_t)i * c.N);
         c.stats.n_product_launches += k;
     }
-    if (c.world > 1) comm_allreduce_sum(c, out, (size_t)c.N * k);
+    if (c.world > 1) {
+        c.prof_begin();
+        comm_allreduce_sum(c, out, (size_t)c.N * k);
+        c.prof_end(k == 1 ? "ncclAllReduce (N doubles)" : "ncclAllReduce (N x k doubles)");
+    }
     if (c.profiling) {
         char nm[48];
         snprintf(nm, sizeof(nm), "[calls] grm_mv k=%02d", k);
