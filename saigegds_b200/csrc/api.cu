@@ -102,6 +102,7 @@ int sgb_ctx_destroy(sgb_context *ctx) {
         cudaStreamSynchronize(ctx->stream);
         sgb::imma_release(*ctx);
         sgb::score_release(*ctx);
+        sgb::solver_release(*ctx);
         sgb::comm_destroy(*ctx);
         cudaEventDestroy(ctx->ev0);
         cudaEventDestroy(ctx->ev1);

@@ -34,6 +34,10 @@ struct Error : std::runtime_error {
 // internal: a kernel with cross-CTA waits timed out; the C-ABI layer redoes the call on kernels without such waits (api.cu)
 constexpr int SGB_INTERNAL_RETRY_NO_WAIT_KERNELS = -1000;
 
+// host time spent in cudaMalloc / cudaFree by DevBuf (a debugging aid: SGB_FIT_TIMING prints it per fit)
+inline double g_alloc_seconds = 0;
+inline long g_alloc_calls = 0;
+
 // Owning device buffer (cudaMalloc / cudaFree), resizable without preserving contents.
 template <typename T>
 struct DevBuf {
@@ -44,14 +48,22 @@ struct DevBuf {
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            const auto t0 = std::chrono::steady_clock::now();
+            cudaFree(p);
+            g_alloc_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            g_alloc_calls++;
+        }
         p = nullptr;
         n = 0;
     }
     void ensure(size_t count) {
         if (count <= n) return;
         release();
+        const auto t0 = std::chrono::steady_clock::now();
         SGB_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+        g_alloc_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        g_alloc_calls++;
         n = count;
     }
     T *get() const { return p; }
@@ -78,6 +90,8 @@ struct Comm;  // comm.cu (NCCL through dlopen)
 struct ImmaPlan;
 // Model and workspaces of the single-variant score test (score.cu)
 struct ScoreState;
+// Device workspaces of the null-model fits, kept between calls (solver.cu)
+struct SolverWs;
 
 struct Context {
     int dev = 0;
@@ -107,6 +121,7 @@ struct Context {
     DevBuf<double> ws_vec;      // scratch N x k
     ImmaPlan *imma = nullptr;
     ScoreState *score = nullptr;
+    SolverWs *solver_ws = nullptr;
 
     // ---- generic reduction workspace ----
     DevBuf<double> red_partial;
@@ -205,6 +220,7 @@ void umma_class_digits(Context &c, const double *cols_device, int64_t n, int nco
                        double *scal_device, long long *tot_device);
 void umma_class_sums(Context &c, const uint8_t *packed_device, size_t pitch, int64_t rows, int64_t n, const int8_t *digits_device,
                      int64_t cpad, int ncols, int amode, unsigned long long *out_lo, unsigned long long *out_hi, int *err_device);
+void solver_release(Context &c);   // solver.cu: frees the kept workspaces of the fits
 // ---- product dispatch (solver.cu) ----
 void grm_mv_device(Context &c, const double *b_device, double *out_device, int k);
 // ---- score.cu: single-variant score test + SPA (saige_main.cpp:101-407, SPATest.cpp) ----
