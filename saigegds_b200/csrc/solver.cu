@@ -170,6 +170,7 @@ struct SolverWs {
     DevBuf<double> PY, APY, PAPY1, PAPY, PA0PY1, PA0PY;
     DevBuf<double> U, AU, SiU, PU;
     DevBuf<double> eta0;
+    DevBuf<double> vr[10];   // variance-ratio step / interaction test: eta, mu, XVt, XXVX_inv, SiX1, G0, G, SiG, adj, wgt
     DevBuf<int8_t> bits;
     PcgWork pcg;
 };
@@ -621,7 +622,8 @@ void calc_var_ratio(Context &c, bool quant, const sgb_fit0 *f, const double tau_
     int num_marker = P.num_marker;
     Solver S(c, N, p, f->family, P);
     S.init(noK->X1, f->y, nullptr);
-    DevBuf<double> eta, mu, XVt, XXVX_inv, SiX1, G0, G, SiG, adj;
+    DevBuf<double> (&vr)[10] = S.ws.vr;
+    DevBuf<double> &eta = vr[0], &mu = vr[1], &XVt = vr[2], &XXVX_inv = vr[3], &SiX1 = vr[4], &G0 = vr[5], &G = vr[6], &SiG = vr[7], &adj = vr[8];
     S.upload(eta, f->linear_predictors, N);
     S.upload(mu, f->fitted_values, N);
     family_weights(c, f->family, eta.get(), mu.get(), S.W.get());   // W from the *glm* fit (:1281-1284)
@@ -648,7 +650,7 @@ void calc_var_ratio(Context &c, bool quant, const sgb_fit0 *f, const double tau_
         Minv = mat_inv(c, XtS);
     }
     // var2 weights: mu (1 - mu) for binary (:1325), 1 for quantitative (:1436)
-    DevBuf<double> wgt;
+    DevBuf<double> &wgt = vr[9];
     if (!quant) {
         wgt.ensure(N);
         std::vector<double> h(N);
@@ -767,7 +769,8 @@ void gxg_snp_bin(Context &c, const sgb_fit0 *f, const double tau_in[2], const do
     const double tau[2] = {tau_in[0], tau_in[1]};
     Solver S(c, N, p, f->family, P);
     S.init(noK->X1, f->y, nullptr);
-    DevBuf<double> eta, mu, XVt, XXVX_inv, SiX1, G0, G, SiG, adj, wgt;
+    DevBuf<double> (&vr)[10] = S.ws.vr;
+    DevBuf<double> &eta = vr[0], &mu = vr[1], &XVt = vr[2], &XXVX_inv = vr[3], &SiX1 = vr[4], &G0 = vr[5], &G = vr[6], &SiG = vr[7], &adj = vr[8], &wgt = vr[9];
     S.upload(eta, f->linear_predictors, N);
     S.upload(mu, f->fitted_values, N);
     family_weights(c, f->family, eta.get(), mu.get(), S.W.get());   // :1499-1502
