@@ -174,11 +174,18 @@ struct Context {
     bool fused_disabled = false;         // set after a time-out of the fused kernel: the two-pass kernels take over
     volatile int *async_err = nullptr;   // pinned flag copied back after every fused-kernel launch
     int *async_err_dev = nullptr;        // its device-side source (cleared after an error was reported)
+    bool product_reduced = false;        // the product kernels already summed `out` over the ranks (combine + all-reduce in one kernel)
+    volatile int *comm_err = nullptr;    // pinned flag of the peer-memory all-reduce kernel (comm.cu): a rank did not arrive in time
     void sync() {
         const auto t_sync0 = std::chrono::steady_clock::now();
         SGB_CUDA(cudaStreamSynchronize(stream));
         stats.n_host_syncs++;
         stats.host_wait_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_sync0).count();
+        if (comm_err && *comm_err) {
+            *comm_err = 0;
+            throw Error(SGB_ERR_COMM, "the peer-memory all-reduce timed out waiting for another rank (SGB_WAIT_TIMEOUT_MS); "
+                                      "SGB_NO_PEER_ALLREDUCE=1 selects ncclAllReduce for every collective");
+        }
         if (async_err && *async_err) {
             const int code = *async_err;
             *async_err = 0;
@@ -241,5 +248,11 @@ void comm_unique_id(unsigned char id[128]);
 void comm_init(Context &c, const unsigned char id[128], int rank, int world);
 void comm_destroy(Context &c);
 void comm_allreduce_sum(Context &c, double *buf_device, size_t count);
+// parts of a fused single-RHS product before its last addition: out_n = rout_n + sum(h_part) - sum_t cpart[t][n]
+struct CombineSrc {
+    const double *rout = nullptr, *cpart = nullptr, *h_part = nullptr;
+    int n_ctiles = 0, n_hpart = 0;
+};
+bool comm_combine_allreduce(Context &c, const CombineSrc &src, double *out_device);
 
 }  // namespace sgb

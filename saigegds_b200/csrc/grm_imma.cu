@@ -1673,10 +1673,18 @@ void imma_grm_mv(Context &c, const double *b_all, double *out_all, int k) {
             launch_sparse(c, p, false, p->hm.get(), c.stream, sp_grid, false);
             c.prof_end("sparse_tile_sum_kernel (corr_n)");
             c.prof_begin();
-            combine_fused_kernel<<<(unsigned)((N + 255) / 256), 256, 0, c.stream>>>(p->f_rout.get(), N, p->cpart.get(), p->n_vtiles,
-                                                                                  p->f_hpart.get(), p->f_grid, out);
-            SGB_CHECK_LAUNCH();
-            c.prof_end("combine_kernel");
+            CombineSrc cs;
+            cs.rout = p->f_rout.get(); cs.cpart = p->cpart.get(); cs.n_ctiles = p->n_vtiles; cs.h_part = p->f_hpart.get(); cs.n_hpart = p->f_grid;
+            if (k == 1 && comm_combine_allreduce(c, cs, out)) {
+                // several ranks on one node: the last addition and the sum over the ranks are one kernel over peer memory (comm.cu)
+                c.product_reduced = true;
+                c.prof_end("peer_allreduce_kernel (combine + sum over ranks)");
+            } else {
+                combine_fused_kernel<<<(unsigned)((N + 255) / 256), 256, 0, c.stream>>>(p->f_rout.get(), N, p->cpart.get(), p->n_vtiles,
+                                                                                      p->f_hpart.get(), p->f_grid, out);
+                SGB_CHECK_LAUNCH();
+                c.prof_end("combine_kernel");
+            }
             c.stats.n_kernel_launches += 7;
             c.stats.n_product_launches += 1;
         }

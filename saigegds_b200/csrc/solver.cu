@@ -20,6 +20,7 @@ namespace sgb {
 
 void grm_mv_device(Context &c, const double *b, double *out, int k) {
     c.require_stored();
+    c.product_reduced = false;
     const bool use_imma = (c.kernel == SGB_KERNEL_IMMA) || (c.kernel == SGB_KERNEL_IMMA_TWOPASS) || (c.kernel == SGB_KERNEL_UMMA) ||
                           (c.kernel == SGB_KERNEL_AUTO && imma_available(c));
     if (use_imma) {
@@ -28,7 +29,9 @@ void grm_mv_device(Context &c, const double *b, double *out, int k) {
         for (int i = 0; i < k; i++) simt_grm_mv(c, b + (size_t)i * c.N, out + (size_t)i * c.N);
         c.stats.n_product_launches += k;
     }
-    if (c.world > 1) {
+    if (c.product_reduced) {
+        c.product_reduced = false;
+    } else if (c.world > 1) {
         c.prof_begin();
         comm_allreduce_sum(c, out, (size_t)c.N * k);
         c.prof_end(k == 1 ? "ncclAllReduce (N doubles)" : "ncclAllReduce (N x k doubles)");
