@@ -70,7 +70,8 @@ struct ImmaPlan {
                              // four issuer threads: 4.6 ms per phase at K = 30, 3.5 ms for few columns), 0 = one CTA per MMA (5.0 / 4.0 ms),
                              // 1 = the single-CTA kernel's structure with pair MMAs (7.6 ms: hand-over loop too long); env SGB_UMMA_PAIR
     int um_fork = 0;         // batched path: sparse corrections on the side stream beside the GEMMs (env SGB_UMMA_FORK)
-    int um_gather_w = 16;    // columns per pass of the row-gather kernel: 8, 16 or 32 (env SGB_UMMA_GATHER_W)
+    int um_gather_w = 0;     // columns per pass of the row-gather kernel: 8, 16 or 32 (env SGB_UMMA_GATHER_W); 0 = by the column count
+    int um_gather_v2 = -1;   // 16-byte loads in the row-gather kernel (env SGB_UMMA_GATHER_V2); -1 = with 32-column passes
     int um_gather_cols = 8;  // batched path: more columns than this take the row-gather sparse kernel (env SGB_UMMA_GATHER_COLS)
     int um_min_cols = 3;     // AUTO: batched tcgen05 path from this many columns (two columns: 8.3 ms against 2 x 3.4 ms for the fused
                              // single-RHS kernel at N = 430K; env SGB_UMMA_MIN_COLS; 0 disables)
@@ -1162,22 +1163,27 @@ void launch_sparse_multi(Context &c, ImmaPlan *p, bool by_variant, const double 
         const int32_t *idx = (by_variant ? p->mv_idx : p->ms_idx).get();
         const int grid = c.sm_count * 8;
         c.prof_begin();
-        // passes of W columns: narrower rows keep the transposed block smaller (better L2 hit rate) at the price of re-reading the
-        // index lists; measured best at W = 16 (profiles/r02_multicol_*.json)
-        const int W = p->um_gather_w;
+        // passes of W columns.  Measured at N = 430K, M = 100K (profiles/r02_gather_variants.txt), both gathers of one product:
+        // 30 columns: 2 passes of 16 columns 9.1 ms, 1 pass of 32 columns 10.6 ms, 1 pass of 32 columns with 16-byte loads 7.8 ms;
+        // 12 columns: 16 columns 4.35 ms (16-byte loads 4.45), 32 columns 6.8-9.2 ms
+        const int W = p->um_gather_w ? p->um_gather_w : (ncols > 16 ? 32 : 16);
+        const bool v2 = p->um_gather_v2 >= 0 ? p->um_gather_v2 != 0 : W == 32;
         for (int c0 = 0; c0 < ncols; c0 += W) {
             const int nc = std::min(W, ncols - c0);
             const double *v0 = vec + (size_t)c0 * ldv;
             double *o0 = out + (size_t)c0 * ldo;
             if (W == 32) {
                 transpose_cols_kernel<32><<<(unsigned)((Cn + 256) / 256), 256, 0, st>>>(v0, ldv, nc, Cn, u.vt.get());
-                sparse_rows_gather_kernel<32><<<grid, 256, 0, st>>>(ptr, idx, u.vt.get(), Cn, nc, R, o0, ldo);
+                if (v2) sparse_rows_gather2_kernel<32><<<grid, 256, 0, st>>>(ptr, idx, u.vt.get(), Cn, nc, R, o0, ldo);
+                else sparse_rows_gather_kernel<32><<<grid, 256, 0, st>>>(ptr, idx, u.vt.get(), Cn, nc, R, o0, ldo);
             } else if (W == 16) {
                 transpose_cols_kernel<16><<<(unsigned)((Cn + 256) / 256), 256, 0, st>>>(v0, ldv, nc, Cn, u.vt.get());
-                sparse_rows_gather_kernel<16><<<grid, 256, 0, st>>>(ptr, idx, u.vt.get(), Cn, nc, R, o0, ldo);
+                if (v2) sparse_rows_gather2_kernel<16><<<grid, 256, 0, st>>>(ptr, idx, u.vt.get(), Cn, nc, R, o0, ldo);
+                else sparse_rows_gather_kernel<16><<<grid, 256, 0, st>>>(ptr, idx, u.vt.get(), Cn, nc, R, o0, ldo);
             } else {
                 transpose_cols_kernel<8><<<(unsigned)((Cn + 256) / 256), 256, 0, st>>>(v0, ldv, nc, Cn, u.vt.get());
-                sparse_rows_gather_kernel<8><<<grid, 256, 0, st>>>(ptr, idx, u.vt.get(), Cn, nc, R, o0, ldo);
+                if (v2) sparse_rows_gather2_kernel<8><<<grid, 256, 0, st>>>(ptr, idx, u.vt.get(), Cn, nc, R, o0, ldo);
+                else sparse_rows_gather_kernel<8><<<grid, 256, 0, st>>>(ptr, idx, u.vt.get(), Cn, nc, R, o0, ldo);
             }
             c.stats.n_kernel_launches += 2;
         }
@@ -1578,6 +1584,7 @@ void imma_prepare(Context &c) {
         if (const char *e = getenv("SGB_UMMA_FORK")) p->um_fork = atoi(e);
         if (const char *e = getenv("SGB_UMMA_PAIR")) p->um_pair = atoi(e);
         if (const char *e = getenv("SGB_UMMA_GATHER_COLS")) p->um_gather_cols = atoi(e);
+        if (const char *e = getenv("SGB_UMMA_GATHER_V2")) p->um_gather_v2 = atoi(e) != 0 ? 1 : 0;
         if (const char *e = getenv("SGB_UMMA_GATHER_W")) { const int w = atoi(e); if (w == 8 || w == 16 || w == 32) p->um_gather_w = w; }
         if (const char *e = getenv("SGB_SPARSE_FORK")) p->opt_fork = atoi(e);
         if (const char *e = getenv("SGB_FUSED_FORK")) p->opt_fork_fused = atoi(e);

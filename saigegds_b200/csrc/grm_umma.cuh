@@ -671,6 +671,47 @@ __global__ void __launch_bounds__(256) sparse_rows_gather_kernel(const int64_t *
         if (r < R && col < ncols) out[(size_t)col * ldo + r] = acc;
     }
 }
+// Same walk with 16-byte loads: a sub-warp of W / 2 lanes per row, lane <-> two right-hand sides, so one load instruction of a warp
+// covers 64 / W rows (half the load instructions per byte of the kernel above; env SGB_UMMA_GATHER_V2).
+template <int W>
+__global__ void __launch_bounds__(256) sparse_rows_gather2_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx,
+                                                                  const double *__restrict__ vt, int64_t zero_row, int ncols, int64_t R,
+                                                                  double *__restrict__ out, int64_t ldo) {
+    constexpr int L = W / 2;                          // lanes per row
+    constexpr int RPW = 32 / L;                       // rows per warp
+    constexpr int NB = L < 16 ? L : 16;               // loads in flight per lane
+    const int lane = threadIdx.x & 31, sub = lane / L, cl = lane % L;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const double2 *vcol = reinterpret_cast<const double2 *>(vt) + cl;
+    for (int64_t rb = warp0 * RPW; rb < R; rb += n_warps * RPW) {
+        const int64_t r = rb + sub;
+        int64_t e0 = 0, e1 = 0;
+        if (r < R) { e0 = ptr[r]; e1 = ptr[r + 1]; }
+        int64_t len = e1 - e0, maxlen = len;
+#pragma unroll
+        for (int o = 16; o >= L; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+        double2 acc = make_double2(0.0, 0.0);
+        for (int64_t base = 0; base < maxlen; base += L) {
+            const int64_t me = base + cl;
+            const int64_t my = (me < len) ? (int64_t)idx[e0 + me] : zero_row;     // padding reads the all-zero row: no predicates below
+            const int cnt = (int)min((int64_t)L, maxlen - base);
+            for (int t0 = 0; t0 < cnt; t0 += NB) {
+                double2 v[NB];
+#pragma unroll
+                for (int u = 0; u < NB; u++) {
+                    const int64_t i = __shfl_sync(0xffffffffu, (t0 + u < L) ? my : zero_row, (t0 + u) & (L - 1), L);
+                    v[u] = __ldg(vcol + (size_t)((t0 + u < cnt) ? i : zero_row) * L);
+                }
+#pragma unroll
+                for (int u = 0; u < NB; u++) { acc.x += v[u].x; acc.y += v[u].y; }   // list order: deterministic, same sums as above
+            }
+        }
+        if (r < R) {
+            if (2 * cl < ncols) out[(size_t)(2 * cl) * ldo + r] = acc.x;
+            if (2 * cl + 1 < ncols) out[(size_t)(2 * cl + 1) * ldo + r] = acc.y;
+        }
+    }
+}
 // dst[i][c] = src[c][i] for c < ncols, 0 for ncols <= c < W; row n is the all-zero row.  grid ceil((n + 1) / 256)
 template <int W>
 __global__ void transpose_cols_kernel(const double *__restrict__ src, int64_t ld, int ncols, int64_t n, double *__restrict__ dst) {
