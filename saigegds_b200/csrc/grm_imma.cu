@@ -1174,7 +1174,9 @@ void launch_sparse_multi(Context &c, ImmaPlan *p, bool by_variant, const double 
             double *o0 = out + (size_t)c0 * ldo;
             if (W == 32) {
                 transpose_cols_kernel<32><<<(unsigned)((Cn + 256) / 256), 256, 0, st>>>(v0, ldv, nc, Cn, u.vt.get());
-                if (v2) sparse_rows_gather2_kernel<32><<<grid, 256, 0, st>>>(ptr, idx, u.vt.get(), Cn, nc, R, o0, ldo);
+                // four loads in flight per lane: the gather is bound by the L2's random-row throughput (~14.5 TB/s), not by latency
+                // (4 / 8 / 16 in flight: 7.43 / 7.59 / 7.72 ms for both gathers), and fewer registers keep more warps resident
+                if (v2) sparse_rows_gather2_kernel<32, 4><<<grid, 256, 0, st>>>(ptr, idx, u.vt.get(), Cn, nc, R, o0, ldo);
                 else sparse_rows_gather_kernel<32><<<grid, 256, 0, st>>>(ptr, idx, u.vt.get(), Cn, nc, R, o0, ldo);
             } else if (W == 16) {
                 transpose_cols_kernel<16><<<(unsigned)((Cn + 256) / 256), 256, 0, st>>>(v0, ldv, nc, Cn, u.vt.get());

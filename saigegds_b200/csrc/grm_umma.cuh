@@ -673,13 +673,13 @@ __global__ void __launch_bounds__(256) sparse_rows_gather_kernel(const int64_t *
 }
 // Same walk with 16-byte loads: a sub-warp of W / 2 lanes per row, lane <-> two right-hand sides, so one load instruction of a warp
 // covers 64 / W rows (half the load instructions per byte of the kernel above; env SGB_UMMA_GATHER_V2).
-template <int W>
+template <int W, int NBX = 16>
 __global__ void __launch_bounds__(256) sparse_rows_gather2_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx,
                                                                   const double *__restrict__ vt, int64_t zero_row, int ncols, int64_t R,
                                                                   double *__restrict__ out, int64_t ldo) {
     constexpr int L = W / 2;                          // lanes per row
     constexpr int RPW = 32 / L;                       // rows per warp
-    constexpr int NB = L < 16 ? L : 16;               // loads in flight per lane
+    constexpr int NB = L < NBX ? L : NBX;             // loads in flight per lane
     const int lane = threadIdx.x & 31, sub = lane / L, cl = lane % L;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const double2 *vcol = reinterpret_cast<const double2 *>(vt) + cl;
