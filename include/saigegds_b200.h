@@ -34,7 +34,7 @@ enum {
     SGB_ERR_INVALID = 1,   /* std::invalid_argument in the reference */
     SGB_ERR_CUDA = 2,      /* CUDA runtime / no device */
     SGB_ERR_OVERFLOW = 3,  /* std::overflow_error: "Large variance estimate ...", "Sigma_E = 0 ..." */
-    SGB_ERR_COMM = 4,      /* NCCL */
+    SGB_ERR_COMM = 4,      /* NCCL, or a rank that did not reach a collective within SGB_WAIT_TIMEOUT_MS */
     SGB_ERR_STATE = 5      /* call order (e.g. fit before store) */
 };
 
