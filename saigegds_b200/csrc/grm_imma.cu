@@ -73,6 +73,7 @@ struct ImmaPlan {
     int um_gather_w = 0;     // columns per pass of the row-gather kernel: 8, 16 or 32 (env SGB_UMMA_GATHER_W); 0 = by the column count
     int um_gather_v2 = -1;   // 16-byte loads in the row-gather kernel (env SGB_UMMA_GATHER_V2); -1 = with 32-column passes
     int um_gather_cols = 8;  // batched path: more columns than this take the row-gather sparse kernel (env SGB_UMMA_GATHER_COLS)
+    int um_small_cols = 4;   // batched path: up to this many columns the GEMMs run on mma.sync (imma_small_gemm_kernel; env SGB_UMMA_SMALL_COLS, 0 = never)
     int um_min_cols = 3;     // AUTO: batched tcgen05 path from this many columns (two columns: 8.3 ms against 2 x 3.4 ms for the fused
                              // single-RHS kernel at N = 430K; env SGB_UMMA_MIN_COLS; 0 disables)
     bool use_csr = false;    // env SGB_SPARSE_CSR: the older row-per-thread kernel (comparison only)
@@ -1261,6 +1262,23 @@ void umma_launch(Context &c, ImmaPlan *p, bool pair, bool prof, int64_t rows, in
     (void)p;
 }
 
+// few right-hand sides: the integer GEMM of one phase on mma.sync (imma_small_gemm_kernel); same operands and limb outputs as umma_launch
+void small_gemm_launch(Context &c, const uint8_t *P, size_t pitch, int64_t R, int64_t C, const int8_t *D, int64_t cpad, int ncols,
+                       unsigned long long *out_lo, unsigned long long *out_hi, int64_t ldo) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        SGB_CUDA(cudaFuncSetAttribute(imma_small_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSgSmemBytes));
+        attr_set = true;
+    }
+    const int64_t ksteps = (C + 255) / 256;
+    const int64_t row_ctas = (R + kSgRows - 1) / kSgRows;
+    int split = (int)((ksteps + kSgMaxSteps - 1) / kSgMaxSteps);                       // int32 accumulators
+    split = std::max<int>(split, (int)std::min<int64_t>(ksteps, (8 * c.sm_count + row_ctas - 1) / row_ctas));   // >= ~8 waves of CTAs
+    imma_small_gemm_kernel<<<dim3((unsigned)row_ctas, (unsigned)split), kSgThreads, kSgSmemBytes, c.stream>>>(P, pitch, R, ksteps, split, D, cpad,
+                                                                                                            ncols, out_lo, out_hi, ldo);
+    SGB_CHECK_LAUNCH();
+}
+
 // one pass: ncols <= 32 columns
 void umma_grm_mv_pass(Context &c, ImmaPlan *p, const double *b, double *out, int ncols) {
     ImmaPlan::Umma &u = p->um;
@@ -1304,7 +1322,9 @@ void umma_grm_mv_pass(Context &c, ImmaPlan *p, const double *b, double *out, int
         SGB_CUDA(cudaMemsetAsync(u.prof.get(), 0, sizeof(long long) * 16 * 65536, c.stream));
         a.prof = u.prof.get();
     }
-    umma_launch(c, p, pair, prof, M, ns_a, p->um_pair == 2 ? u.tmap_p128 : u.tmap_p, *umma_digit_map(u, false, pair ? ng / 2 : ng), a);
+    const bool small = ncols <= p->um_small_cols && kUND * ncols <= 8 * kSgNT;      // few columns: mma.sync GEMM (a tcgen05.mma costs its dispatch whatever N)
+    if (small) small_gemm_launch(c, c.packed.get(), c.pitch, M, N, u.db.get(), u.cpad_a, ncols, u.t_lo.get(), u.t_hi.get(), M);
+    else umma_launch(c, p, pair, prof, M, ns_a, p->um_pair == 2 ? u.tmap_p128 : u.tmap_p, *umma_digit_map(u, false, pair ? ng / 2 : ng), a);
     if (prof) {
         // debugging aid: cycle counters of one issuer thread and of one expander warp of the leader CTAs, per OWN stage
         std::vector<long long> h((size_t)16 * 65536);
@@ -1318,7 +1338,7 @@ void umma_grm_mv_pass(Context &c, ImmaPlan *p, const double *b, double *out, int
                  s[4] / ks, s[8] / es, s[9] / es, s[10] / es, s[11] / es, s[12] / es, s[13] / es);
     }
     SGB_CHECK_LAUNCH();
-    c.prof_end("umma_gemm_kernel (phase A)");
+    c.prof_end(small ? "imma_small_gemm_kernel (phase A)" : "umma_gemm_kernel (phase A)");
     if (fork) SGB_CUDA(cudaStreamWaitEvent(c.stream, p->ev_u, 0));
     c.prof_begin();
     const int Gm = (int)std::min<int64_t>(1024, std::max<int64_t>(1, (M + 255) / 256));
@@ -1339,9 +1359,10 @@ void umma_grm_mv_pass(Context &c, ImmaPlan *p, const double *b, double *out, int
     a.out_lo = u.r_lo.get(); a.out_hi = u.r_hi.get(); a.ldo = N;
     const int ns_b = (u.boxes_b + a.boxes_per_split - 1) / a.boxes_per_split;
     c.prof_begin();
-    umma_launch(c, p, pair, false, N, ns_b, p->um_pair == 2 ? u.tmap_pt128 : u.tmap_pt, *umma_digit_map(u, true, pair ? ng / 2 : ng), a);
+    if (small) small_gemm_launch(c, u.pt.get(), u.pitch_t, N, M, u.de.get(), u.cpad_b, ncols, u.r_lo.get(), u.r_hi.get(), N);
+    else umma_launch(c, p, pair, false, N, ns_b, p->um_pair == 2 ? u.tmap_pt128 : u.tmap_pt, *umma_digit_map(u, true, pair ? ng / 2 : ng), a);
     SGB_CHECK_LAUNCH();
-    c.prof_end("umma_gemm_kernel (phase B)");
+    c.prof_end(small ? "imma_small_gemm_kernel (phase B)" : "umma_gemm_kernel (phase B)");
     if (fork) SGB_CUDA(cudaStreamWaitEvent(c.stream, p->ev_corr, 0));
     c.prof_begin();
     umma_combine_kernel<<<dim3((unsigned)((N + 255) / 256), ncols), 256, 0, c.stream>>>(u.r_lo.get(), u.r_hi.get(), N, u.corr.get(), 1, u.scal.get(), out);
@@ -1585,6 +1606,7 @@ void imma_prepare(Context &c) {
         if (const char *e = getenv("SGB_UMMA_MIN_COLS")) { p->um_min_cols = atoi(e); if (p->um_min_cols <= 0) p->um_min_cols = INT_MAX; }
         if (const char *e = getenv("SGB_UMMA_FORK")) p->um_fork = atoi(e);
         if (const char *e = getenv("SGB_UMMA_PAIR")) p->um_pair = atoi(e);
+        if (const char *e = getenv("SGB_UMMA_SMALL_COLS")) p->um_small_cols = atoi(e);
         if (const char *e = getenv("SGB_UMMA_GATHER_COLS")) p->um_gather_cols = atoi(e);
         if (const char *e = getenv("SGB_UMMA_GATHER_V2")) p->um_gather_v2 = atoi(e) != 0 ? 1 : 0;
         if (const char *e = getenv("SGB_UMMA_GATHER_W")) { const int w = atoi(e); if (w == 8 || w == 16 || w == 32) p->um_gather_w = w; }

@@ -503,6 +503,164 @@ __global__ void umma_combine_kernel(const unsigned long long *__restrict__ r_lo,
     out[(size_t)c * N + n] = (unit_e == 0 ? 0.0 : unit_e * r) + H - corr;
 }
 
+// ---- few right-hand sides: the same exact integer GEMM on mma.sync (legacy IMMA) -----------------------------------------------------
+// A tcgen05.mma costs its ~96 clk dispatch whatever N, so with 3-4 right-hand sides (18-24 digit columns of 192) a phase of the
+// kernels above takes 3.5-3.9 ms -- as long as with 30 columns.  mma.sync.m16n8k32 has N = 8: 24 digit columns are three
+// instructions per A fragment, i.e. three times the tensor work of the single-RHS two-pass kernels, which is about their HBM time.
+// Same inputs (row-major 2-bit matrix, digit matrix in the permuted element order) and same outputs (exact 64-bit limbs added with
+// red.add.u64) as umma_gemm_kernel, so prepare / finalise / combine and the results do not change by a bit.
+//   CTA = 8 warps x 2 row-blocks of 16 rows = 256 rows x a contraction range, two CTAs per SM; 2-stage cp.async ring; a stage = 2 K-steps of 64
+//   packed bytes (256 elements) per row + the 24 digit rows of those 512 elements.  Per K-step a warp loads its digit fragments once
+//   (3 n-tiles x 64 B per lane) and uses them for both row-blocks: per row-block and 2-bit plane t four LOP3 (bytes & 3 << 2t, the
+//   products carry 4^t) feed six IMMAs.  A split holds at most 2,048 K-steps (int32 safe).
+#ifndef SGB_SG_WARPS
+#define SGB_SG_WARPS 8
+#endif
+#ifndef SGB_SG_STAGES
+#define SGB_SG_STAGES 2
+#endif
+constexpr int kSgWarps = SGB_SG_WARPS, kSgRB = 2, kSgNT = 3;
+constexpr int kSgThreads = kSgWarps * 32;
+constexpr int kSgRows = kSgWarps * kSgRB * 16;          // 256
+constexpr int kSgStageSteps = 2, kSgStages = SGB_SG_STAGES;
+static_assert((8 * kSgNT) % kSgWarps == 0 && (kSgThreads / 8) % 2 == 0, "copy mapping");
+constexpr int kSgARow = 64 * kSgStageSteps;             // packed bytes per row and stage
+constexpr int kSgDRow = 256 * kSgStageSteps + 16;       // digit bytes per digit row and stage (+ one granule: rows start in different bank groups)
+constexpr int kSgStageBytes = kSgRows * kSgARow + 8 * kSgNT * kSgDRow;
+constexpr int kSgSmemBytes = kSgStages * kSgStageBytes;
+constexpr int kSgMaxSteps = 2048;                       // K-steps per split: 128 terms of at most 48 * 128 per K-step and accumulator
+static_assert(kSgSmemBytes <= 227 * 1024, "small-K GEMM shared memory");
+static_assert(kSgRows * 25 * 4 <= kSgSmemBytes, "epilogue staging");
+
+__global__ void __launch_bounds__(kSgThreads, kSgThreads <= 256 ? 2 : 1) imma_small_gemm_kernel(const uint8_t *__restrict__ P, size_t pitch, int64_t R, int64_t ksteps,
+                                                                        int split, const int8_t *__restrict__ D, int64_t cpad, int ncols,
+                                                                        unsigned long long *__restrict__ out_lo,
+                                                                        unsigned long long *__restrict__ out_hi, int64_t ldo) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tq = lane & 3;
+    const int64_t r0cta = (int64_t)blockIdx.x * kSgRows;
+    const int ks_per = (int)((ksteps + split - 1) / split);
+    const int ks_begin = (int)blockIdx.y * ks_per, ks_end = min((int)ksteps, ks_begin + ks_per);
+    const int n_stage = (ks_end > ks_begin) ? (ks_end - ks_begin + kSgStageSteps - 1) / kSgStageSteps : 0;
+
+    // copies of one stage: per thread 8 granules of packed rows and 3 of digit rows; everything but the K-step is fixed per thread
+    // (row pointers and shared-memory offsets are computed once: the address arithmetic of a naive loop costs more issue slots than
+    // the tensor-core instructions of the stage)
+    const int a_r = tid >> 3, a_gran = tid & 7;
+    unsigned a_row[8];                                     // 32-bit row numbers (a pointer per copy would cost eight more registers)
+#pragma unroll
+    for (int k = 0; k < 8; k++) a_row[k] = (unsigned)min(r0cta + a_r + (kSgThreads / 8) * k, R - 1);
+    const uint8_t *a_base = P + (size_t)(a_gran & 3) * 16;
+    // odd rows: the two K-steps swap halves of the 128-byte line, so that rows g and g + 1 of a fragment load use different banks
+    const unsigned a_dst = smem_u32(smem) + a_r * kSgARow + ((a_gran ^ ((a_r & 1) << 2)) << 4);
+    const int d_n = tid >> 5, d_gran = tid & 31;
+    constexpr int kDCopies = 8 * kSgNT / kSgWarps;
+    const int8_t *d_base = D + (size_t)d_n * cpad + (size_t)(d_gran & 15) * 16;
+    // granule index ^ 2 in the upper half of every 16: lanes tq = 0..3 of one fragment load hit four different bank groups
+    const unsigned d_dst = smem_u32(smem) + kSgRows * kSgARow + d_n * kSgDRow + ((d_gran ^ (((d_gran >> 3) & 1) << 1)) << 4);
+    const int ks_last = (int)ksteps - 1;
+    auto cp16 = [](unsigned dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); };
+    auto issue = [&](int st) {
+        if (st < n_stage) {
+            const unsigned so = (unsigned)(st % kSgStages) * kSgStageBytes;
+            const int ks0 = ks_begin + st * kSgStageSteps;
+            const size_t ka = (size_t)min(ks0 + (a_gran >> 2), ks_last) * 64, kd = (size_t)min(ks0 + (d_gran >> 4), ks_last) * 256;
+#pragma unroll
+            for (int k = 0; k < 8; k++) cp16(a_dst + so + k * (kSgThreads / 8) * kSgARow, a_base + (size_t)a_row[k] * pitch + ka);
+#pragma unroll
+            for (int k = 0; k < kDCopies; k++) cp16(d_dst + so + k * kSgWarps * kSgDRow, d_base + (size_t)(k * kSgWarps) * cpad + kd);
+        }
+        cp_async_commit();
+    };
+
+    // accumulators [row-block][plane pair][n-tile]: pair 0 = planes 0, 1 (products at scale 1), pair 1 = planes 2, 3 (scale 16)
+    int acc[kSgRB][2][kSgNT][4];
+#pragma unroll
+    for (int rb = 0; rb < kSgRB; rb++)
+#pragma unroll
+        for (int pp = 0; pp < 2; pp++)
+#pragma unroll
+            for (int nt = 0; nt < kSgNT; nt++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) acc[rb][pp][nt][q] = 0;
+
+    for (int s = 0; s < kSgStages - 1; s++) issue(s);
+    for (int st = 0; st < n_stage; st++) {
+        cp_async_wait<kSgStages - 2>();
+        __syncthreads();
+        issue(st + kSgStages - 1);
+        const uint8_t *buf = smem + (size_t)(st % kSgStages) * kSgStageBytes;
+        const uint8_t *dbuf = buf + kSgRows * kSgARow;
+        const int ks0 = ks_begin + st * kSgStageSteps;
+#pragma unroll
+        for (int s = 0; s < kSgStageSteps; s++) {
+            if (ks0 + s >= ks_end) break;
+            // digit fragments of this lane: digit row 8 nt + g, granules 4 tq + j of the K-step; word t of granule j = plane t of the
+            // packed bytes 16 tq + 4 j .. + 3.  One IMMA takes the four packed bytes of word j of this lane's rows twice: plane 2 pp in
+            // its first k-half, plane 2 pp + 1 (the word shifted right by two bits, same mask, hence the same scale) in its second --
+            // the B operand is then the adjacent word pair (2 pp, 2 pp + 1) of ONE granule, i.e. a register pair straight out of the
+            // 16-byte load (no moves), and planes 2 pp and 2 pp + 1 share an accumulator
+            uint32_t wa[kSgRB][4], wb[kSgRB][4];
+#pragma unroll
+            for (int rb = 0; rb < kSgRB; rb++) {
+                const int r0 = warp * (kSgRB * 16) + rb * 16 + g;
+                const int gran = (s * 4 + tq) ^ ((r0 & 1) << 2);     // r0 and r0 + 8 have the same parity
+                const uint4 wa4 = *reinterpret_cast<const uint4 *>(buf + r0 * kSgARow + (gran << 4));
+                const uint4 wb4 = *reinterpret_cast<const uint4 *>(buf + (r0 + 8) * kSgARow + (gran << 4));
+                wa[rb][0] = wa4.x; wa[rb][1] = wa4.y; wa[rb][2] = wa4.z; wa[rb][3] = wa4.w;
+                wb[rb][0] = wb4.x; wb[rb][1] = wb4.y; wb[rb][2] = wb4.z; wb[rb][3] = wb4.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                // digit granule j of the three n-tiles (12 registers live at a time), used by both row-blocks
+                uint4 bf[kSgNT];
+                const int gran = s * 16 + 4 * tq + j;
+#pragma unroll
+                for (int nt = 0; nt < kSgNT; nt++)
+                    bf[nt] = *reinterpret_cast<const uint4 *>(dbuf + (nt * 8 + g) * kSgDRow + ((gran ^ (((gran >> 3) & 1) << 1)) << 4));
+#pragma unroll
+                for (int rb = 0; rb < kSgRB; rb++) {
+                    const uint32_t sa = wa[rb][j] >> 2, sb = wb[rb][j] >> 2;
+#pragma unroll
+                    for (int pp = 0; pp < 2; pp++) {
+                        const uint32_t m = pp ? 0x30303030u : 0x03030303u;
+                        const uint32_t a0 = wa[rb][j] & m, a1 = wb[rb][j] & m, a2 = sa & m, a3 = sb & m;
+#pragma unroll
+                        for (int nt = 0; nt < kSgNT; nt++) {
+                            const uint32_t b0 = pp ? bf[nt].z : bf[nt].x, b1 = pp ? bf[nt].w : bf[nt].y;
+                            imma_nv(acc[rb][pp][nt], a0, a1, a2, a3, b0, b1);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    // epilogue: plane factors removed (exact shifts), the 24 digit-column sums of a row through shared memory ([row][25] ints), then
+    // one lane per (row, right-hand side, limb): sum_k S[3 limb + k] 256^k added to the limb plane
+    int *stg = reinterpret_cast<int *>(smem);
+#pragma unroll
+    for (int rb = 0; rb < kSgRB; rb++)
+#pragma unroll
+        for (int nt = 0; nt < kSgNT; nt++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int v = acc[rb][0][nt][q] + (acc[rb][1][nt][q] >> 4);
+                const int row = warp * (kSgRB * 16) + rb * 16 + g + (q >> 1) * 8, n = nt * 8 + 2 * tq + (q & 1);
+                stg[row * 25 + n] = v;
+            }
+    __syncthreads();
+    for (int i = tid; i < kSgRows * 8; i += kSgThreads) {
+        const int row = i >> 3, slot = i & 7, cidx = slot >> 1, limb = slot & 1;
+        const int64_t rr = r0cta + row;
+        if (rr >= R || cidx >= ncols || n_stage == 0) continue;
+        const int *sp = stg + row * 25 + cidx * kUND + 3 * limb;
+        const long long v = (long long)sp[0] + 256ll * sp[1] + 65536ll * sp[2];
+        red_add_u64((limb ? out_hi : out_lo) + (size_t)cidx * ldo + rr, (unsigned long long)v);
+    }
+}
+
 // ---- multi-column variant of sparse_ell_sum_kernel: part[c][t][r] = sum over the entries of row r in tile t of vec[c][column] ----
 // Same lane-interleaved index blocks; an item is 16 groups (512 rows) so that C vector tiles and two index stages fit in
 // shared memory; every index is fetched once per C gathers.
