@@ -74,8 +74,8 @@ struct ImmaPlan {
     int um_gather_v2 = -1;   // 16-byte loads in the row-gather kernel (env SGB_UMMA_GATHER_V2); -1 = with 32-column passes
     int um_gather_cols = 8;  // batched path: more columns than this take the row-gather sparse kernel (env SGB_UMMA_GATHER_COLS)
     int um_small_cols = 4;   // batched path: up to this many columns the GEMMs run on mma.sync (imma_small_gemm_kernel; env SGB_UMMA_SMALL_COLS, 0 = never)
-    int um_min_cols = 3;     // AUTO: batched tcgen05 path from this many columns (two columns: 8.3 ms against 2 x 3.4 ms for the fused
-                             // single-RHS kernel at N = 430K; env SGB_UMMA_MIN_COLS; 0 disables)
+    int um_min_cols = 2;     // AUTO: batched path from this many columns (two columns: 5.3 ms with the mma.sync GEMMs against 2 x 3.4 ms
+                             // for the fused single-RHS kernel and 8.3 ms on tcgen05 at N = 430K; env SGB_UMMA_MIN_COLS; 0 disables)
     bool use_csr = false;    // env SGB_SPARSE_CSR: the older row-per-thread kernel (comparison only)
     int n_stiles = 0, n_vtiles = 0;
     int opt_fork = 1, opt_fork_fused = -1, opt_grid_mult = 2, opt_stages = 3;   // tuning knobs (env: SGB_SPARSE_FORK, SGB_SPARSE_GRID_MULT, SGB_DOTS_STAGES)
@@ -1267,15 +1267,34 @@ void small_gemm_launch(Context &c, const uint8_t *P, size_t pitch, int64_t R, in
                        unsigned long long *out_lo, unsigned long long *out_hi, int64_t ldo) {
     static bool attr_set = false;
     if (!attr_set) {
-        SGB_CUDA(cudaFuncSetAttribute(imma_small_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSgSmemBytes));
+        SGB_CUDA(cudaFuncSetAttribute(imma_small_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSgSmemBytes));
+        SGB_CUDA(cudaFuncSetAttribute(imma_small_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSgSmemBytes));
+        SGB_CUDA(cudaFuncSetAttribute(imma_small_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSgSmemBytes));
         attr_set = true;
     }
     const int64_t ksteps = (C + 255) / 256;
     const int64_t row_ctas = (R + kSgRows - 1) / kSgRows;
-    int split = (int)((ksteps + kSgMaxSteps - 1) / kSgMaxSteps);                       // int32 accumulators
-    split = std::max<int>(split, (int)std::min<int64_t>(ksteps, (8 * c.sm_count + row_ctas - 1) / row_ctas));   // >= ~8 waves of CTAs
-    imma_small_gemm_kernel<<<dim3((unsigned)row_ctas, (unsigned)split), kSgThreads, kSgSmemBytes, c.stream>>>(P, pitch, R, ksteps, split, D, cpad,
-                                                                                                            ncols, out_lo, out_hi, ldo);
+    // split of the contraction range: all CTAs cost the same, so what counts is the number of waves (two CTAs per SM) times the length
+    // of a CTA (its K-steps + ~8 K-steps of pipeline fill and epilogue); at least what keeps the int32 accumulators safe
+    static int per_sm = 0;
+    if (!per_sm) {
+        SGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, imma_small_gemm_kernel<3>, kSgThreads, kSgSmemBytes));
+        per_sm = std::max(per_sm, 1);
+    }
+    const int64_t slots = (int64_t)per_sm * c.sm_count;
+    const int s_min = (int)((ksteps + kSgMaxSteps - 1) / kSgMaxSteps);
+    int split = s_min;
+    double best = 1e300;
+    for (int sp = s_min; sp <= 32 && sp <= std::max<int64_t>(s_min, ksteps / 8); sp++) {
+        const int64_t ctas = row_ctas * sp, waves = (ctas + slots - 1) / slots;
+        const double cost = (double)waves * ((double)((ksteps + sp - 1) / sp) + 8.0);
+        if (cost < best * 0.99) { best = cost; split = sp; }
+    }
+    const dim3 grid((unsigned)row_ctas, (unsigned)split);
+    const int nt = (kUND * ncols + 7) / 8;
+    if (nt == 1) imma_small_gemm_kernel<1><<<grid, kSgThreads, kSgSmemBytes, c.stream>>>(P, pitch, R, ksteps, split, D, cpad, ncols, out_lo, out_hi, ldo);
+    else if (nt == 2) imma_small_gemm_kernel<2><<<grid, kSgThreads, kSgSmemBytes, c.stream>>>(P, pitch, R, ksteps, split, D, cpad, ncols, out_lo, out_hi, ldo);
+    else imma_small_gemm_kernel<3><<<grid, kSgThreads, kSgSmemBytes, c.stream>>>(P, pitch, R, ksteps, split, D, cpad, ncols, out_lo, out_hi, ldo);
     SGB_CHECK_LAUNCH();
 }
 

@@ -523,7 +523,7 @@ constexpr int kSgWarps = SGB_SG_WARPS, kSgRB = 2, kSgNT = 3;
 constexpr int kSgThreads = kSgWarps * 32;
 constexpr int kSgRows = kSgWarps * kSgRB * 16;          // 256
 constexpr int kSgStageSteps = 2, kSgStages = SGB_SG_STAGES;
-static_assert((8 * kSgNT) % kSgWarps == 0 && (kSgThreads / 8) % 2 == 0, "copy mapping");
+static_assert(kSgWarps == 8 && (kSgThreads / 8) % 2 == 0, "copy mapping: one digit row per warp and n-tile");
 constexpr int kSgARow = 64 * kSgStageSteps;             // packed bytes per row and stage
 constexpr int kSgDRow = 256 * kSgStageSteps + 16;       // digit bytes per digit row and stage (+ one granule: rows start in different bank groups)
 constexpr int kSgStageBytes = kSgRows * kSgARow + 8 * kSgNT * kSgDRow;
@@ -532,6 +532,7 @@ constexpr int kSgMaxSteps = 2048;                       // K-steps per split: 12
 static_assert(kSgSmemBytes <= 227 * 1024, "small-K GEMM shared memory");
 static_assert(kSgRows * 25 * 4 <= kSgSmemBytes, "epilogue staging");
 
+template <int NT>   // n-tiles of eight digit columns: 6 K <= 8 NT
 __global__ void __launch_bounds__(kSgThreads, kSgThreads <= 256 ? 2 : 1) imma_small_gemm_kernel(const uint8_t *__restrict__ P, size_t pitch, int64_t R, int64_t ksteps,
                                                                         int split, const int8_t *__restrict__ D, int64_t cpad, int ncols,
                                                                         unsigned long long *__restrict__ out_lo,
@@ -554,7 +555,7 @@ __global__ void __launch_bounds__(kSgThreads, kSgThreads <= 256 ? 2 : 1) imma_sm
     // odd rows: the two K-steps swap halves of the 128-byte line, so that rows g and g + 1 of a fragment load use different banks
     const unsigned a_dst = smem_u32(smem) + a_r * kSgARow + ((a_gran ^ ((a_r & 1) << 2)) << 4);
     const int d_n = tid >> 5, d_gran = tid & 31;
-    constexpr int kDCopies = 8 * kSgNT / kSgWarps;
+    constexpr int kDCopies = 8 * NT / kSgWarps;
     const int8_t *d_base = D + (size_t)d_n * cpad + (size_t)(d_gran & 15) * 16;
     // granule index ^ 2 in the upper half of every 16: lanes tq = 0..3 of one fragment load hit four different bank groups
     const unsigned d_dst = smem_u32(smem) + kSgRows * kSgARow + d_n * kSgDRow + ((d_gran ^ (((d_gran >> 3) & 1) << 1)) << 4);
@@ -574,13 +575,13 @@ __global__ void __launch_bounds__(kSgThreads, kSgThreads <= 256 ? 2 : 1) imma_sm
     };
 
     // accumulators [row-block][plane pair][n-tile]: pair 0 = planes 0, 1 (products at scale 1), pair 1 = planes 2, 3 (scale 16)
-    int acc[kSgRB][2][kSgNT][4];
+    int acc[kSgRB][2][NT][4];
 #pragma unroll
     for (int rb = 0; rb < kSgRB; rb++)
 #pragma unroll
         for (int pp = 0; pp < 2; pp++)
 #pragma unroll
-            for (int nt = 0; nt < kSgNT; nt++)
+            for (int nt = 0; nt < NT; nt++)
 #pragma unroll
                 for (int q = 0; q < 4; q++) acc[rb][pp][nt][q] = 0;
 
@@ -613,10 +614,10 @@ __global__ void __launch_bounds__(kSgThreads, kSgThreads <= 256 ? 2 : 1) imma_sm
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 // digit granule j of the three n-tiles (12 registers live at a time), used by both row-blocks
-                uint4 bf[kSgNT];
+                uint4 bf[NT];
                 const int gran = s * 16 + 4 * tq + j;
 #pragma unroll
-                for (int nt = 0; nt < kSgNT; nt++)
+                for (int nt = 0; nt < NT; nt++)
                     bf[nt] = *reinterpret_cast<const uint4 *>(dbuf + (nt * 8 + g) * kSgDRow + ((gran ^ (((gran >> 3) & 1) << 1)) << 4));
 #pragma unroll
                 for (int rb = 0; rb < kSgRB; rb++) {
@@ -626,7 +627,7 @@ __global__ void __launch_bounds__(kSgThreads, kSgThreads <= 256 ? 2 : 1) imma_sm
                         const uint32_t m = pp ? 0x30303030u : 0x03030303u;
                         const uint32_t a0 = wa[rb][j] & m, a1 = wb[rb][j] & m, a2 = sa & m, a3 = sb & m;
 #pragma unroll
-                        for (int nt = 0; nt < kSgNT; nt++) {
+                        for (int nt = 0; nt < NT; nt++) {
                             const uint32_t b0 = pp ? bf[nt].z : bf[nt].x, b1 = pp ? bf[nt].w : bf[nt].y;
                             imma_nv(acc[rb][pp][nt], a0, a1, a2, a3, b0, b1);
                         }
@@ -643,7 +644,7 @@ __global__ void __launch_bounds__(kSgThreads, kSgThreads <= 256 ? 2 : 1) imma_sm
 #pragma unroll
     for (int rb = 0; rb < kSgRB; rb++)
 #pragma unroll
-        for (int nt = 0; nt < kSgNT; nt++)
+        for (int nt = 0; nt < NT; nt++)
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const int v = acc[rb][0][nt][q] + (acc[rb][1][nt][q] >> 4);
