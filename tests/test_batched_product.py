@@ -55,6 +55,9 @@ def test_batched_columns_do_not_depend_on_the_batch(gpu, fx):
     part = gpu.get_crossprod_b_grm(B[:, 7:12])
     assert np.array_equal(full[:, 7:12], part)
     assert np.array_equal(full, gpu.get_crossprod_b_grm(B))            # and bit-reproducible
+    # two to four columns: the GEMMs run on mma.sync (imma_small_gemm_kernel<NT>) and produce the same limbs as tcgen05
+    for k0, k in ((0, 2), (5, 3), (20, 4)):
+        assert np.array_equal(full[:, k0:k0 + k], gpu.get_crossprod_b_grm(B[:, k0:k0 + k])), k
     gpu.set_kernel("umma")
     try:
         assert np.array_equal(full[:, 3], gpu.get_crossprod_b_grm(B[:, 3]))
@@ -76,11 +79,15 @@ def test_batched_ragged_shapes(gpu, n_samp, n_var, missing):
     o = Oracle()
     o.store_2b_geno(packed, n_samp)
     gpu.saige_store_2b_geno(packed, n_samp)
-    B = rng.standard_normal((n_samp, 3))
-    got = gpu.get_crossprod_b_grm(B)
-    for c in range(3):
+    B = rng.standard_normal((n_samp, 6))
+    got = gpu.get_crossprod_b_grm(B)                       # six columns: tcgen05
+    for c in range(6):
         want = o.grm_mv(B[:, c])
         assert np.max(np.abs(got[:, c] - want)) <= PROD_TOL * max(np.max(np.abs(want)), 1e-300) + 1e-300
+    # two, three and four columns: mma.sync GEMMs, same limbs
+    assert np.array_equal(gpu.get_crossprod_b_grm(B[:, :3]), got[:, :3])
+    assert np.array_equal(gpu.get_crossprod_b_grm(B[:, 2:6]), got[:, 2:6])
+    assert np.array_equal(gpu.get_crossprod_b_grm(B[:, 4:6]), got[:, 4:6])
 
 
 def test_batched_equals_single_rhs_kernels_at_scale(gpu):
@@ -147,6 +154,14 @@ def test_full_width_kernels_match_oracle(gpu, m):
         assert relinf(out[:, 0], want) < PROD_TOL
         for c in (1, 2):
             assert relinf(out[:, c], o.grm_mv(B[:, c])) < PROD_TOL, c
+        # three columns run the integer GEMMs on mma.sync (imma_small_gemm_kernel), six on tcgen05: both against the oracle at this
+        # width, and the shared columns bit for bit (same limbs)
+        B6 = np.column_stack([B, rng.standard_normal((n, 3))])
+        out6 = gpu.get_crossprod_b_grm(B6)
+        assert np.array_equal(out6[:, :3], out)
+        assert relinf(out6[:, 0], want) < PROD_TOL
+        assert relinf(out6[:, 5], o.grm_mv(B6[:, 5])) < PROD_TOL
+        assert np.array_equal(gpu.get_crossprod_b_grm(B6[:, 4:6]), out6[:, 4:6])      # two columns: two n-tiles
     finally:
         gpu.set_kernel("auto")
         gpu.store_synthetic(1024, 64)
