@@ -289,6 +289,9 @@ void peer_setup(Context &c, size_t count) {
     P.tried = true;
     const int R = c.world;
     int ok = (R <= kPeerMax && api().AllGather != nullptr && getenv("SGB_NO_PEER_ALLREDUCE") == nullptr) ? 1 : 0;
+    // Measured on one NVSwitch node (same box, alternating runs, profiles/r02_peer_vs_nccl_ab.txt): 2 ranks +1 %, 8 ranks +4.0 % over
+    // combine + ncclAllReduce, 4 ranks -1 % (one-shot and two-shot alike): three and four ranks stay on NCCL unless SGB_PEER_FORCE=1
+    if ((R == 3 || R == 4) && getenv("SGB_PEER_FORCE") == nullptr) ok = 0;
     const size_t cap = (count + 31) / 32 * 32, bytes = 256 + 2 * cap * sizeof(double);
     PeerRecord mine{};
     if (ok) {
@@ -352,7 +355,10 @@ void peer_setup(Context &c, size_t count) {
         SGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peer_allreduce_kernel, kPeerThreads, 0));
         P.blocks = std::max(1, sms * std::min(per_sm, 1));
     }
-    P.one_shot = (R == 2) && getenv("SGB_PEER_TWO_SHOT") == nullptr;
+    // one-shot (every rank sums all send buffers itself) up to this many ranks, reduce-scatter + all-gather above
+    int one_shot_max = 2;
+    if (const char *e = getenv("SGB_PEER_ONE_SHOT_MAX")) one_shot_max = atoi(e);
+    P.one_shot = (R <= one_shot_max) && getenv("SGB_PEER_TWO_SHOT") == nullptr;
     P.cap = cap;
     P.ready = true;
 }
