@@ -209,10 +209,15 @@ __global__ void __launch_bounds__(kFThreads, 1) imma_fused_kernel(const __grid_c
             int x[8];
 #pragma unroll
             for (int l = 0; l < 8; l++) x[l] = 0;
+            // a lane owns 32 contiguous bytes; lanes 4..7 of every eight read their second 16 bytes first, so that the eight lanes of
+            // a quarter-warp hit eight different bank groups (in lane order these loads were 2-way conflicts: 29 M excess wavefronts
+            // per product, profiles/r02_ncu_fused_summary.json)
+            const int sel = (lane >> 2) & 1;
 #pragma unroll
             for (int w = 0; w < kFComputeWarps; w++) {
-                const int4 v0 = *reinterpret_cast<const int4 *>(&S.part[a][w][lane * 8]);
-                const int4 v1 = *reinterpret_cast<const int4 *>(&S.part[a][w][lane * 8 + 4]);
+                const int4 va = *reinterpret_cast<const int4 *>(&S.part[a][w][lane * 8 + 4 * sel]);
+                const int4 vb = *reinterpret_cast<const int4 *>(&S.part[a][w][lane * 8 + 4 * (sel ^ 1)]);
+                const int4 v0 = sel ? vb : va, v1 = sel ? va : vb;
                 x[0] += v0.x; x[1] += v0.y; x[2] += v0.z; x[3] += v0.w;
                 x[4] += v1.x; x[5] += v1.y; x[6] += v1.z; x[7] += v1.w;
             }
