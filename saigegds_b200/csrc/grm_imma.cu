@@ -73,6 +73,8 @@ struct ImmaPlan {
     int um_gather_w = 0;     // columns per pass of the row-gather kernel: 8, 16 or 32 (env SGB_UMMA_GATHER_W); 0 = by the column count
     int um_gather_v2 = -1;   // 16-byte loads in the row-gather kernel (env SGB_UMMA_GATHER_V2); -1 = with 32-column passes
     int um_gather_cols = 8;  // batched path: more columns than this take the row-gather sparse kernel (env SGB_UMMA_GATHER_COLS)
+    bool sg_attr_set = false;   // imma_small_gemm_kernel: shared-memory attribute set / resident CTAs per SM on this device
+    int sg_per_sm = 0;
     int um_small_cols = 4;   // batched path: up to this many columns the GEMMs run on mma.sync (imma_small_gemm_kernel; env SGB_UMMA_SMALL_COLS, 0 = never)
     int um_min_cols = 2;     // AUTO: batched path from this many columns (two columns: 5.3 ms with the mma.sync GEMMs against 2 x 3.4 ms
                              // for the fused single-RHS kernel and 8.3 ms on tcgen05 at N = 430K; env SGB_UMMA_MIN_COLS; 0 disables)
@@ -1263,9 +1265,10 @@ void umma_launch(Context &c, ImmaPlan *p, bool pair, bool prof, int64_t rows, in
 }
 
 // few right-hand sides: the integer GEMM of one phase on mma.sync (imma_small_gemm_kernel); same operands and limb outputs as umma_launch
-void small_gemm_launch(Context &c, const uint8_t *P, size_t pitch, int64_t R, int64_t C, const int8_t *D, int64_t cpad, int ncols,
+void small_gemm_launch(Context &c, ImmaPlan *p, const uint8_t *P, size_t pitch, int64_t R, int64_t C, const int8_t *D, int64_t cpad, int ncols,
                        unsigned long long *out_lo, unsigned long long *out_hi, int64_t ldo) {
-    static bool attr_set = false;
+    bool &attr_set = p->sg_attr_set;          // per plan = per context / device (function attributes are per device)
+    int &per_sm = p->sg_per_sm;
     if (!attr_set) {
         SGB_CUDA(cudaFuncSetAttribute(imma_small_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSgSmemBytes));
         SGB_CUDA(cudaFuncSetAttribute(imma_small_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSgSmemBytes));
@@ -1276,7 +1279,6 @@ void small_gemm_launch(Context &c, const uint8_t *P, size_t pitch, int64_t R, in
     const int64_t row_ctas = (R + kSgRows - 1) / kSgRows;
     // split of the contraction range: all CTAs cost the same, so what counts is the number of waves (two CTAs per SM) times the length
     // of a CTA (its K-steps + ~8 K-steps of pipeline fill and epilogue); at least what keeps the int32 accumulators safe
-    static int per_sm = 0;
     if (!per_sm) {
         SGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, imma_small_gemm_kernel<3>, kSgThreads, kSgSmemBytes));
         per_sm = std::max(per_sm, 1);
@@ -1342,7 +1344,7 @@ void umma_grm_mv_pass(Context &c, ImmaPlan *p, const double *b, double *out, int
         a.prof = u.prof.get();
     }
     const bool small = ncols <= p->um_small_cols && kUND * ncols <= 8 * kSgNT;      // few columns: mma.sync GEMM (a tcgen05.mma costs its dispatch whatever N)
-    if (small) small_gemm_launch(c, c.packed.get(), c.pitch, M, N, u.db.get(), u.cpad_a, ncols, u.t_lo.get(), u.t_hi.get(), M);
+    if (small) small_gemm_launch(c, p, c.packed.get(), c.pitch, M, N, u.db.get(), u.cpad_a, ncols, u.t_lo.get(), u.t_hi.get(), M);
     else umma_launch(c, p, pair, prof, M, ns_a, p->um_pair == 2 ? u.tmap_p128 : u.tmap_p, *umma_digit_map(u, false, pair ? ng / 2 : ng), a);
     if (prof) {
         // debugging aid: cycle counters of one issuer thread and of one expander warp of the leader CTAs, per OWN stage
@@ -1378,7 +1380,7 @@ void umma_grm_mv_pass(Context &c, ImmaPlan *p, const double *b, double *out, int
     a.out_lo = u.r_lo.get(); a.out_hi = u.r_hi.get(); a.ldo = N;
     const int ns_b = (u.boxes_b + a.boxes_per_split - 1) / a.boxes_per_split;
     c.prof_begin();
-    if (small) small_gemm_launch(c, u.pt.get(), u.pitch_t, N, M, u.de.get(), u.cpad_b, ncols, u.r_lo.get(), u.r_hi.get(), N);
+    if (small) small_gemm_launch(c, p, u.pt.get(), u.pitch_t, N, M, u.de.get(), u.cpad_b, ncols, u.r_lo.get(), u.r_hi.get(), N);
     else umma_launch(c, p, pair, false, N, ns_b, p->um_pair == 2 ? u.tmap_pt128 : u.tmap_pt, *umma_digit_map(u, true, pair ? ng / 2 : ng), a);
     SGB_CHECK_LAUNCH();
     c.prof_end(small ? "imma_small_gemm_kernel (phase B)" : "umma_gemm_kernel (phase B)");
@@ -1415,11 +1417,8 @@ void umma_class_sums(Context &c, const uint8_t *packed, size_t pitch, int64_t ro
                      int amode, unsigned long long *out_lo, unsigned long long *out_hi, int *err_dev) {
     if (pitch % 128 != 0 || (int64_t)pitch * 4 > cpad || ((uintptr_t)packed & 127) != 0)
         throw Error(SGB_ERR_INVALID, "umma_class_sums: the packed block needs a 128-byte aligned base and pitch");
-    static bool attr_set = false;
-    if (!attr_set) {
-        SGB_CUDA(cudaFuncSetAttribute(umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes));
-        attr_set = true;
-    }
+    // per call: function attributes are per device, and a process may hold contexts on several devices (microseconds next to the kernel)
+    SGB_CUDA(cudaFuncSetAttribute(umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes));
     const int ng = ((kUND * ncols + 31) / 32) * 32;
     CUtensorMap tp, td;
     CUresult r = encode_tmap_2d(&tp, packed, pitch, (uint64_t)rows, pitch, kUBoxBytes, kPRows, CU_TENSOR_MAP_SWIZZLE_128B);
