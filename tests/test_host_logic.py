@@ -163,3 +163,31 @@ def test_collinear_covariates_are_dropped_like_lm_does():
     X = np.column_stack([X, 2 * X[:, 1] - X[:, 0], rng.standard_normal(50), np.zeros(50), X[:, 2] * (1 + 1e-12)])
     assert rsetup.independent_columns(X).tolist() == [0, 1, 2, 4]
     assert rsetup.independent_columns(X[:, :3]).tolist() == [0, 1, 2]
+
+
+def test_hot_kernels_hold_the_instructions_the_design_claims():
+    """SASS of the in-tree library (cuobjdump, no GPU needed): tcgen05 / TMA / tensor-memory instructions in the batched kernel,
+    mma.sync + TMA in the fused single-RHS kernel, mma.sync + cp.async in the small-K GEMM, system-scope loads in the peer-memory
+    all-reduce -- the mnemonics profiles/r02_sass_opcounts.txt lists."""
+    import shutil
+    if shutil.which("cuobjdump") is None or shutil.which("cu++filt") is None:
+        pytest.skip("no cuobjdump in this environment")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_opcounts
+    counts, _ = sass_opcounts.kernel_counts()
+
+    def of(fragment):
+        hits = [c for name, c in counts.items() if fragment in name]
+        assert hits, fragment
+        return hits
+
+    for c in of("umma_pair_kernel"):
+        assert c["UTCIMMA.2CTA"] >= 1 and c["UTCBAR.2CTA.MULTICAST"] >= 1 and c["LDTM"] >= 1 and c["STTM"] >= 1 and c["UTMALDG"] >= 1
+    for c in of("umma_gemm_kernel"):
+        assert c["UTCIMMA"] + c["UTCIMMA.2CTA"] >= 1 and c["UTMALDG"] >= 1 and c["LDTM"] >= 1
+    for c in of("imma_fused_kernel"):
+        assert c["IMMA"] >= 48 and c["UTMALDG"] >= 1 and c["LDSM"] >= 12 and c["USETMAXREG"] == 2
+    for c in of("imma_small_gemm_kernel"):
+        assert c["IMMA"] >= 32 and c["LDGSTS"] >= 1
+    for c in of("peer_allreduce_kernel"):
+        assert c["LDG.SYS"] >= 1 and c["STG.SYS"] >= 1

@@ -27,7 +27,13 @@ def classify(op):
     return base
 
 
-def main():
+def kernel_counts():
+    """{demangled kernel name: Counter of classified mnemonics}, total instruction counts"""
+    counts, total, names, dem = _scan()
+    return {d: counts[n] for n, d in zip(names, dem)}, {d: total[n] for n, d in zip(names, dem)}
+
+
+def _scan():
     sass = subprocess.run(["cuobjdump", "-sass", SO], capture_output=True, text=True, check=True).stdout
     counts, total, name = {}, {}, None
     for line in sass.splitlines():
@@ -43,6 +49,11 @@ def main():
             counts[name][classify(m.group(1))] += 1
     names = list(counts)
     dem = subprocess.run(["cu++filt"], input="\n".join(names), capture_output=True, text=True).stdout.splitlines()
+    return counts, total, names, dem
+
+
+def main():
+    counts, total, names, dem = _scan()
     print("SASS op counts (cuobjdump -sass saigegds_b200/libsaigegds_b200.so, nvcc 12.9, -gencode arch=compute_100a,code=sm_100a); tools/sass_opcounts.py")
     print("tcgen05.mma -> UTCIMMA, tcgen05.commit -> UTCBAR, tcgen05.alloc -> UTCATOMSWS, tcgen05.ld/st -> LDTM/STTM, cp.async.bulk.tensor -> UTMALDG, "
           "cp.async.bulk -> UBLKCP,\nmma.sync u8/s8 -> IMMA, ldmatrix -> LDSM, mbarrier -> SYNCS, setmaxnreg -> USETMAXREG, cp.async -> LDGSTS, "
