@@ -569,6 +569,7 @@ void launch_tensor(Context &c, ScoreState &s, const uint8_t *packed, size_t pitc
 
 void launch_candidates(Context &c, ScoreState &s, const PackedSrc &src, int64_t n_cand, int64_t n_var) {
     const int grid = (int)std::min<int64_t>(n_cand, s.grid_spa);
+    s.spa.ensure((size_t)grid * 2 * s.M.n);                          // saddle-point scratch of the blocks of this launch
     SGB_CUDA(cudaMemsetAsync(s.counter.get(), 0, sizeof(unsigned long long), c.stream));
     c.prof_begin();
     const int K = s.M.K;
@@ -589,6 +590,7 @@ void launch_candidates(Context &c, ScoreState &s, const PackedSrc &src, int64_t 
 template <class Src>
 void launch_per_variant(Context &c, ScoreState &s, const Src &src, int64_t n_items, const int32_t *list) {
     const int grid = (int)std::min<int64_t>(n_items, s.grid);
+    if (s.M.trait == 0) s.spa.ensure((size_t)grid * 2 * s.M.n);      // saddle-point scratch of the blocks of this launch
     SGB_CUDA(cudaMemsetAsync(s.counter.get(), 0, sizeof(unsigned long long), c.stream));
     c.prof_begin();
     const int K = s.M.K;
@@ -826,7 +828,8 @@ void score_init(Context &c, const sgb_score_model *m, double maf, double mac, do
     s->grid_spa = c.sm_count * 2;   // blocks of spa_candidate_kernel (512 threads), scratch rows [0, grid_spa) of `spa`
     // saddle-point scratch (2 n doubles per block of the candidate kernel): binary traits only -- a quantitative trait never
     // takes the saddle-point branch (saige_main.cpp:322-350)
-    if (m->trait == 0) s->spa.ensure((size_t)s->grid * 2 * n);
+    // -- it is allocated by the kernel launches below for the blocks they really start (2.0 GB at n = 430K for the candidate kernel of
+    // the tensor path, nothing for scans without candidates)
     s->counter.ensure(1);
     score::Model &M = s->M;
     M.trait = m->trait; M.n = m->n; M.K = m->K; M.tau0 = m->tau[0];
